@@ -1,0 +1,232 @@
+"""ctypes harness shared by the tests, bench.py's CPU legs and __graft_entry__.smoke().
+
+Three libraries are wrapped behind the same small Python interface:
+  * Ref      -- the UNMODIFIED reference compiled into oracle/_ref/libicer_ref{,15}.so (oracle/Makefile)
+  * Oracle   -- our plain-C restatement, oracle/liboracle.so
+  * (the product library is wrapped in icer_compression_b200/, not here)
+
+Nothing in this file reads /root/reference at run time.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+OK, OVERFLOW, BUF_SMALL, TOO_MANY_SEGMENTS, TOO_MANY_STAGES, QUOTA = 0, -1, -2, -3, -4, -5
+
+FILTERS = dict(A=0, B=1, C=2, D=3, E=4, F=5, Q=6)
+
+
+class _OutBuf(C.Structure):  # icer_output_data_buf_typedef, lib_icer/inc/icer.h:307-312
+    _fields_ = [("size_used", C.c_size_t), ("size_allocated", C.c_size_t),
+                ("data_start", C.POINTER(C.c_uint8)), ("rearrange_start", C.POINTER(C.c_uint8))]
+
+
+def _u16p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint16))
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+class Ref:
+    """The compiled reference.  planes15=True loads the 7-stage / 15-plane build (BASELINE config 4)."""
+
+    def __init__(self, planes15=False):
+        name = "libicer_ref15.so" if planes15 else "libicer_ref.so"
+        path = os.path.join(ORACLE_DIR, "_ref", name)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle ref` where /root/reference exists)")
+        self.lib = C.CDLL(path)
+        self.planes = 15 if planes15 else 9
+        self.max_stages = 7 if planes15 else 6
+        self.lib.icer_init()
+        L = self.lib
+        L.icer_init_output_struct.argtypes = [C.POINTER(_OutBuf), C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t]
+        L.icer_compress_image_uint16.argtypes = [C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_uint8, C.c_int,
+                                                 C.c_uint8, C.POINTER(_OutBuf)]
+        L.icer_compress_image_yuv_uint16.argtypes = [C.POINTER(C.c_uint16)] * 3 + [C.c_size_t, C.c_size_t, C.c_uint8,
+                                                                                    C.c_int, C.c_uint8, C.POINTER(_OutBuf)]
+        L.icer_decompress_image_uint16.argtypes = [C.POINTER(C.c_uint16), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                                   C.c_size_t, C.POINTER(C.c_uint8), C.c_size_t, C.c_uint8, C.c_int,
+                                                   C.c_uint8]
+        L.icer_decompress_image_yuv_uint16.argtypes = [C.POINTER(C.c_uint16)] * 3 + [
+            C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(C.c_uint8), C.c_size_t, C.c_uint8,
+            C.c_int, C.c_uint8]
+        L.icer_wavelet_transform_stages_uint16.argtypes = [C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_uint8, C.c_int]
+        L.icer_inverse_wavelet_transform_stages_uint16.argtypes = L.icer_wavelet_transform_stages_uint16.argtypes
+        L.icer_wavelet_transform_1d_uint16.argtypes = [C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_int]
+        L.icer_inverse_wavelet_transform_1d_uint16.argtypes = L.icer_wavelet_transform_1d_uint16.argtypes
+        L.icer_compute_bin.argtypes = [C.c_uint32, C.c_uint32]
+
+    # ---- whole image -------------------------------------------------------------------------------
+    def compress(self, planes_in, stages, filt, segments, quota):
+        """planes_in: list of 1 or 3 uint16 arrays [h, w].  Returns dict(rc, size_used, stream, prio, coefs)."""
+        imgs = [np.ascontiguousarray(p, dtype=np.uint16).copy() for p in planes_in]
+        h, w = imgs[0].shape
+        buf = np.zeros(2 * quota + 64, dtype=np.uint8)
+        ob = _OutBuf()
+        rc0 = self.lib.icer_init_output_struct(C.byref(ob), _u8p(buf), 2 * quota, quota)
+        assert rc0 == 0
+        if len(imgs) == 1:
+            rc = self.lib.icer_compress_image_uint16(_u16p(imgs[0]), w, h, stages, filt, segments, C.byref(ob))
+        else:
+            rc = self.lib.icer_compress_image_yuv_uint16(_u16p(imgs[0]), _u16p(imgs[1]), _u16p(imgs[2]), w, h, stages,
+                                                         filt, segments, C.byref(ob))
+        n = ob.size_used
+        return dict(rc=rc, size_used=n, stream=bytes(buf[quota:quota + n]), prio=bytes(buf[:n]), coefs=imgs)
+
+    def decompress(self, stream, chan, bufsize_px, stages, filt, segments):
+        data = np.frombuffer(bytes(stream) + b"\0" * 64, dtype=np.uint8).copy()  # slack: the scanner over-reads
+        imgs = [np.zeros(max(bufsize_px, 1), dtype=np.uint16) for _ in range(chan)]
+        w = C.c_size_t(0)
+        h = C.c_size_t(0)
+        if chan == 1:
+            rc = self.lib.icer_decompress_image_uint16(_u16p(imgs[0]), C.byref(w), C.byref(h), bufsize_px, _u8p(data),
+                                                       len(stream), stages, filt, segments)
+        else:
+            rc = self.lib.icer_decompress_image_yuv_uint16(_u16p(imgs[0]), _u16p(imgs[1]), _u16p(imgs[2]), C.byref(w),
+                                                           C.byref(h), bufsize_px, _u8p(data), len(stream), stages, filt,
+                                                           segments)
+        W, H = w.value, h.value
+        out = [im[:W * H].reshape(H, W) for im in imgs] if rc == 0 and W * H <= bufsize_px else None
+        return dict(rc=rc, w=W, h=H, images=out)
+
+    # ---- sub-APIs ----------------------------------------------------------------------------------
+    def dwt_forward(self, img, stages, filt):
+        a = np.ascontiguousarray(img, dtype=np.uint16).copy()
+        rc = self.lib.icer_wavelet_transform_stages_uint16(_u16p(a), a.shape[1], a.shape[0], stages, filt)
+        return rc, a
+
+    def dwt_inverse(self, img, stages, filt):
+        a = np.ascontiguousarray(img, dtype=np.uint16).copy()
+        rc = self.lib.icer_inverse_wavelet_transform_stages_uint16(_u16p(a), a.shape[1], a.shape[0], stages, filt)
+        return rc, a
+
+    def dwt_1d(self, line, filt, inverse=False):
+        a = np.ascontiguousarray(line, dtype=np.uint16).copy()
+        f = self.lib.icer_inverse_wavelet_transform_1d_uint16 if inverse else self.lib.icer_wavelet_transform_1d_uint16
+        rc = f(_u16p(a), a.size, 1, filt)
+        return rc, a
+
+    def bin_of(self, zero, total):
+        return self.lib.icer_compute_bin(zero, total)
+
+
+class _Limits(C.Structure):
+    _fields_ = [("planes", C.c_int), ("max_stages", C.c_int), ("max_packets", C.c_int)]
+
+
+class _Rect(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("w", C.c_int), ("h", C.c_int)]
+
+
+class Oracle:
+    """Our plain-C restatement (oracle/liboracle.so)."""
+
+    def __init__(self, planes=9, max_stages=6, max_packets=800):
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle liboracle.so`)")
+        self.lib = C.CDLL(path)
+        self.lim = _Limits(planes, max_stages, max_packets)
+        self.planes = planes
+        L = self.lib
+        L.orc_init()
+        P3 = C.POINTER(C.c_uint16) * 3
+        self._P3 = P3
+        L.orc_compress_u16.argtypes = [P3, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(_Limits), C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
+        L.orc_decompress_u16.argtypes = [P3, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_size_t,
+                                         C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(_Limits)]
+        L.orc_dwt_forward_u16.argtypes = [C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_int, C.c_int]
+        L.orc_dwt_inverse_u16.argtypes = L.orc_dwt_forward_u16.argtypes
+        L.orc_dwt_forward_1d_u16.argtypes = [C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_int]
+        L.orc_dwt_inverse_1d_u16.argtypes = L.orc_dwt_forward_1d_u16.argtypes
+        L.orc_partition_rects.argtypes = [C.c_size_t, C.c_size_t, C.c_int, C.POINTER(_Rect)]
+        L.orc_bin_of.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_crc32.argtypes = [C.POINTER(C.c_uint8), C.c_size_t]
+        L.orc_crc32.restype = C.c_uint32
+        L.orc_synth_frame.argtypes = [C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_synth_frame.restype = None
+        L.orc_encode_segment_plane.argtypes = [C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
+                                               C.c_int, C.POINTER(C.c_uint8), C.c_size_t]
+        L.orc_encode_segment_plane.restype = C.c_long
+
+    def compress(self, planes_in, stages, filt, segments, quota):
+        imgs = [np.ascontiguousarray(p, dtype=np.uint16).copy() for p in planes_in]
+        h, w = imgs[0].shape
+        buf = np.zeros(2 * quota + 64, dtype=np.uint8)
+        ptrs = self._P3(*[_u16p(imgs[min(i, len(imgs) - 1)]) for i in range(3)])
+        used = C.c_size_t(0)
+        rc = self.lib.orc_compress_u16(ptrs, len(imgs), w, h, stages, filt, segments, C.byref(self.lim), _u8p(buf),
+                                       quota, C.byref(used))
+        n = used.value
+        return dict(rc=rc, size_used=n, stream=bytes(buf[quota:quota + n]), prio=bytes(buf[:n]), coefs=imgs)
+
+    def decompress(self, stream, chan, bufsize_px, stages, filt, segments):
+        data = np.frombuffer(bytes(stream) + b"\0" * 64, dtype=np.uint8).copy()
+        imgs = [np.zeros(max(bufsize_px, 1), dtype=np.uint16) for _ in range(chan)]
+        ptrs = self._P3(*[_u16p(imgs[min(i, chan - 1)]) for i in range(3)])
+        w = C.c_size_t(0)
+        h = C.c_size_t(0)
+        rc = self.lib.orc_decompress_u16(ptrs, chan, C.byref(w), C.byref(h), bufsize_px, _u8p(data), len(stream),
+                                         stages, filt, segments, C.byref(self.lim))
+        W, H = w.value, h.value
+        out = [im[:W * H].reshape(H, W) for im in imgs] if rc == 0 and W * H <= bufsize_px else None
+        return dict(rc=rc, w=W, h=H, images=out)
+
+    def dwt_forward(self, img, stages, filt):
+        a = np.ascontiguousarray(img, dtype=np.uint16).copy()
+        rc = self.lib.orc_dwt_forward_u16(_u16p(a), a.shape[1], a.shape[0], stages, filt)
+        return rc, a
+
+    def dwt_inverse(self, img, stages, filt):
+        a = np.ascontiguousarray(img, dtype=np.uint16).copy()
+        rc = self.lib.orc_dwt_inverse_u16(_u16p(a), a.shape[1], a.shape[0], stages, filt)
+        return rc, a
+
+    def dwt_1d(self, line, filt, inverse=False):
+        a = np.ascontiguousarray(line, dtype=np.uint16).copy()
+        f = self.lib.orc_dwt_inverse_1d_u16 if inverse else self.lib.orc_dwt_forward_1d_u16
+        rc = f(_u16p(a), a.size, 1, filt)
+        return rc, a
+
+    def partition(self, w, h, segments):
+        r = (_Rect * 40)()
+        n = self.lib.orc_partition_rects(w, h, segments, r)
+        return n, [(r[i].x, r[i].y, r[i].w, r[i].h) for i in range(max(n, 0))]
+
+    def bin_of(self, zero, total):
+        return self.lib.orc_bin_of(zero, total)
+
+    def crc32(self, data):
+        a = np.frombuffer(bytes(data) + b"\0", dtype=np.uint8).copy()
+        return self.lib.orc_crc32(_u8p(a), len(data))
+
+    def synth(self, w, h, frame, seed, kind):
+        a = np.empty((h, w), dtype=np.uint16)
+        self.lib.orc_synth_frame(_u16p(a), w, h, frame, seed, kind)
+        return a
+
+
+def have_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libicer_ref.so"))
+
+
+def load_boat():
+    """512x512 8-bit grayscale test image (tests/golden/boat512.u8.gz, from the reference's boat.512.bmp)."""
+    import gzip
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "boat512.u8.gz"), "rb") as f:
+        return np.frombuffer(f.read(), dtype=np.uint8).reshape(512, 512).astype(np.uint16)
+
+
+def load_boatcolor_yuv():
+    """512x512 Y,U,V planes (uint16) of the reference's boatcolor.512.bmp after the tools' RGB->YCbCr."""
+    import gzip
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "boatcolor512.yuv.u8.gz"), "rb") as f:
+        a = np.frombuffer(f.read(), dtype=np.uint8).reshape(3, 512, 512).astype(np.uint16)
+    return [a[0], a[1], a[2]]
