@@ -1,0 +1,678 @@
+// api.cu -- the C ABI of libicer_b200.so: codec context, device workspace, batch encode/decode orchestration and
+// the lib_icer-compatible single-image entry points (include/icer.h) implemented as batch-of-one wrappers.
+//
+// There is NO CPU codec path in this file: every compress/decompress call runs the CUDA kernels of wavelet.cu,
+// encode.cu and decode.cu; if no CUDA device is usable the calls fail with ICER_FATAL_ERROR.
+// Host-side work is limited to planning (plan.cu), the byte-stream scanner that locates CRC-valid segments
+// (lib_icer does this on the host too: icer_compress.c:443-459,:569-588) and buffer management.
+#include "common.h"
+#include <algorithm>
+#include <string.h>
+#include <string>
+#include <thread>
+#include <mutex>
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return ICER_RESULT_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        CUDA_TRY(cudaMalloc(&p, want));
+        cap = want;
+        return ICER_RESULT_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct icer_b200_ctx {
+    int device = 0;
+    int planes = ICER_BITPLANES_TO_COMPRESS_16, max_stages = ICER_MAX_DECOMP_STAGES, max_packets = ICER_MAX_PACKETS_16;
+    int scratch_bits = 3;
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int>, Plan *> plans;
+    LaunchStats ls;
+    DevBuf coefs, tmp, scratch, bits, crc, rings, out, out_prio, size_used, rc, keep, offp, offr, mean, ovf, misc,
+        streams, segoff, dims, frame_ok;
+    uint32_t ring_threads = 0;
+    bool timing = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float phase_ms[4] = {0, 0, 0, 0};
+    size_t workspace_budget = (size_t) 64 << 30;
+};
+
+namespace {
+
+Plan *get_plan(icer_b200_ctx *c, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages, uint32_t segments) {
+    auto key = std::make_tuple(w, h, chan, stages, segments, (uint32_t) c->planes, c->scratch_bits);
+    auto it = c->plans.find(key);
+    if (it != c->plans.end()) return it->second;
+    if (c->plans.size() > 64) {   // keep the cache bounded
+        for (auto &kv : c->plans) { free_plan_device(*kv.second); delete kv.second; }
+        c->plans.clear();
+    }
+    Plan *pl = new Plan();
+    build_plan(*pl, w, h, chan, stages, segments, (uint32_t) c->planes, (uint32_t) c->max_stages, (uint32_t) c->max_packets,
+               c->scratch_bits);
+    if (upload_plan(*pl) != ICER_RESULT_OK) pl->status = ICER_FATAL_ERROR;
+    c->plans[key] = pl;
+    return pl;
+}
+
+void ev_record(icer_b200_ctx *c, int i, cudaStream_t st) {
+    if (!c->timing) return;
+    if (!c->ev[i]) cudaEventCreate(&c->ev[i]);
+    cudaEventRecord(c->ev[i], st);
+}
+
+int copy_in(void *dst, const void *src, size_t bytes, int mem, cudaStream_t st) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, mem == ICER_B200_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    return ICER_RESULT_OK;
+}
+int copy_out(void *dst, const void *src, size_t bytes, int mem, cudaStream_t st) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, mem == ICER_B200_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    return ICER_RESULT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *icer_b200_version(void) { return "icer_b200 0.1 (sm_100a)"; }
+
+int icer_b200_create(icer_b200_ctx **out, int device) {
+    if (!out) return ICER_INVALID_INPUT;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "[icer_b200] no usable CUDA device (%s); this library has no CPU fallback\n", cudaGetErrorString(e));
+        return ICER_FATAL_ERROR;
+    }
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    CUDA_TRY(cudaSetDevice(device));
+    icer_b200_ctx *c = new icer_b200_ctx();
+    c->device = device;
+    const char *gb = getenv("ICER_B200_WORKSPACE_GB");
+    if (gb && atof(gb) > 0) c->workspace_budget = (size_t) (atof(gb) * (double) ((size_t) 1 << 30));
+    *out = c;
+    return ICER_RESULT_OK;
+}
+
+void icer_b200_destroy(icer_b200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto &kv : c->plans) { free_plan_device(*kv.second); delete kv.second; }
+    DevBuf *all[] = {&c->coefs, &c->tmp, &c->scratch, &c->bits, &c->crc, &c->rings, &c->out, &c->out_prio, &c->size_used, &c->rc,
+                     &c->keep, &c->offp, &c->offr, &c->mean, &c->ovf, &c->misc, &c->streams, &c->segoff, &c->dims, &c->frame_ok};
+    for (auto b : all) b->release();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    delete c;
+}
+
+int icer_b200_set_limits(icer_b200_ctx *c, int planes, int max_stages, int max_packets) {
+    if (!c) return ICER_INVALID_INPUT;
+    if (planes) { if (planes < 1 || planes > 15) return ICER_BITPLANE_OUT_OF_RANGE; c->planes = planes; }
+    if (max_stages) { if (max_stages < 1 || max_stages > 15) return ICER_TOO_MANY_STAGES; c->max_stages = max_stages; }
+    if (max_packets) c->max_packets = max_packets;
+    return ICER_RESULT_OK;
+}
+
+int icer_b200_set_scratch_bits(icer_b200_ctx *c, int bits) {
+    if (!c || bits < 1 || bits > 24) return ICER_INVALID_INPUT;
+    c->scratch_bits = bits;
+    return ICER_RESULT_OK;
+}
+
+uint64_t icer_b200_launch_count(const icer_b200_ctx *c) { return c ? c->ls.launches : 0; }
+float icer_b200_last_phase_ms(const icer_b200_ctx *c, int phase) { return (c && phase >= 0 && phase < 4) ? c->phase_ms[phase] : 0.f; }
+void icer_b200_enable_timing(icer_b200_ctx *c, int on) { if (c) c->timing = on != 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// batch encode
+// ---------------------------------------------------------------------------------------------------------
+int icer_b200_compress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, const uint16_t *frames, size_t n, uint8_t *out,
+                                 size_t out_stride, uint8_t *out_prio, uint16_t *coefs_out, uint64_t *size_used, int32_t *rc,
+                                 int mem, void *stream) {
+    if (!c || !p || !frames || !out || !size_used || !rc) return ICER_INVALID_INPUT;
+    if (p->channels != 1 && p->channels != 3) return ICER_INVALID_INPUT;
+    if (out_stride < p->byte_quota) return ICER_OUTPUT_BUF_TOO_SMALL;
+    if (n == 0) return ICER_RESULT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const uint32_t w = p->width, h = p->height, chan = p->channels;
+    Plan *pl = get_plan(c, w, h, chan, p->stages, p->segments);
+    if (pl->status == ICER_FATAL_ERROR) return ICER_FATAL_ERROR;
+    const bool host = mem == ICER_B200_MEM_HOST;
+    if (pl->status != ICER_RESULT_OK) {   // every frame of this shape fails the same way, nothing is written
+        std::vector<uint64_t> z(n, 0);
+        std::vector<int32_t> r(n, pl->status);
+        CUDA_TRY(cudaMemcpyAsync(size_used, z.data(), n * 8, host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(rc, r.data(), n * 4, host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return ICER_RESULT_OK;
+    }
+    const size_t plane_px = (size_t) w * h, frame_px = plane_px * chan;
+    if (c->ring_threads == 0) c->ring_threads = encode_resident_threads(c->device);
+
+    ev_record(c, 0, st);
+    float ms_dwt = 0, ms_enc = 0, ms_asm = 0;
+    size_t done = 0;
+    while (done < n) {
+        // chunk size under the workspace budget
+        const size_t per_frame = frame_px * 2 * 2 + pl->scratch_words * 4 + (size_t) pl->nstreams * 24 + (host ? out_stride * (out_prio ? 2 : 1) : 0) + 64;
+        size_t nb = std::max<size_t>(1, c->workspace_budget / per_frame);
+        nb = std::min(nb, n - done);
+        int e;
+        if ((e = c->coefs.ensure(nb * frame_px * 2))) return e;
+        if ((e = c->tmp.ensure(nb * frame_px * 2))) return e;
+        if ((e = c->bits.ensure(nb * pl->nstreams * 4))) return e;
+        if ((e = c->crc.ensure(nb * pl->nstreams * 4))) return e;
+        if ((e = c->offp.ensure(nb * pl->nstreams * 8))) return e;
+        if ((e = c->offr.ensure(nb * pl->nstreams * 8))) return e;
+        if ((e = c->rings.ensure((size_t) c->ring_threads * ICER_RING * 2))) return e;
+        if ((e = c->mean.ensure(nb * chan * 2))) return e;
+        if ((e = c->ovf.ensure(nb * chan * 4))) return e;
+        if ((e = c->keep.ensure(nb * 4))) return e;
+        if ((e = c->misc.ensure(64))) return e;
+        uint8_t *d_out = out + done * out_stride, *d_prio = out_prio ? out_prio + done * out_stride : nullptr;
+        uint64_t *d_used = size_used + done;
+        int32_t *d_rc = rc + done;
+        if (host) {
+            if ((e = c->out.ensure(nb * out_stride))) return e;
+            if (out_prio && (e = c->out_prio.ensure(nb * out_stride))) return e;
+            if ((e = c->size_used.ensure(nb * 8))) return e;
+            if ((e = c->rc.ensure(nb * 4))) return e;
+            d_out = c->out.as<uint8_t>(); d_prio = out_prio ? c->out_prio.as<uint8_t>() : nullptr;
+            d_used = c->size_used.as<uint64_t>(); d_rc = c->rc.as<int32_t>();
+        }
+        uint16_t *d_coefs = c->coefs.as<uint16_t>();
+        if ((e = copy_in(d_coefs, frames + done * frame_px, nb * frame_px * 2, mem, st))) return e;
+        CUDA_TRY(cudaMemsetAsync(c->ovf.p, 0, nb * chan * 4, st));
+        ev_record(c, 1, st);
+        if ((e = launch_dwt_forward(d_coefs, c->tmp.as<uint16_t>(), nb * chan, w, h, p->stages, p->filter, c->ovf.as<int>(), st, c->ls))) return e;
+        if ((e = launch_ll_mean_signmag(d_coefs, nb * chan, w, h, (uint32_t) dim_low(w, p->stages), (uint32_t) dim_low(h, p->stages),
+                                        c->mean.as<uint16_t>(), c->ovf.as<int>(), st, c->ls))) return e;
+        if (coefs_out) if ((e = copy_out(coefs_out + done * frame_px, d_coefs, nb * frame_px * 2, mem, st))) return e;
+        ev_record(c, 2, st);
+        // entropy coder, retried with a larger payload scratch in the (rare) case a stream outgrows its slot
+        for (;;) {
+            if ((e = c->scratch.ensure(nb * pl->scratch_words * 4))) return e;
+            CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 64, st));
+            EncodeArgs ea;
+            ea.coefs = d_coefs; ea.nframes = (uint32_t) nb; ea.w = w; ea.h = h; ea.chan = chan; ea.planes = pl->planes;
+            ea.units = pl->d_units; ea.nunits = (uint32_t) pl->units.size(); ea.soff = pl->d_soff; ea.scap = pl->d_scap;
+            ea.scratch_words = pl->scratch_words; ea.scratch = c->scratch.as<uint32_t>(); ea.bits = c->bits.as<uint32_t>();
+            ea.crc = c->crc.as<uint32_t>(); ea.rings = c->rings.as<uint16_t>(); ea.nring_threads = c->ring_threads;
+            ea.work_counter = c->misc.as<unsigned long long>(); ea.overflow = c->misc.as<int>() + 4;
+            if ((e = launch_encode(ea, st, c->ls))) return e;
+            int ovf = 0;
+            CUDA_TRY(cudaMemcpyAsync(&ovf, c->misc.as<int>() + 4, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (!ovf) break;
+            if (c->scratch_bits >= 24) { fprintf(stderr, "[icer_b200] payload scratch overflow at the worst-case bound\n"); return ICER_FATAL_ERROR; }
+            c->scratch_bits = std::min(24, c->scratch_bits * 2);
+            pl = get_plan(c, w, h, chan, p->stages, p->segments);
+            if (pl->status != ICER_RESULT_OK) return ICER_FATAL_ERROR;
+        }
+        ev_record(c, 3, st);
+        AssembleArgs aa;
+        aa.nframes = (uint32_t) nb; aa.nstreams = pl->nstreams; aa.planes = pl->planes; aa.chan = chan; aa.w = w; aa.h = h;
+        aa.units = pl->d_units; aa.prio = pl->d_prio; aa.rearr = pl->d_rearr; aa.soff = pl->d_soff; aa.scratch_words = pl->scratch_words;
+        aa.scratch = c->scratch.as<uint32_t>(); aa.bits = c->bits.as<uint32_t>(); aa.crc = c->crc.as<uint32_t>();
+        aa.mean = c->mean.as<uint16_t>(); aa.ovf = c->ovf.as<int>(); aa.plan_status = ICER_RESULT_OK; aa.quota = p->byte_quota;
+        aa.out = d_out; aa.out_stride = out_stride; aa.out_prio = d_prio; aa.size_used = d_used; aa.rc = d_rc;
+        aa.keep = c->keep.as<uint32_t>(); aa.off_prio = c->offp.as<uint64_t>(); aa.off_rearr = c->offr.as<uint64_t>();
+        if ((e = launch_assemble(aa, st, c->ls))) return e;
+        ev_record(c, 4, st);
+        if (host) {
+            CUDA_TRY(cudaMemcpyAsync(size_used + done, d_used, nb * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(rc + done, d_rc, nb * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            // only the used part of every slot travels back
+            for (size_t i = 0; i < nb; i++) {
+                const size_t len = (size_t) size_used[done + i];
+                if (len) CUDA_TRY(cudaMemcpyAsync(out + (done + i) * out_stride, d_out + i * out_stride, len, cudaMemcpyDeviceToHost, st));
+                if (len && out_prio) CUDA_TRY(cudaMemcpyAsync(out_prio + (done + i) * out_stride, d_prio + i * out_stride, len, cudaMemcpyDeviceToHost, st));
+            }
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        if (c->timing) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            float t;
+            cudaEventElapsedTime(&t, c->ev[1], c->ev[2]); ms_dwt += t;
+            cudaEventElapsedTime(&t, c->ev[2], c->ev[3]); ms_enc += t;
+            cudaEventElapsedTime(&t, c->ev[3], c->ev[4]); ms_asm += t;
+        }
+        done += nb;
+    }
+    if (c->timing) {
+        cudaEventElapsedTime(&c->phase_ms[0], c->ev[0], c->ev[4]);
+        c->phase_ms[1] = ms_dwt; c->phase_ms[2] = ms_enc; c->phase_ms[3] = ms_asm;
+    }
+    return ICER_RESULT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stream scanner (host): lib_icer's icer_find_packet_in_bytestream, icer_compress.c:569-588
+// ---------------------------------------------------------------------------------------------------------
+static inline uint32_t rd16(const uint8_t *p) { return p[0] | (p[1] << 8); }
+static inline uint32_t rd32(const uint8_t *p) { return rd16(p) | (rd16(p + 2) << 16); }
+
+uint32_t icer_calculate_packet_crc32(const icer_image_segment_typedef *pkt) {
+    return host_crc32((const uint8_t *) pkt, ICER_HDR_BYTES - 4);
+}
+uint32_t icer_calculate_segment_crc32(const icer_image_segment_typedef *pkt) {
+    return host_crc32((const uint8_t *) pkt + ICER_HDR_BYTES, (pkt->data_length + 7) / 8);
+}
+
+static bool segment_at(const uint8_t *p, size_t left, size_t *len) {
+    if (left < ICER_HDR_BYTES) return false;   // lib_icer reads the header without this check (past the buffer)
+    if (rd16(p) != ICER_PACKET_PREAMBLE) return false;
+    if (rd32(p + 24) != host_crc32(p, 24)) return false;
+    const size_t nbytes = ((size_t) rd32(p + 16) + 7) / 8;
+    if (nbytes > left - ICER_HDR_BYTES) return false;
+    if (rd32(p + 20) != host_crc32(p + ICER_HDR_BYTES, nbytes)) return false;
+    *len = ICER_HDR_BYTES + nbytes;
+    return true;
+}
+
+int icer_find_packet_in_bytestream(const icer_image_segment_typedef **seg, const uint8_t *datastream, size_t data_length,
+                                   size_t *offset) {
+    *offset = 0;
+    *seg = nullptr;
+    while (*offset < data_length) {
+        size_t len;
+        if (segment_at(datastream + *offset, data_length - *offset, &len)) {
+            *seg = (const icer_image_segment_typedef *) (datastream + *offset);
+            *offset += len;
+            return ICER_RESULT_OK;
+        }
+        (*offset)++;
+    }
+    return ICER_DECODER_OUT_OF_DATA;
+}
+
+int icer_get_image_dimensions(const uint8_t *datastream, size_t data_length, size_t *image_w, size_t *image_h) {
+    if (!datastream || !image_w || !image_h) return ICER_INVALID_INPUT;   // icer_compress.c:541-566: FIRST valid segment
+    size_t off = 0;
+    while (off < data_length) {
+        size_t len;
+        if (segment_at(datastream + off, data_length - off, &len)) {
+            *image_w = rd32(datastream + off + 8);
+            *image_h = rd32(datastream + off + 12);
+            return ICER_RESULT_OK;
+        }
+        off++;
+    }
+    return ICER_DECODER_OUT_OF_DATA;
+}
+
+namespace {
+struct SegRec { uint32_t off; uint8_t level, subband, seg, lsb_chan; };
+struct Parsed { std::vector<SegRec> segs; uint32_t w = 0, h = 0; uint16_t mean[3] = {0, 0, 0}; bool any = false; };
+
+void parse_stream(const uint8_t *s, size_t len, uint32_t chan, Parsed &out) {
+    size_t off = 0;
+    while (off < len) {
+        size_t slen;
+        if (segment_at(s + off, len - off, &slen)) {
+            const uint8_t *p = s + off;
+            out.segs.push_back(SegRec{(uint32_t) off, p[4], p[5], p[6], p[7]});
+            out.w = rd32(p + 8); out.h = rd32(p + 12);               // the LAST valid header wins (icer_compress.c:454-456)
+            const uint32_t ch = chan == 1 ? 0 : (p[7] >> 4);
+            if (ch < 3) out.mean[ch] = (uint16_t) rd16(p + 2);
+            out.any = true;
+            off += slen;
+        } else {
+            off++;
+        }
+    }
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// batch decode
+// ---------------------------------------------------------------------------------------------------------
+int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, const uint8_t *streams, size_t stream_stride,
+                                   const uint64_t *stream_len, size_t n, uint16_t *frames, uint32_t *dims, int32_t *rc, int mem,
+                                   void *stream) {
+    if (!c || !p || !streams || !stream_len || !frames || !rc) return ICER_INVALID_INPUT;
+    if (p->channels != 1 && p->channels != 3) return ICER_INVALID_INPUT;
+    if (n == 0) return ICER_RESULT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const bool host = mem == ICER_B200_MEM_HOST;
+    const uint32_t chan = p->channels;
+    const size_t cap_px = (size_t) p->width * p->height;
+    ev_record(c, 0, st);
+
+    // 1. the streams on the host (scanner) and on the device (decoder)
+    std::vector<uint64_t> lens(n);
+    std::vector<uint8_t> hstage;
+    const uint8_t *hs = streams;
+    const uint8_t *d_streams = streams;
+    const size_t total_bytes = n * stream_stride;
+    if (host) {
+        memcpy(lens.data(), stream_len, n * 8);
+        int e;
+        if ((e = c->streams.ensure(total_bytes + 16))) return e;
+        CUDA_TRY(cudaMemcpyAsync(c->streams.p, streams, total_bytes, cudaMemcpyHostToDevice, st));
+        d_streams = c->streams.as<uint8_t>();
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(lens.data(), stream_len, n * 8, cudaMemcpyDeviceToHost, st));
+        hstage.resize(total_bytes);
+        CUDA_TRY(cudaMemcpyAsync(hstage.data(), streams, total_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        hs = hstage.data();
+    }
+    // 2. scan every stream for CRC-valid segments (parallel over frames)
+    std::vector<Parsed> parsed(n);
+    {
+        unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 32));
+        if (n < 4) nt = 1;
+        std::vector<std::thread> th;
+        for (unsigned k = 0; k < nt; k++)
+            th.emplace_back([&, k]() {
+                for (size_t i = k; i < n; i += nt) {
+                    size_t len = std::min<uint64_t>(lens[i], stream_stride);
+                    parse_stream(hs + i * stream_stride, len, chan, parsed[i]);
+                }
+            });
+        for (auto &t : th) t.join();
+    }
+    ev_record(c, 1, st);
+    // 3. per-frame status; frames are grouped by their header dimensions (one plan per group)
+    std::vector<int32_t> hrc(n, ICER_RESULT_OK);
+    std::vector<uint32_t> hdims(n * 2, 0);
+    std::map<std::pair<uint32_t, uint32_t>, std::vector<size_t>> groups;
+    for (size_t i = 0; i < n; i++) {
+        hdims[2 * i] = parsed[i].w; hdims[2 * i + 1] = parsed[i].h;
+        if (!parsed[i].any) { hrc[i] = ICER_DECODER_OUT_OF_DATA; continue; }   // lib_icer: dimensions left uninitialised
+        if (cap_px < (size_t) parsed[i].w * parsed[i].h) { hrc[i] = ICER_BYTE_QUOTA_EXCEEDED; continue; }   // icer_compress.c:461-463
+        groups[{parsed[i].w, parsed[i].h}].push_back(i);
+    }
+    int e;
+    if ((e = c->coefs.ensure(n * chan * cap_px * 2))) return e;
+    if ((e = c->tmp.ensure(n * chan * cap_px * 2))) return e;
+    if ((e = c->mean.ensure(n * chan * 2))) return e;
+    if ((e = c->frame_ok.ensure(n * 4))) return e;
+    if ((e = c->dims.ensure(n * 8))) return e;
+    if ((e = c->misc.ensure(64))) return e;
+    uint16_t *d_frames = host ? c->coefs.as<uint16_t>() : frames;
+    float ms_dec = 0, ms_dwt = 0;
+    for (auto &g : groups) {
+        const uint32_t w = g.first.first, h = g.first.second;
+        Plan *pl = get_plan(c, w, h, chan, p->stages, p->segments);
+        if (pl->status == ICER_FATAL_ERROR) return ICER_FATAL_ERROR;
+        std::vector<int32_t> ok(n, 0);
+        if (pl->status != ICER_RESULT_OK) {
+            // lib_icer's decoder reports the partition / stage errors per image (icer_compress.c:480, icer_wavelet.c:92-94);
+            // ICER_PACKET_COUNT_EXCEEDED cannot occur on the decode side, treat it as a plain plan failure
+            for (size_t i : g.second) hrc[i] = pl->status;
+            continue;
+        }
+        // segment table of this group
+        std::vector<uint32_t> segoff(n * (size_t) pl->nstreams, 0xFFFFFFFFu);
+        std::vector<uint16_t> hmean(n * chan, 0);
+        for (size_t i : g.second) {
+            ok[i] = 1;
+            for (auto &r : parsed[i].segs) {
+                const int ch = chan == 1 ? 0 : (r.lsb_chan >> 4);
+                const int lsb = r.lsb_chan & 0x0F;
+                if (lsb >= (int) pl->planes) continue;
+                auto it = pl->unit_of.find(std::make_tuple(ch, (int) r.level, (int) r.subband, (int) r.seg));
+                if (it == pl->unit_of.end()) continue;
+                segoff[i * pl->nstreams + it->second * pl->planes + lsb] = r.off;
+            }
+            for (uint32_t ch = 0; ch < chan; ch++) hmean[i * chan + ch] = parsed[i].mean[ch];
+        }
+        if ((e = c->segoff.ensure(segoff.size() * 4))) return e;
+        CUDA_TRY(cudaMemcpyAsync(c->segoff.p, segoff.data(), segoff.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->mean.p, hmean.data(), hmean.size() * 2, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->frame_ok.p, ok.data(), n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 64, st));
+        // zero the output slots of this group's frames (icer_compress.c:470)
+        for (size_t i : g.second) CUDA_TRY(cudaMemsetAsync(d_frames + i * chan * cap_px, 0, chan * cap_px * 2, st));
+        ev_record(c, 2, st);
+        DecodeArgs da;
+        da.coefs = d_frames; da.nframes = (uint32_t) n; da.chan = chan; da.planes = pl->planes; da.cap_px = cap_px;
+        da.units = pl->d_units; da.nunits = (uint32_t) pl->units.size(); da.dims = nullptr; da.plan_w = w; da.plan_h = h;
+        da.streams = d_streams; da.stream_stride = stream_stride; da.total_bytes = total_bytes;
+        da.seg_off = c->segoff.as<uint32_t>(); da.frame_ok = c->frame_ok.as<int32_t>();
+        da.work_counter = c->misc.as<unsigned long long>();
+        if ((e = launch_decode(da, st, c->ls))) return e;
+        ev_record(c, 3, st);
+        // 4. from sign-magnitude + LL mean, inverse wavelet, clamp -- per frame of the group (planes are cap_px apart)
+        const uint32_t llw = (uint32_t) dim_low(w, p->stages), llh = (uint32_t) dim_low(h, p->stages);
+        const bool dense = (size_t) w * h == cap_px;
+        if (dense && g.second.size() == n) {
+            if ((e = launch_from_signmag_add_mean(d_frames, n * chan, w, h, llw, llh, c->mean.as<uint16_t>(), st, c->ls))) return e;
+            if ((e = launch_dwt_inverse(d_frames, c->tmp.as<uint16_t>(), n * chan, w, h, p->stages, p->filter, true, st, c->ls))) return e;
+        } else {
+            for (size_t i : g.second)
+                for (uint32_t ch = 0; ch < chan; ch++) {
+                    uint16_t *pp = d_frames + (i * chan + ch) * cap_px;
+                    if ((e = launch_from_signmag_add_mean(pp, 1, w, h, llw, llh, c->mean.as<uint16_t>() + i * chan + ch, st, c->ls))) return e;
+                    if ((e = launch_dwt_inverse(pp, c->tmp.as<uint16_t>(), 1, w, h, p->stages, p->filter, true, st, c->ls))) return e;
+                }
+        }
+        ev_record(c, 4, st);
+        if (c->timing) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            float t;
+            cudaEventElapsedTime(&t, c->ev[2], c->ev[3]); ms_dec += t;
+            cudaEventElapsedTime(&t, c->ev[3], c->ev[4]); ms_dwt += t;
+        }
+    }
+    // 5. results back
+    if (host) {
+        for (size_t i = 0; i < n; i++)
+            if (hrc[i] == ICER_RESULT_OK)
+                CUDA_TRY(cudaMemcpyAsync(frames + i * chan * cap_px, d_frames + i * chan * cap_px, chan * cap_px * 2, cudaMemcpyDeviceToHost, st));
+        memcpy(rc, hrc.data(), n * 4);
+        if (dims) memcpy(dims, hdims.data(), n * 8);
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(rc, hrc.data(), n * 4, cudaMemcpyHostToDevice, st));
+        if (dims) CUDA_TRY(cudaMemcpyAsync(dims, hdims.data(), n * 8, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));   // host vectors above must outlive the copies
+    if (c->timing) {
+        ev_record(c, 4, st);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&c->phase_ms[0], c->ev[0], c->ev[4]);
+        float t = 0;
+        cudaEventElapsedTime(&t, c->ev[0], c->ev[1]);
+        c->phase_ms[1] = ms_dwt; c->phase_ms[2] = ms_dec; c->phase_ms[3] = t;
+    }
+    return ICER_RESULT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// wavelet-only hook
+// ---------------------------------------------------------------------------------------------------------
+int icer_b200_dwt_batch_u16(icer_b200_ctx *c, uint16_t *planes, size_t n, uint32_t width, uint32_t height, uint32_t stages,
+                            uint32_t filter, int inverse, int32_t *rc, int mem, void *stream) {
+    if (!c || !planes || filter > ICER_FILTER_Q) return ICER_INVALID_INPUT;
+    if (n == 0) return ICER_RESULT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const bool host = mem == ICER_B200_MEM_HOST;
+    const size_t ps = (size_t) width * height;
+    if (dim_low(width, stages) < 3 || dim_low(height, stages) < 3) {   // icer_wavelet.c:66-68
+        if (rc) {
+            std::vector<int32_t> r(n, ICER_TOO_MANY_STAGES);
+            CUDA_TRY(cudaMemcpy(rc, r.data(), n * 4, host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice));
+        }
+        return ICER_RESULT_OK;
+    }
+    int e;
+    if ((e = c->tmp.ensure(n * ps * 2))) return e;
+    if ((e = c->ovf.ensure(n * 4))) return e;
+    uint16_t *d = planes;
+    if (host) {
+        if ((e = c->coefs.ensure(n * ps * 2))) return e;
+        d = c->coefs.as<uint16_t>();
+        CUDA_TRY(cudaMemcpyAsync(d, planes, n * ps * 2, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemsetAsync(c->ovf.p, 0, n * 4, st));
+    if (inverse) e = launch_dwt_inverse(d, c->tmp.as<uint16_t>(), n, width, height, stages, filter, false, st, c->ls);
+    else e = launch_dwt_forward(d, c->tmp.as<uint16_t>(), n, width, height, stages, filter, c->ovf.as<int>(), st, c->ls);
+    if (e) return e;
+    std::vector<int> ovf(n, 0);
+    CUDA_TRY(cudaMemcpyAsync(ovf.data(), c->ovf.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if (host) CUDA_TRY(cudaMemcpyAsync(planes, d, n * ps * 2, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (rc) {
+        std::vector<int32_t> r(n);
+        for (size_t i = 0; i < n; i++) r[i] = ovf[i] ? ICER_INTEGER_OVERFLOW : ICER_RESULT_OK;
+        CUDA_TRY(cudaMemcpy(rc, r.data(), n * 4, host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice));
+    }
+    return ICER_RESULT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// lib_icer-compatible single-image API (include/icer.h)
+// ---------------------------------------------------------------------------------------------------------
+static icer_b200_ctx *g_ctx = nullptr;
+static std::mutex g_mu;
+
+static icer_b200_ctx *default_ctx() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) {
+        if (icer_b200_create(&g_ctx, -1) != ICER_RESULT_OK) g_ctx = nullptr;
+        else {
+            const char *pl = getenv("ICER_B200_PLANES"), *ms = getenv("ICER_B200_MAX_STAGES");
+            icer_b200_set_limits(g_ctx, pl ? atoi(pl) : 0, ms ? atoi(ms) : 0, 0);
+        }
+    }
+    return g_ctx;
+}
+
+int icer_init(void) {   // icer_init.c:24-35: table set-up; here it also binds the default device context
+    icer_host_tables();
+    return default_ctx() ? ICER_RESULT_OK : ICER_FATAL_ERROR;
+}
+
+int icer_init_output_struct(icer_output_data_buf_typedef *out, uint8_t *data, size_t buf_len, size_t byte_quota) {
+    if (byte_quota * 2 > buf_len) return ICER_OUTPUT_BUF_TOO_SMALL;   // icer_util.c:38-45
+    out->size_used = 0;
+    out->data_start = data;
+    out->size_allocated = byte_quota;
+    out->rearrange_start = data + byte_quota;
+    return ICER_RESULT_OK;
+}
+
+size_t icer_get_dim_n_low_stages(size_t dim, uint8_t stages) { return dim_low(dim, stages); }
+size_t icer_get_dim_n_high_stages(size_t dim, uint8_t stages) { return dim_high(dim, stages); }
+
+int icer_generate_partition_parameters(partition_param_typdef *params, size_t ll_w, size_t ll_h, uint16_t segments) {
+    int n = partition_rects(ll_w, ll_h, segments, nullptr, nullptr, nullptr, nullptr, params);
+    return n < 0 ? n : ICER_RESULT_OK;
+}
+
+static int compress_common(uint16_t *const ch[3], uint32_t chan, size_t w, size_t h, uint8_t stages, int filt, uint8_t segments,
+                           icer_output_data_buf_typedef *od) {
+    icer_b200_ctx *c = default_ctx();
+    if (!c) return ICER_FATAL_ERROR;
+    if (!od || !ch[0]) return ICER_INVALID_INPUT;
+    icer_b200_params p;
+    p.width = (uint32_t) w; p.height = (uint32_t) h; p.channels = chan; p.stages = stages; p.filter = (uint32_t) filt;
+    p.segments = segments; p.byte_quota = od->size_allocated;
+    const size_t px = w * h;
+    std::vector<uint16_t> stage;
+    const uint16_t *src = ch[0];
+    if (chan == 3) {
+        stage.resize(px * 3);
+        for (int k = 0; k < 3; k++) memcpy(stage.data() + k * px, ch[k], px * 2);
+        src = stage.data();
+    }
+    std::vector<uint16_t> coefs(px * chan);
+    uint64_t used = 0;
+    int32_t rc = ICER_FATAL_ERROR;
+    int e = icer_b200_compress_batch_u16(c, &p, src, 1, od->rearrange_start, od->size_allocated, od->data_start, coefs.data(), &used,
+                                         &rc, ICER_B200_MEM_HOST, nullptr);
+    if (e != ICER_RESULT_OK) return e;
+    if (rc == ICER_RESULT_OK || rc == ICER_BYTE_QUOTA_EXCEEDED) {
+        // lib_icer leaves the LL-mean-removed sign-magnitude coefficients in the caller's image buffer
+        for (uint32_t k = 0; k < chan; k++) memcpy(ch[k], coefs.data() + k * px, px * 2);
+        od->size_used = (size_t) used;
+    }
+    return rc;
+}
+
+int icer_compress_image_uint16(uint16_t *image, size_t image_w, size_t image_h, uint8_t stages, enum icer_filter_types filt,
+                               uint8_t segments, icer_output_data_buf_typedef *output_data) {
+    uint16_t *ch[3] = {image, nullptr, nullptr};
+    return compress_common(ch, 1, image_w, image_h, stages, filt, segments, output_data);
+}
+
+int icer_compress_image_yuv_uint16(uint16_t *y, uint16_t *u, uint16_t *v, size_t image_w, size_t image_h, uint8_t stages,
+                                   enum icer_filter_types filt, uint8_t segments, icer_output_data_buf_typedef *output_data) {
+    uint16_t *ch[3] = {y, u, v};
+    if (!u || !v) return ICER_INVALID_INPUT;
+    return compress_common(ch, 3, image_w, image_h, stages, filt, segments, output_data);
+}
+
+static int decompress_common(uint16_t *const ch[3], uint32_t chan, size_t *image_w, size_t *image_h, size_t bufsize,
+                             const uint8_t *data, size_t len, uint8_t stages, int filt, uint8_t segments) {
+    icer_b200_ctx *c = default_ctx();
+    if (!c) return ICER_FATAL_ERROR;
+    if (!data || !image_w || !image_h) return ICER_INVALID_INPUT;
+    // dimensions of the LAST valid header decide the geometry (icer_compress.c:454-455)
+    Parsed ps;
+    parse_stream(data, len, chan, ps);
+    if (!ps.any) return ICER_DECODER_OUT_OF_DATA;
+    *image_w = ps.w; *image_h = ps.h;
+    if (bufsize < (size_t) ps.w * ps.h) return ICER_BYTE_QUOTA_EXCEEDED;
+    icer_b200_params p;
+    p.width = ps.w; p.height = ps.h; p.channels = chan; p.stages = stages; p.filter = (uint32_t) filt; p.segments = segments;
+    p.byte_quota = 0;
+    const size_t px = (size_t) ps.w * ps.h;
+    std::vector<uint16_t> outbuf(px * chan);
+    uint64_t l = len;
+    uint32_t dims[2];
+    int32_t rc = ICER_FATAL_ERROR;
+    int e = icer_b200_decompress_batch_u16(c, &p, data, len, &l, 1, outbuf.data(), dims, &rc, ICER_B200_MEM_HOST, nullptr);
+    if (e != ICER_RESULT_OK) return e;
+    if (rc == ICER_RESULT_OK)
+        for (uint32_t k = 0; k < chan; k++) memcpy(ch[k], outbuf.data() + k * px, px * 2);
+    return rc;
+}
+
+int icer_decompress_image_uint16(uint16_t *image, size_t *image_w, size_t *image_h, size_t image_bufsize, const uint8_t *datastream,
+                                 size_t data_length, uint8_t stages, enum icer_filter_types filt, uint8_t segments) {
+    uint16_t *ch[3] = {image, nullptr, nullptr};
+    if (!image) return ICER_INVALID_INPUT;
+    return decompress_common(ch, 1, image_w, image_h, image_bufsize, datastream, data_length, stages, filt, segments);
+}
+
+int icer_decompress_image_yuv_uint16(uint16_t *y, uint16_t *u, uint16_t *v, size_t *image_w, size_t *image_h, size_t image_bufsize,
+                                     const uint8_t *datastream, size_t data_length, uint8_t stages, enum icer_filter_types filt,
+                                     uint8_t segments) {
+    uint16_t *ch[3] = {y, u, v};
+    if (!y || !u || !v) return ICER_INVALID_INPUT;
+    return decompress_common(ch, 3, image_w, image_h, image_bufsize, datastream, data_length, stages, filt, segments);
+}
+
+int icer_wavelet_transform_stages_uint16(uint16_t *image, size_t image_w, size_t image_h, uint8_t stages, enum icer_filter_types filt) {
+    icer_b200_ctx *c = default_ctx();
+    if (!c) return ICER_FATAL_ERROR;
+    int32_t rc = ICER_FATAL_ERROR;
+    int e = icer_b200_dwt_batch_u16(c, image, 1, (uint32_t) image_w, (uint32_t) image_h, stages, (uint32_t) filt, 0, &rc, ICER_B200_MEM_HOST, nullptr);
+    return e != ICER_RESULT_OK ? e : rc;
+}
+
+int icer_inverse_wavelet_transform_stages_uint16(uint16_t *image, size_t image_w, size_t image_h, uint8_t stages,
+                                                 enum icer_filter_types filt) {
+    icer_b200_ctx *c = default_ctx();
+    if (!c) return ICER_FATAL_ERROR;
+    int32_t rc = ICER_FATAL_ERROR;
+    int e = icer_b200_dwt_batch_u16(c, image, 1, (uint32_t) image_w, (uint32_t) image_h, stages, (uint32_t) filt, 1, &rc, ICER_B200_MEM_HOST, nullptr);
+    // lib_icer reports inverse overflow too (icer_wavelet.c:102) but no caller looks at it; we return OK / TOO_MANY_STAGES
+    return e != ICER_RESULT_OK ? e : rc;
+}
+
+}  // extern "C"

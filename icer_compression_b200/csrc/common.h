@@ -1,0 +1,138 @@
+// common.h -- internal declarations shared by the host orchestration and the CUDA kernels of libicer_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <vector>
+#include <map>
+#include <tuple>
+
+#include "../../include/icer.h"
+#include "../../include/icer_b200.h"
+
+#define ICER_HDR_BYTES 28
+#define ICER_RING 2048
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            fprintf(stderr, "[icer_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__,  \
+                    __LINE__, cudaGetErrorString(_e));                                                   \
+            return ICER_FATAL_ERROR;                                                                     \
+        }                                                                                                \
+    } while (0)
+
+// ---- code tables (ICER standard; lib_icer builds the same at run time in src/icer_init.c) ---------------
+struct V2VEntry { uint8_t in_bits, out_bits, out; };
+struct HostTables {
+    V2VEntry enc[8][32];       // [bin 0..7][input word]   (bin 0 unused)
+    V2VEntry dec[8][32];       // [bin][emitted word] -> input word, bit-reversed
+    uint8_t flush[8][9][6];    // [bin][prefix][len] -> pad_word | pad_len << 4
+    uint16_t gol_m[17], gol_l[17], gol_i[17];
+    uint32_t cutoff[17];
+};
+const HostTables &icer_host_tables();
+
+// ---- plan: everything that depends only on (w, h, channels, stages, segments, planes) ---------------------
+// A "unit" is one error-containment segment of one subband of one channel; it carries `planes` bit-plane
+// streams (stream id = unit * planes + lsb).  Units are ordered big-first (level 1 first) so that warps get
+// similar amounts of work and the long streams start early.
+struct Unit {
+    int32_t x, y, w, h;        // rectangle inside the channel plane
+    uint8_t chan, level, subband, seg;
+    uint32_t px;
+};
+
+struct Plan {
+    uint32_t w, h, chan, stages, segments, planes, max_stages;
+    int status;                          // ICER_RESULT_OK or the error every frame of this shape gets
+    std::vector<Unit> units;
+    uint32_t nstreams;                   // units.size() * planes
+    std::vector<uint32_t> prio_order;    // stream ids in (priority packet, segment) order
+    std::vector<uint32_t> rearr_order;   // stream ids in the rearranged output order
+    std::vector<uint32_t> scratch_off;   // per stream: 32-bit word offset into the frame's payload scratch
+    std::vector<uint32_t> scratch_cap;   // per stream: capacity in 32-bit words
+    uint64_t scratch_words;              // per frame
+    int scratch_bits;
+    // device copies
+    Unit *d_units = nullptr;
+    uint32_t *d_prio = nullptr, *d_rearr = nullptr, *d_soff = nullptr, *d_scap = nullptr;
+    // lookup (chan, level, subband, seg) -> unit index, for the decoder's segment table
+    std::map<std::tuple<int, int, int, int>, uint32_t> unit_of;
+};
+
+int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages, uint32_t segments, uint32_t planes,
+               uint32_t max_stages, uint32_t max_packets, int scratch_bits);
+void free_plan_device(Plan &pl);
+int upload_plan(Plan &pl);
+
+static inline size_t dim_low(size_t d, unsigned s) { size_t p = (size_t) 1 << s; return (d + p - 1) / p; }
+static inline size_t dim_high(size_t d, unsigned s) { return dim_low(d, s - 1) / 2; }
+int partition_rects(size_t w, size_t h, int segments, int *xs, int *ys, int *ws, int *hs, partition_param_typdef *pp);
+uint32_t host_crc32(const uint8_t *buf, size_t len);
+
+// ---- kernel launchers (wavelet.cu / encode.cu / decode.cu) -------------------------------------------
+struct LaunchStats { uint64_t launches = 0; };
+
+// forward / inverse multi-stage DWT over `nplanes` planes of w*h int16, in place (tmp has the same size)
+int launch_dwt_forward(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
+                       uint32_t filt, int *d_ovf /* per plane, pre-zeroed */, cudaStream_t st, LaunchStats &ls);
+int launch_dwt_inverse(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
+                       uint32_t filt, bool clamp_negative, cudaStream_t st, LaunchStats &ls);
+// LL mean removal + sign-magnitude (encode), and the inverse (decode)
+int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
+                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls);
+int launch_from_signmag_add_mean(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
+                                 const uint16_t *d_mean, cudaStream_t st, LaunchStats &ls);
+
+struct EncodeArgs {
+    const uint16_t *coefs;     // [nframes][chan][h][w] sign-magnitude
+    uint32_t nframes, w, h, chan, planes;
+    const Unit *units; uint32_t nunits;
+    const uint32_t *soff, *scap;   // per stream
+    uint64_t scratch_words;        // per frame
+    uint32_t *scratch;             // [nframes][scratch_words]
+    uint32_t *bits;                // [nframes][nstreams] payload length in bits
+    uint32_t *crc;                 // [nframes][nstreams] crc32 of the payload bytes
+    uint16_t *rings;               // [resident threads][2048]
+    uint32_t nring_threads;
+    unsigned long long *work_counter;  // dynamic work fetch, pre-zeroed
+    int *overflow;                 // set when any stream outgrew its scratch
+};
+int launch_encode(const EncodeArgs &a, cudaStream_t st, LaunchStats &ls);
+uint32_t encode_resident_threads(int device);
+
+struct AssembleArgs {
+    uint32_t nframes, nstreams, planes, chan, w, h;
+    const Unit *units;
+    const uint32_t *prio, *rearr;  // stream id orders
+    const uint32_t *soff;
+    uint64_t scratch_words;
+    const uint32_t *scratch, *bits, *crc;
+    const uint16_t *mean;          // [nframes][chan]
+    const int *ovf;                // [nframes][chan] wavelet/mean overflow
+    int plan_status;
+    uint64_t quota;
+    uint8_t *out; uint64_t out_stride;        // rearranged streams
+    uint8_t *out_prio;                        // optional
+    uint64_t *size_used; int32_t *rc;         // [nframes]
+    uint32_t *keep;                           // [nframes] number of streams (in priority order) kept
+    uint64_t *off_prio, *off_rearr;           // [nframes][nstreams] byte offsets (scratch)
+};
+int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls);
+
+struct DecodeArgs {
+    uint16_t *coefs;               // [nframes][chan][cap_px] zero-initialised, receives sign-magnitude
+    uint32_t nframes, chan, planes;
+    uint64_t cap_px;               // pixels per channel slot
+    const Unit *units; uint32_t nunits;
+    const uint32_t *dims;          // [nframes][2] actual (w,h); frames whose dims differ from the plan are skipped
+    uint32_t plan_w, plan_h;
+    const uint8_t *streams; uint64_t stream_stride; uint64_t total_bytes;
+    const uint32_t *seg_off;       // [nframes][nstreams] byte offset of the segment header inside the frame's stream, 0xFFFFFFFF = absent
+    const int32_t *frame_ok;       // [nframes] 0 => skip
+    unsigned long long *work_counter;
+};
+int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls);

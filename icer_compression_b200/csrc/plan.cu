@@ -1,0 +1,266 @@
+// plan.cu -- host-side planning: code tables, segment geometry, packet priority order, stream orderings.
+//
+// Reference behaviour restated here (lib_icer/src): icer_init.c:24-255 (tables), icer_partition.c:7-54 (+ the
+// segment walk :299-385), icer_compress.c:315-365 / icer_color.c:398-458 (packet list, priority, sort),
+// icer_compress.c:409-423 / icer_color.c:508-527 (rearranged order).
+#include "common.h"
+#include <algorithm>
+#include <string.h>
+
+// ---------------------------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+// {bin, input word (first bit = bit 0), input bits, output word (first emitted bit = bit 0), output bits}
+const uint8_t kV2V[][5] = {
+    {1, 0x01, 2, 0x02, 2}, {1, 0x03, 3, 0x03, 3}, {1, 0x07, 4, 0x0F, 4}, {1, 0x0F, 4, 0x10, 5}, {1, 0x02, 2, 0x01, 2},
+    {1, 0x04, 3, 0x04, 3}, {1, 0x08, 4, 0x08, 4}, {1, 0x10, 5, 0x00, 5}, {1, 0x00, 5, 0x07, 4},
+    {2, 0x02, 2, 0x01, 2}, {2, 0x04, 3, 0x00, 2}, {2, 0x00, 4, 0x03, 3}, {2, 0x18, 5, 0x12, 5}, {2, 0x08, 5, 0x0F, 4},
+    {2, 0x01, 2, 0x06, 3}, {2, 0x03, 4, 0x07, 4}, {2, 0x0B, 4, 0x02, 5}, {2, 0x07, 3, 0x0A, 4},
+    {3, 0x02, 2, 0x02, 2}, {3, 0x04, 3, 0x03, 3}, {3, 0x00, 3, 0x00, 2}, {3, 0x01, 2, 0x01, 2}, {3, 0x03, 2, 0x07, 3},
+    {4, 0x00, 2, 0x01, 1}, {4, 0x02, 3, 0x00, 3}, {4, 0x06, 3, 0x0A, 4}, {4, 0x05, 3, 0x02, 4}, {4, 0x09, 4, 0x0E, 4},
+    {4, 0x01, 5, 0x04, 4}, {4, 0x11, 5, 0x06, 5}, {4, 0x03, 3, 0x0C, 4}, {4, 0x07, 3, 0x16, 5},
+    {5, 0x01, 1, 0x02, 2}, {5, 0x02, 3, 0x03, 3}, {5, 0x06, 3, 0x0F, 4}, {5, 0x04, 3, 0x05, 3}, {5, 0x08, 4, 0x01, 3},
+    {5, 0x10, 5, 0x07, 4}, {5, 0x00, 5, 0x00, 2},
+    {6, 0x00, 3, 0x00, 1}, {6, 0x04, 3, 0x01, 3}, {6, 0x02, 3, 0x05, 3}, {6, 0x06, 3, 0x0F, 5}, {6, 0x03, 2, 0x07, 4},
+    {6, 0x01, 3, 0x03, 3}, {6, 0x05, 3, 0x1F, 5},
+    {7, 0x02, 2, 0x05, 3}, {7, 0x04, 3, 0x01, 3}, {7, 0x00, 4, 0x00, 1}, {7, 0x08, 5, 0x07, 4}, {7, 0x18, 5, 0x0F, 5},
+    {7, 0x01, 2, 0x03, 3}, {7, 0x03, 2, 0x1F, 5}};
+// {bin, incomplete prefix, prefix bits, pad word, pad bits}: what a forced flush appends
+const uint8_t kFlush[][5] = {
+    {1, 0x1, 1, 0, 1}, {1, 0x3, 2, 0, 1}, {1, 0x7, 3, 0, 1}, {1, 0x0, 1, 1, 1}, {1, 0x0, 2, 1, 1}, {1, 0x0, 3, 1, 1},
+    {1, 0x0, 4, 0, 1},
+    {2, 0x0, 1, 1, 1}, {2, 0x0, 2, 1, 1}, {2, 0x0, 3, 0, 1}, {2, 0x8, 4, 0, 1}, {2, 0x1, 1, 0, 1}, {2, 0x3, 2, 1, 1},
+    {2, 0x3, 3, 0, 1},
+    {3, 0x0, 1, 1, 1}, {3, 0x0, 2, 0, 1}, {3, 0x1, 1, 0, 1},
+    {4, 0x0, 1, 0, 1}, {4, 0x2, 2, 0, 1}, {4, 0x1, 2, 1, 1}, {4, 0x1, 3, 1, 1}, {4, 0x1, 4, 0, 1}, {4, 0x1, 1, 1, 2},
+    {4, 0x3, 2, 0, 1},
+    {5, 0x0, 1, 1, 2}, {5, 0x1, 2, 0, 1}, {5, 0x0, 2, 1, 1}, {5, 0x0, 3, 1, 1}, {5, 0x0, 4, 0, 1},
+    {6, 0x0, 1, 0, 2}, {6, 0x0, 2, 0, 1}, {6, 0x2, 2, 0, 1}, {6, 0x1, 1, 1, 1}, {6, 0x1, 2, 0, 1},
+    {7, 0x0, 1, 1, 1}, {7, 0x0, 2, 1, 1}, {7, 0x0, 3, 0, 1}, {7, 0x8, 4, 0, 1}, {7, 0x1, 1, 0, 1}};
+const int kGolombM[17] = {0, 0, 0, 0, 0, 0, 0, 0, 5, 6, 7, 11, 17, 31, 70, 200, 512};
+const uint32_t kCutoff[17] = {35298, 37345, 40503, 43591, 47480, 50133, 53645, 55902, 57755,
+                              58894, 60437, 62267, 63613, 64557, 65134, 65392, 65536};
+
+unsigned rev(unsigned v, unsigned n) { unsigned r = 0; while (n--) { r = (r << 1) | (v & 1); v >>= 1; } return r; }
+
+HostTables make_tables() {
+    HostTables t;
+    memset(&t, 0, sizeof t);
+    for (auto &e : kV2V) {
+        t.enc[e[0]][e[1]] = V2VEntry{e[2], e[4], e[3]};
+        t.dec[e[0]][e[3]] = V2VEntry{e[4], e[2], (uint8_t) rev(e[1], e[2])};
+    }
+    for (auto &e : kFlush) t.flush[e[0]][e[1]][e[2]] = (uint8_t) (e[3] | (e[4] << 4));
+    for (int b = 0; b < 17; b++) {
+        t.cutoff[b] = kCutoff[b];
+        if (kGolombM[b] > 0) {
+            unsigned m = (unsigned) kGolombM[b], l = 0;
+            while ((1u << l) < m) l++;
+            t.gol_m[b] = (uint16_t) m; t.gol_l[b] = (uint16_t) l; t.gol_i[b] = (uint16_t) ((1u << l) - m);
+        }
+    }
+    return t;
+}
+}  // namespace
+
+const HostTables &icer_host_tables() {
+    static const HostTables t = make_tables();
+    return t;
+}
+
+uint32_t host_crc32(const uint8_t *buf, size_t len) {
+    static uint32_t tab[256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t n = 0; n < 256; n++) {
+            uint32_t c = n;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            tab[n] = c;
+        }
+        ready = true;
+    }
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t k = 0; k < len; k++) c = tab[(c ^ buf[k]) & 0xFF] ^ (c >> 8);
+    return ~c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// segment geometry
+// ---------------------------------------------------------------------------------------------------------
+int partition_rects(size_t w, size_t h, int segments, int *xs, int *ys, int *ws, int *hs, partition_param_typdef *pp) {
+    size_t s = (size_t) segments;
+    if (segments < 1 || s > w * h || segments > ICER_MAX_SEGMENTS) return ICER_TOO_MANY_SEGMENTS;
+    size_t r, c;
+    if (h > (s - 1) * w) r = s;
+    else for (r = 1; r < s && (r + 1) * r * w < h * s; r++) {}
+    c = s / r;
+    size_t r_t = (c + 1) * r - s;
+    size_t h_t = ((2 * h * c * r_t + s) / 2) / s;
+    if (h_t < r_t) h_t = r_t;
+    size_t x_t = w / c, c_t0 = (x_t + 1) * c - w, y_t = h_t / r_t, r_t0 = (y_t + 1) * r_t - h_t;
+    size_t x_b = 0, c_b0 = 0, y_b = 0, r_b0 = 0;
+    if (r_t < r) {
+        x_b = w / (c + 1);
+        c_b0 = (x_b + 1) * (c + 1) - w;
+        y_b = (h - h_t) / (r - r_t);
+        r_b0 = (y_b + 1) * (r - r_t) - (h - h_t);
+    }
+    if (pp) {
+        pp->w = (uint16_t) w; pp->h = (uint16_t) h; pp->s = (uint16_t) s; pp->r = (uint16_t) r; pp->c = (uint16_t) c;
+        pp->r_t = (uint16_t) r_t; pp->h_t = (uint16_t) h_t; pp->x_t = (uint16_t) x_t; pp->c_t0 = (uint16_t) c_t0;
+        pp->y_t = (uint16_t) y_t; pp->r_t0 = (uint16_t) r_t0; pp->x_b = (uint16_t) x_b; pp->c_b0 = (uint16_t) c_b0;
+        pp->y_b = (uint16_t) y_b; pp->r_b0 = (uint16_t) r_b0;
+    }
+    if (!xs) return (int) s;
+    int n = 0;
+    size_t y = 0;
+    for (size_t row = 0; row < r_t; row++) {
+        size_t sh = y_t + (row >= r_t0 ? 1 : 0), x = 0;
+        for (size_t col = 0; col < c; col++) {
+            size_t sw = x_t + (col >= c_t0 ? 1 : 0);
+            xs[n] = (int) x; ys[n] = (int) y; ws[n] = (int) sw; hs[n] = (int) sh; n++;
+            x += sw;
+        }
+        y += sh;
+    }
+    for (size_t row = 0; row < r - r_t; row++) {
+        size_t sh = y_b + (row >= r_b0 ? 1 : 0), x = 0;
+        for (size_t col = 0; col < c + 1; col++) {
+            size_t sw = x_b + (col >= c_b0 ? 1 : 0);
+            xs[n] = (int) x; ys[n] = (int) y; ws[n] = (int) sw; hs[n] = (int) sh; n++;
+            x += sw;
+        }
+        y += sh;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct Packet { int level, subband, lsb, chan; uint64_t prio; int order; };
+}
+
+int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages, uint32_t segments, uint32_t planes,
+               uint32_t max_stages, uint32_t max_packets, int scratch_bits) {
+    pl.w = w; pl.h = h; pl.chan = chan; pl.stages = stages; pl.segments = segments; pl.planes = planes;
+    pl.max_stages = max_stages; pl.scratch_bits = scratch_bits;
+    pl.status = ICER_RESULT_OK;
+    pl.units.clear(); pl.prio_order.clear(); pl.rearr_order.clear(); pl.unit_of.clear();
+    pl.nstreams = 0; pl.scratch_words = 0;
+    if (stages < 1 || stages > max_stages) { pl.status = ICER_TOO_MANY_STAGES; return pl.status; }
+    if (dim_low(w, stages) < 3 || dim_low(h, stages) < 3) { pl.status = ICER_TOO_MANY_STAGES; return pl.status; }
+
+    // units, big first: level ascending; the LL band rides with the last level
+    int xs[40], ys[40], ws[40], hs[40];
+    for (uint32_t lv = 1; lv <= stages; lv++)
+        for (uint32_t ch = 0; ch < chan; ch++)
+            for (int sb = 3; sb >= 0; sb--) {
+                if (sb == 0 && lv != stages) continue;
+                size_t x0 = (sb == 1 || sb == 3) ? dim_low(w, lv) : 0, y0 = (sb == 2 || sb == 3) ? dim_low(h, lv) : 0;
+                size_t sw = (sb == 1 || sb == 3) ? dim_high(w, lv) : dim_low(w, lv);
+                size_t sh = (sb == 2 || sb == 3) ? dim_high(h, lv) : dim_low(h, lv);
+                int n = partition_rects(sw, sh, (int) segments, xs, ys, ws, hs, nullptr);
+                if (n < 0) { pl.status = n; return n; }   // lib_icer: undefined behaviour (icer_compress.c:401)
+                for (int sg = 0; sg < n; sg++) {
+                    Unit u;
+                    u.x = (int) x0 + xs[sg]; u.y = (int) y0 + ys[sg]; u.w = ws[sg]; u.h = hs[sg];
+                    u.chan = (uint8_t) ch; u.level = (uint8_t) lv; u.subband = (uint8_t) sb; u.seg = (uint8_t) sg;
+                    u.px = (uint32_t) ws[sg] * (uint32_t) hs[sg];
+                    pl.unit_of[std::make_tuple((int) ch, (int) lv, sb, sg)] = (uint32_t) pl.units.size();
+                    pl.units.push_back(u);
+                }
+            }
+    pl.nstreams = (uint32_t) pl.units.size() * planes;
+
+    // packets in the reference's insertion order, then a stable sort by (priority desc, subband asc)
+    std::vector<Packet> pk;
+    auto add = [&](int lv, int sb, int lsb, int ch, uint64_t pr) { pk.push_back(Packet{lv, sb, lsb, ch, pr, (int) pk.size()}); };
+    if (chan == 1) {
+        for (uint32_t st = 1; st <= stages; st++) {
+            uint64_t pr = (uint64_t) 1 << st;
+            for (uint32_t lsb = 0; lsb < planes; lsb++) {
+                add(st, 1, lsb, 0, pr << lsb);
+                add(st, 2, lsb, 0, pr << lsb);
+                add(st, 3, lsb, 0, ((pr / 2) << lsb) + 1);
+            }
+        }
+        uint64_t pr = (uint64_t) 1 << stages;
+        for (uint32_t lsb = 0; lsb < planes; lsb++) add(stages, 0, lsb, 0, (2 * pr) << lsb);
+    } else {
+        // colour: a uint32_t priority doubled at every Y packet, cumulatively over the lsb loop (icer_color.c:401-404)
+        for (uint32_t st = 1; st <= stages; st++) {
+            uint32_t pr = 1u << st;
+            for (uint32_t lsb = 0; lsb < planes; lsb++)
+                for (uint32_t ch = 0; ch < 3; ch++) {
+                    if (ch == 0) pr *= 2;
+                    add(st, 1, lsb, ch, (uint32_t) (pr << lsb));
+                    add(st, 2, lsb, ch, (uint32_t) (pr << lsb));
+                    add(st, 3, lsb, ch, (uint32_t) (((pr / 2) << lsb) + 1));
+                }
+        }
+        uint32_t pr = 1u << stages;
+        for (uint32_t lsb = 0; lsb < planes; lsb++)
+            for (uint32_t ch = 0; ch < 3; ch++) {
+                if (ch == 0) pr *= 2;
+                add(stages, 0, lsb, ch, (uint32_t) ((2 * pr) << lsb));
+            }
+    }
+    // lib_icer: `ind++; if (ind >= ICER_MAX_PACKETS_16) return ICER_PACKET_COUNT_EXCEEDED` (icer_compress.c:327)
+    if (pk.size() >= max_packets) { pl.status = ICER_PACKET_COUNT_EXCEEDED; return pl.status; }
+    std::stable_sort(pk.begin(), pk.end(), [](const Packet &a, const Packet &b) {
+        if (a.prio != b.prio) return a.prio > b.prio;
+        return a.subband < b.subband;
+    });
+    for (auto &p : pk)
+        for (int sg = 0;; sg++) {
+            auto it = pl.unit_of.find(std::make_tuple(p.chan, p.level, p.subband, sg));
+            if (it == pl.unit_of.end()) break;
+            pl.prio_order.push_back(it->second * planes + (uint32_t) p.lsb);
+        }
+    // rearranged order: segment asc, subband 3..0, level hi..lo, lsb hi..lo, channel asc
+    for (int sg = 0; sg <= ICER_MAX_SEGMENTS; sg++)
+        for (int sb = 3; sb >= 0; sb--)
+            for (int lv = (int) max_stages; lv >= 0; lv--)
+                for (int lsb = (int) planes - 1; lsb >= 0; lsb--)
+                    for (int ch = 0; ch < (int) chan; ch++) {
+                        auto it = pl.unit_of.find(std::make_tuple(ch, lv, sb, sg));
+                        if (it != pl.unit_of.end()) pl.rearr_order.push_back(it->second * planes + (uint32_t) lsb);
+                    }
+    // payload scratch layout
+    pl.scratch_off.resize(pl.nstreams);
+    pl.scratch_cap.resize(pl.nstreams);
+    uint64_t off = 0;
+    for (size_t u = 0; u < pl.units.size(); u++)
+        for (uint32_t l = 0; l < planes; l++) {
+            uint64_t cap = ((uint64_t) pl.units[u].px * (uint64_t) scratch_bits + 31) / 32 + 2;
+            pl.scratch_off[u * planes + l] = (uint32_t) off;
+            pl.scratch_cap[u * planes + l] = (uint32_t) cap;
+            off += cap;
+        }
+    pl.scratch_words = off;
+    return ICER_RESULT_OK;
+}
+
+void free_plan_device(Plan &pl) {
+    cudaFree(pl.d_units); cudaFree(pl.d_prio); cudaFree(pl.d_rearr); cudaFree(pl.d_soff); cudaFree(pl.d_scap);
+    pl.d_units = nullptr; pl.d_prio = pl.d_rearr = pl.d_soff = pl.d_scap = nullptr;
+}
+
+int upload_plan(Plan &pl) {
+    free_plan_device(pl);
+    if (pl.status != ICER_RESULT_OK || pl.units.empty()) return ICER_RESULT_OK;
+    CUDA_TRY(cudaMalloc(&pl.d_units, pl.units.size() * sizeof(Unit)));
+    CUDA_TRY(cudaMalloc(&pl.d_prio, pl.nstreams * 4));
+    CUDA_TRY(cudaMalloc(&pl.d_rearr, pl.nstreams * 4));
+    CUDA_TRY(cudaMalloc(&pl.d_soff, pl.nstreams * 4));
+    CUDA_TRY(cudaMalloc(&pl.d_scap, pl.nstreams * 4));
+    CUDA_TRY(cudaMemcpy(pl.d_units, pl.units.data(), pl.units.size() * sizeof(Unit), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pl.d_prio, pl.prio_order.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pl.d_rearr, pl.rearr_order.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pl.d_soff, pl.scratch_off.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pl.d_scap, pl.scratch_cap.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
+    return ICER_RESULT_OK;
+}

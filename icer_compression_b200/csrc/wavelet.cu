@@ -1,0 +1,302 @@
+// wavelet.cu -- K1/K2/K3/K8: multi-level reversible integer lifting DWT and the pre/post passes around it.
+//
+// Reference behaviour (lib_icer/src/icer_wavelet.c): one 1-D pass over a line of n samples produces
+// ceil(n/2) lows followed by floor(n/2) highs (:385-465); a stage is every row then every column of the
+// current LL region (:155-171); stages shrink the region by ceil(/2) (:57-77).  The reference works in place
+// with a cycle-leader unshuffle; here every pass is out of place (src -> dst) between the coefficient buffer and
+// a scratch buffer of the same size, so a thread that produces l[k] and h[k] writes them straight to their
+// final positions.  All stored values wrap to int16 exactly like the reference's casts; the overflow flag is
+// raised under the same conditions (:412-415, :460-461).
+#include "common.h"
+
+__constant__ int c_filt[7][4] = {{0, 4, 4, 0}, {0, 4, 6, 4}, {-1, 4, 8, 6}, {0, 4, 5, 2},
+                                 {0, 3, 8, 6}, {0, 3, 9, 8}, {0, 4, 4, 4}};   // icer_config.c:18-24
+
+namespace {
+
+// A line view: element i of line `line` of plane `p`.
+template <bool COL>
+struct LineView {
+    const int16_t *s;
+    size_t es;
+    __device__ LineView(const int16_t *base, size_t plane_stride, int plane, int line, int W)
+        : s(base + (size_t) plane * plane_stride + (COL ? (size_t) line : (size_t) line * W)), es(COL ? (size_t) W : 1) {}
+    __device__ int operator()(int i) const { return (int) s[(size_t) i * es]; }
+};
+
+// ---- forward pass: thread (line, k) produces l[k] and h[k] --------------------------------------------
+template <bool COL>
+__global__ void __launch_bounds__(256) k_fwd_pass(const int16_t *__restrict__ src, int16_t *__restrict__ dst, int n,
+                                                  int nlines, int W, size_t plane_stride, int filt, int plane0,
+                                                  int *__restrict__ ovf) {
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y;
+    const int line = COL ? tx : ty, k = COL ? ty : tx;
+    const int nl = (n + 1) >> 1, nh = n >> 1;
+    if (line >= nlines || k >= nl) return;
+    const int plane = plane0 + blockIdx.z;
+    const bool odd = n & 1;
+    LineView<COL> X(src, plane_stride, plane, line, W);
+    int16_t *d = dst + (size_t) plane * plane_stride + (COL ? (size_t) line : (size_t) line * W);
+    const size_t es = COL ? (size_t) W : 1;
+
+    // stored (int16-wrapped) low / high of pair j
+    auto LO = [&](int j) -> int { return j < nh ? (int) (int16_t) ((X(2 * j) + X(2 * j + 1)) >> 1) : X(n - 1); };
+    auto HI = [&](int j) -> int { return (int) (int16_t) (X(2 * j) - X(2 * j + 1)); };
+    auto R = [&](int j) -> int { return (int) (int16_t) (LO(j - 1) - LO(j)); };   // get_r_int16 :206-208
+
+    d[(size_t) k * es] = (int16_t) LO(k);
+    if (k >= nh) return;
+    const int a = X(2 * k), b = X(2 * k + 1);
+    const int hi = a - b;
+    bool o = hi > 32767 || hi < -32768;
+    const int dk = (int) (int16_t) hi;
+    const int f0 = c_filt[filt][0], f1 = c_filt[filt][1], f2 = c_filt[filt][2], f3 = c_filt[filt][3];
+    int sub;
+    if (k == 0) {
+        sub = R(1) >> 2;
+    } else if (k == 1 && f0 != 0) {                       // filter C quirk :436-440
+        const int x = (odd && nl - 1 == 2) ? 0 : HI(1);
+        sub = (2 * R(1) + 3 * R(2) - 2 * x + 4) >> 3;
+    } else if (!odd && k == nh - 1) {
+        sub = R(k) >> 2;
+    } else {
+        const int rm1 = (f0 != 0) ? ((k - 1 > 0) ? R(k - 1) : 1) : 0;
+        const int dn = (odd && k + 1 == nl - 1) ? 0 : HI(k + 1);
+        sub = (f0 * rm1 + f1 * R(k) + f2 * R(k + 1) - f3 * dn + 8) >> 4;
+    }
+    const int hv = dk - sub;
+    o |= hv > 32767 || hv < -32768;
+    d[(size_t) (nl + k) * es] = (int16_t) hv;
+    if (o) atomicOr(&ovf[plane], 1);
+}
+
+// ---- inverse pass, data-parallel form (beta == 0 and alpha_-1 == 0: filter A) -----------------------------
+template <bool COL, bool CLAMP>
+__global__ void __launch_bounds__(256) k_inv_pass_par(const int16_t *__restrict__ src, int16_t *__restrict__ dst, int n,
+                                                      int nlines, int W, size_t plane_stride, int filt, int plane0) {
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y;
+    const int line = COL ? tx : ty, k = COL ? ty : tx;
+    const int nl = (n + 1) >> 1, nh = n >> 1;
+    if (line >= nlines || k >= nl) return;
+    const int plane = plane0 + blockIdx.z;
+    const bool odd = n & 1;
+    LineView<COL> S(src, plane_stride, plane, line, W);
+    int16_t *d = dst + (size_t) plane * plane_stride + (COL ? (size_t) line : (size_t) line * W);
+    const size_t es = COL ? (size_t) W : 1;
+    auto R = [&](int j) -> int { return (int) (int16_t) (S(j - 1) - S(j)); };
+    if (k >= nh) {   // odd tail: low + floor(1/2) = low (:537-545)
+        int v = S(nl - 1);
+        if (CLAMP && v < 0) v = 0;
+        d[(size_t) (n - 1) * es] = (int16_t) v;
+        return;
+    }
+    const int f1 = c_filt[filt][1], f2 = c_filt[filt][2];
+    int add;
+    if (k == 0) add = R(1) >> 2;
+    else if (!odd && k == nh - 1) add = R(k) >> 2;
+    else add = (f1 * R(k) + f2 * R(k + 1) + 8) >> 4;
+    const int dk = (int) (int16_t) (S(nl + k) + add);
+    const int t = S(k) + ((dk + 1) >> 1);
+    int v0 = (int) (int16_t) t, v1 = (int) (int16_t) (t - dk);
+    if (CLAMP) { v0 = v0 < 0 ? 0 : v0; v1 = v1 < 0 ? 0 : v1; }
+    d[(size_t) (2 * k) * es] = (int16_t) v0;
+    d[(size_t) (2 * k + 1) * es] = (int16_t) v1;
+}
+
+// ---- inverse pass, serial along the line (beta != 0: d[k] needs the restored d[k+1]; :478-508) --------------
+template <bool COL, bool CLAMP>
+__global__ void __launch_bounds__(128) k_inv_pass_ser(const int16_t *__restrict__ src, int16_t *__restrict__ dst, int n,
+                                                      int nlines, int W, size_t plane_stride, int filt, int plane0) {
+    const int line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= nlines) return;
+    const int plane = plane0 + blockIdx.z;
+    const int nl = (n + 1) >> 1, nh = n >> 1;
+    const bool odd = n & 1;
+    LineView<COL> S(src, plane_stride, plane, line, W);
+    int16_t *d = dst + (size_t) plane * plane_stride + (COL ? (size_t) line : (size_t) line * W);
+    const size_t es = COL ? (size_t) W : 1;
+    auto R = [&](int j) -> int { return (int) (int16_t) (S(j - 1) - S(j)); };
+    const int f0 = c_filt[filt][0], f1 = c_filt[filt][1], f2 = c_filt[filt][2], f3 = c_filt[filt][3];
+    if (odd) {
+        int v = S(nl - 1);
+        if (CLAMP && v < 0) v = 0;
+        d[(size_t) (n - 1) * es] = (int16_t) v;
+    }
+    int dnext = 0;
+    for (int k = nh - 1; k >= 0; k--) {
+        int add;
+        if (k == 0) {
+            add = R(1) >> 2;
+        } else if (k == 1 && f0 != 0) {
+            const int x = (odd && nl - 1 == 2) ? 0 : S(nl + 1);   // still the un-restored h[1] (:488-492)
+            add = (2 * R(1) + 3 * R(2) - 2 * x + 4) >> 3;
+        } else if (!odd && k == nh - 1) {
+            add = R(k) >> 2;
+        } else {
+            const int rm1 = (f0 != 0) ? ((k - 1 > 0) ? R(k - 1) : 1) : 0;
+            const int dn = (odd && k + 1 == nl - 1) ? 0 : dnext;
+            add = (f0 * rm1 + f1 * R(k) + f2 * R(k + 1) - f3 * dn + 8) >> 4;
+        }
+        const int dk = (int) (int16_t) (S(nl + k) + add);
+        dnext = dk;
+        const int t = S(k) + ((dk + 1) >> 1);
+        int v0 = (int) (int16_t) t, v1 = (int) (int16_t) (t - dk);
+        if (CLAMP) { v0 = v0 < 0 ? 0 : v0; v1 = v1 < 0 ? 0 : v1; }
+        d[(size_t) (2 * k) * es] = (int16_t) v0;
+        d[(size_t) (2 * k + 1) * es] = (int16_t) v1;
+    }
+}
+
+// ---- K3: LL mean (unsigned sum, icer_compress.c:289-302), subtract on LL, then sign-magnitude everywhere ----
+__global__ void __launch_bounds__(256) k_ll_mean(uint16_t *__restrict__ planes, size_t plane_stride, int W, int llw,
+                                                 int llh, uint16_t *__restrict__ mean_out, int *__restrict__ ovf) {
+    __shared__ unsigned long long red[256];
+    __shared__ unsigned s_mean;
+    uint16_t *p = planes + (size_t) blockIdx.x * plane_stride;
+    const int total = llw * llh;
+    unsigned long long sum = 0;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) sum += p[(size_t) (i / llw) * W + (i % llw)];
+    red[threadIdx.x] = sum;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int) threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        unsigned m = (unsigned) ((red[0] / (unsigned long long) total) & 0xFFFF);   // uint16_t ll_mean = sum / n
+        s_mean = m;
+        mean_out[blockIdx.x] = (uint16_t) m;
+        if (m > 32767) atomicOr(&ovf[blockIdx.x], 2);
+    }
+    __syncthreads();
+    const int m = (int) (int16_t) s_mean;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        uint16_t *q = &p[(size_t) (i / llw) * W + (i % llw)];
+        *q = (uint16_t) (int16_t) ((int) (int16_t) *q - m);
+    }
+}
+
+__device__ __forceinline__ uint32_t to_signmag(uint32_t v) {          // icer_wavelet.c:871-877
+    const int s = (int) (int16_t) v;
+    return s < 0 ? (uint32_t) ((-s) & 0x7FFF) | 0x8000u : (uint32_t) s;
+}
+__device__ __forceinline__ uint32_t from_signmag(uint32_t v) {        // icer_wavelet.c:880-886
+    return (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;
+}
+
+__global__ void __launch_bounds__(256) k_to_signmag(uint16_t *__restrict__ data, size_t count) {
+    // 8 samples (128 bits) per thread per iteration
+    size_t nvec = count / 8;
+    uint4 *v = reinterpret_cast<uint4 *>(data);
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t) gridDim.x * blockDim.x) {
+        uint4 q = v[i];
+        uint32_t *w = reinterpret_cast<uint32_t *>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = to_signmag(w[j] & 0xFFFF) | (to_signmag(w[j] >> 16) << 16);
+        v[i] = q;
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = nvec * 8 + threadIdx.x; i < count; i += blockDim.x) data[i] = (uint16_t) to_signmag(data[i]);
+}
+
+// decode side: from sign-magnitude everywhere, then add the header's LL mean on the LL region
+__global__ void __launch_bounds__(256) k_from_signmag(uint16_t *__restrict__ planes, size_t plane_stride, size_t count,
+                                                      int W, int llw, int llh, const uint16_t *__restrict__ mean) {
+    uint16_t *p = planes + (size_t) blockIdx.y * plane_stride;
+    const int m = (int) (int16_t) mean[blockIdx.y];
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x) {
+        uint32_t v = from_signmag(p[i]);
+        const int r = (int) (i / W), c = (int) (i % W);
+        if (r < llh && c < llw) v = (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + m);
+        p[i] = (uint16_t) v;
+    }
+}
+
+template <typename F>
+int for_plane_chunks(size_t nplanes, F f) {
+    for (size_t p0 = 0; p0 < nplanes; p0 += 32768) {
+        size_t cnt = nplanes - p0 < 32768 ? nplanes - p0 : 32768;
+        f((int) p0, (unsigned) cnt);
+    }
+    return 0;
+}
+
+}  // namespace
+
+int launch_dwt_forward(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
+                       uint32_t filt, int *d_ovf, cudaStream_t st, LaunchStats &ls) {
+    uint32_t lw = w, lh = h;
+    const size_t ps = (size_t) w * h;
+    int16_t *A = reinterpret_cast<int16_t *>(planes), *B = reinterpret_cast<int16_t *>(tmp);
+    for (uint32_t s = 0; s < stages; s++) {
+        for_plane_chunks(nplanes, [&](int p0, unsigned cnt) {
+            dim3 blk(64, 4);
+            dim3 g1(((lw + 1) / 2 + 63) / 64, (lh + 3) / 4, cnt);
+            k_fwd_pass<false><<<g1, blk, 0, st>>>(A, B, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, d_ovf);
+            dim3 g2((lw + 63) / 64, ((lh + 1) / 2 + 3) / 4, cnt);
+            k_fwd_pass<true><<<g2, blk, 0, st>>>(B, A, (int) lh, (int) lw, (int) w, ps, (int) filt, p0, d_ovf);
+            ls.launches += 2;
+        });
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+
+int launch_dwt_inverse(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
+                       uint32_t filt, bool clamp_negative, cudaStream_t st, LaunchStats &ls) {
+    const size_t ps = (size_t) w * h;
+    int16_t *A = reinterpret_cast<int16_t *>(planes), *B = reinterpret_cast<int16_t *>(tmp);
+    const bool parallel = (filt == ICER_FILTER_A);
+    for (int s = (int) stages - 1; s >= 0; s--) {
+        const uint32_t lw = (uint32_t) dim_low(w, s), lh = (uint32_t) dim_low(h, s);
+        const bool clamp = clamp_negative && s == 0;
+        for_plane_chunks(nplanes, [&](int p0, unsigned cnt) {
+            if (parallel) {
+                dim3 blk(64, 4);
+                dim3 g1((lw + 63) / 64, ((lh + 1) / 2 + 3) / 4, cnt);
+                k_inv_pass_par<true, false><<<g1, blk, 0, st>>>(A, B, (int) lh, (int) lw, (int) w, ps, (int) filt, p0);
+                dim3 g2(((lw + 1) / 2 + 63) / 64, (lh + 3) / 4, cnt);
+                if (clamp) k_inv_pass_par<false, true><<<g2, blk, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0);
+                else k_inv_pass_par<false, false><<<g2, blk, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0);
+            } else {
+                dim3 g1((lw + 127) / 128, 1, cnt);
+                k_inv_pass_ser<true, false><<<g1, 128, 0, st>>>(A, B, (int) lh, (int) lw, (int) w, ps, (int) filt, p0);
+                dim3 g2((lh + 127) / 128, 1, cnt);
+                if (clamp) k_inv_pass_ser<false, true><<<g2, 128, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0);
+                else k_inv_pass_ser<false, false><<<g2, 128, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0);
+            }
+            ls.launches += 2;
+        });
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+
+int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
+                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls) {
+    const size_t ps = (size_t) w * h;
+    k_ll_mean<<<(unsigned) nplanes, 256, 0, st>>>(planes, ps, (int) w, (int) llw, (int) llh, d_mean, d_ovf);
+    const size_t count = ps * nplanes;
+    unsigned blocks = (unsigned) ((count / 8 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks == 0) blocks = 1;
+    k_to_signmag<<<blocks, 256, 0, st>>>(planes, count);
+    ls.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+
+int launch_from_signmag_add_mean(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
+                                 const uint16_t *d_mean, cudaStream_t st, LaunchStats &ls) {
+    const size_t ps = (size_t) w * h;
+    for (size_t p0 = 0; p0 < nplanes; p0 += 32768) {
+        unsigned cnt = (unsigned) (nplanes - p0 < 32768 ? nplanes - p0 : 32768);
+        unsigned bx = (unsigned) ((ps + 255) / 256);
+        if (bx > 256) bx = 256;
+        k_from_signmag<<<dim3(bx, cnt), 256, 0, st>>>(planes + p0 * ps, ps, ps, (int) w, (int) llw, (int) llh, d_mean + p0);
+        ls.launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}

@@ -1,0 +1,99 @@
+/*
+ * icer_b200.h -- batch extension of the drop-in C ABI (libicer_b200.so).
+ *
+ * lib_icer's per-image entry points (include/icer.h) are synchronous and single-frame; throughput on a
+ * B200 needs thousands of independent frames in flight.  These calls are what a reference-side binding
+ * would use for batches; the seven legacy entry points are thin wrappers around them with n = 1.
+ *
+ * Plain C ABI: pointers, sizes and PODs only -- no CUDA or torch types in the signatures (`stream` is an
+ * opaque cudaStream_t passed as void*, NULL = the default stream).
+ *
+ * Reference interfaces replaced (lib_icer/inc/icer.h):
+ *   icer_b200_compress_batch_u16    <- icer_compress_image_uint16 :440, icer_compress_image_yuv_uint16 :442
+ *   icer_b200_decompress_batch_u16  <- icer_decompress_image_uint16 :461, icer_decompress_image_yuv_uint16 :463
+ *   icer_b200_set_limits            <- compile-time ICER_BITPLANES_TO_COMPRESS_16 / ICER_MAX_DECOMP_STAGES /
+ *                                      ICER_MAX_PACKETS_16 (:29-46)
+ */
+#ifndef ICER_B200_H
+#define ICER_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct icer_b200_ctx icer_b200_ctx;
+
+/* where the caller's buffers live */
+enum { ICER_B200_MEM_HOST = 0, ICER_B200_MEM_DEVICE = 1 };
+
+typedef struct {
+    uint32_t width, height;
+    uint32_t channels;      /* 1 = gray, 3 = planar Y,U,V (same size) */
+    uint32_t stages;        /* wavelet decomposition stages */
+    uint32_t filter;        /* enum icer_filter_types */
+    uint32_t segments;      /* error-containment segments per subband, 1..32 */
+    uint64_t byte_quota;    /* per frame, same meaning as icer_init_output_struct's byte_quota */
+} icer_b200_params;
+
+/* Create / destroy a codec context bound to one CUDA device (device < 0: the current device).  A context
+ * owns its device workspace and cached plans; it is not thread-safe (use one per host thread / rank). */
+int icer_b200_create(icer_b200_ctx **ctx, int device);
+void icer_b200_destroy(icer_b200_ctx *ctx);
+
+/* Run-time equivalents of the reference's compile-time limits.  planes: bit planes coded (1..15, default 9);
+ * max_stages default 6; max_packets default 800.  Pass 0 to keep a value. */
+int icer_b200_set_limits(icer_b200_ctx *ctx, int planes, int max_stages, int max_packets);
+
+/* Per-stream payload scratch budget in bits per pixel per plane (default 3).  If any stream needs more the
+ * encoder transparently retries with a doubled budget; this knob exists so tests can exercise that path. */
+int icer_b200_set_scratch_bits(icer_b200_ctx *ctx, int bits_per_px_plane);
+
+/*
+ * Encode n frames.
+ *   frames      [n][channels][height][width] uint16 (host or device per `mem`); NOT modified
+ *   out         [n][out_stride] bytes; frame i's rearranged stream (the bytes lib_icer leaves at
+ *               rearrange_start) is written at out + i*out_stride; out_stride >= byte_quota
+ *   out_prio    optional (NULL to skip): same layout, the priority-ordered stream (lib_icer's data_start)
+ *   coefs       optional (NULL to skip): [n][channels][height][width] uint16, receives what lib_icer leaves in
+ *               the caller's image buffer (LL-mean-removed sign-magnitude wavelet coefficients)
+ *   size_used   [n] uint64, rc [n] int32 (enum icer_status per frame; ICER_BYTE_QUOTA_EXCEEDED = normal lossy)
+ * All pointers live in the memory space `mem`.  Returns ICER_RESULT_OK or a call-level error.
+ * With device memory the call is asynchronous on `stream` unless a scratch retry is needed.
+ */
+int icer_b200_compress_batch_u16(icer_b200_ctx *ctx, const icer_b200_params *p, const uint16_t *frames, size_t n,
+                                 uint8_t *out, size_t out_stride, uint8_t *out_prio, uint16_t *coefs,
+                                 uint64_t *size_used, int32_t *rc, int mem, void *stream);
+
+/*
+ * Decode n streams produced with the same (channels, stages, filter, segments); width/height of `p` give the
+ * capacity of each output slot (pixels per channel = width*height); the actual dimensions come from the
+ * stream headers like in lib_icer and are returned in dims.
+ *   streams     [n][stream_stride] bytes, stream i occupies stream_len[i] bytes
+ *   frames      [n][channels][height*width] uint16 output
+ *   dims        [n][2] uint32 (w, h) from the headers;  rc [n] int32
+ */
+int icer_b200_decompress_batch_u16(icer_b200_ctx *ctx, const icer_b200_params *p, const uint8_t *streams,
+                                   size_t stream_stride, const uint64_t *stream_len, size_t n, uint16_t *frames,
+                                   uint32_t *dims, int32_t *rc, int mem, void *stream);
+
+/* Wavelet transform only (parity hook for icer_wavelet_transform_stages_uint16 :446 / inverse :468) over a
+ * batch of [n][height][width] planes, in place.  rc[n] receives ICER_INTEGER_OVERFLOW per plane (forward). */
+int icer_b200_dwt_batch_u16(icer_b200_ctx *ctx, uint16_t *planes, size_t n, uint32_t width, uint32_t height,
+                            uint32_t stages, uint32_t filter, int inverse, int32_t *rc, int mem, void *stream);
+
+/* Number of kernels launched by this context so far (bench.py's gpu_launches), and the elapsed device time of
+ * the last batch call's named phase in milliseconds (measured with CUDA events on the call's stream):
+ * phase 0 = whole call, 1 = wavelet, 2 = entropy coder kernel, 3 = assemble/parse. */
+uint64_t icer_b200_launch_count(const icer_b200_ctx *ctx);
+float icer_b200_last_phase_ms(const icer_b200_ctx *ctx, int phase);
+/* enable/disable phase timing (adds event records + one sync at the end of each batch call) */
+void icer_b200_enable_timing(icer_b200_ctx *ctx, int on);
+
+const char *icer_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

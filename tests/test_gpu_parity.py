@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, must be bit-exact against the CPU oracle
+(oracle/liboracle.so), the committed golden vectors (generated from the unmodified reference) and -- when the
+prebuilt oracle/_ref/*.so travelled to the box -- the reference itself.  Integer work: the bar is equality."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import harness
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))["cases"]
+
+
+def md5(b):
+    return hashlib.md5(bytes(b)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ctx9():
+    import icer_compression_b200 as icer
+    c = icer.IcerB200(device=0, planes=9, max_stages=6)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx15():
+    import icer_compression_b200 as icer
+    c = icer.IcerB200(device=0, planes=15, max_stages=7)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def legacy():
+    import icer_compression_b200 as icer
+    return icer.LegacyAPI()
+
+
+def case_input(c, orc):
+    from test_oracle_vs_ref import case_input as ci
+    return ci(c, orc)
+
+
+# ---- wavelet -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("filt", range(7))
+def test_dwt_forward_inverse_vs_oracle(filt, ctx9, oracle9):
+    rng = np.random.default_rng(200 + filt)
+    for (w, h, st) in ((64, 48, 3), (37, 53, 2), (5, 5, 1), (129, 65, 5), (96, 96, 5), (200, 7, 1), (512, 512, 6), (301, 203, 5)):
+        imgs = np.stack([rng.integers(0, 256, (h, w)).astype(np.uint16),
+                         rng.integers(0, 4096, (h, w)).astype(np.uint16),
+                         rng.integers(0, 65536, (h, w)).astype(np.uint16)])
+        rc, out = ctx9.dwt_batch(imgs, st, filt)
+        for i in range(3):
+            orc_rc, o = oracle9.dwt_forward(imgs[i], st, filt)
+            assert rc[i] == orc_rc, (w, h, st, i)
+            assert (out[i] == o).all(), (w, h, st, i)
+        rc2, back = ctx9.dwt_batch(out, st, filt, inverse=True)
+        for i in range(3):
+            _, o = oracle9.dwt_inverse(out[i], st, filt)
+            assert (back[i] == o).all(), (w, h, st, i, "inverse")
+
+
+def test_dwt_too_many_stages(ctx9, legacy):
+    img = np.zeros((1, 16, 16), dtype=np.uint16)
+    rc, _ = ctx9.dwt_batch(img, 4, 0)
+    assert rc[0] == harness.TOO_MANY_STAGES
+    assert legacy.dwt_forward(img[0], 4, 0)[0] == harness.TOO_MANY_STAGES
+
+
+# ---- golden vectors through the batch API and the legacy API ------------------------------------------------
+@pytest.mark.parametrize("c", GOLD, ids=[c["name"] for c in GOLD])
+def test_golden_encode_decode(c, ctx9, ctx15, oracle9, oracle15):
+    ctx, orc = (ctx15, oracle15) if c["planes"] == 15 else (ctx9, oracle9)
+    imgs = case_input(c, orc)
+    frames = np.stack(imgs)[None]
+    enc = ctx.compress_batch(frames, c["stages"], c["filt"], c["segments"], c["quota"], want_prio=True, want_coefs=True)
+    assert int(enc["rc"][0]) == c["rc"]
+    assert int(enc["size_used"][0]) == c["size_used"]
+    assert md5(enc["streams"][0]) == c["stream_md5"]
+    assert md5(enc["prio"][0]) == c["prio_md5"]
+    assert md5(enc["coefs"][0].tobytes()) == c["coefs_md5"]
+    dec = ctx.decompress_batch(enc["streams"], c["chan"], c["w"], c["h"], c["stages"], c["filt"], c["segments"])
+    assert int(dec["rc"][0]) == c["dec_rc"]
+    assert tuple(dec["dims"][0]) == (c["w"], c["h"])
+    assert md5(dec["frames"][0].tobytes()) == c["decoded_md5"]
+
+
+def test_golden_streams_decode_only(ctx9):
+    """Streams written by the REFERENCE (committed fixtures) decode to the reference's pixels."""
+    import gzip
+    for c in GOLD:
+        p = os.path.join(HERE, "golden", "streams", c["name"] + ".bin.gz")
+        if not os.path.exists(p):
+            continue
+        s = gzip.open(p, "rb").read()
+        assert md5(s) == c["stream_md5"]
+        dec = ctx9.decompress_batch([s], c["chan"], c["w"], c["h"], c["stages"], c["filt"], c["segments"])
+        assert int(dec["rc"][0]) == 0 and md5(dec["frames"][0].tobytes()) == c["decoded_md5"]
+
+
+def test_legacy_api_boat(legacy, oracle9):
+    """BASELINE config 1 through the drop-in entry points (icer_compress_image_uint16 / icer_decompress_image_uint16)."""
+    boat = harness.load_boat()
+    g = [c for c in GOLD if c["name"] == "boat_s6_g10_A"][0]
+    a = legacy.compress([boat], 6, 0, 10, 262144)
+    assert a["rc"] == 0 and a["size_used"] == g["size_used"] and md5(a["stream"]) == g["stream_md5"]
+    assert md5(a["prio"]) == g["prio_md5"] and md5(a["coefs"][0].tobytes()) == g["coefs_md5"]
+    d = legacy.decompress(a["stream"], 1, 512 * 512, 6, 0, 10)
+    assert d["rc"] == 0 and (d["w"], d["h"]) == (512, 512) and md5(d["images"][0].tobytes()) == g["decoded_md5"]
+    assert (d["images"][0] == boat).all()     # lossless at this quota
+    # too-small output buffer: ICER_BYTE_QUOTA_EXCEEDED like icer_compress.c:461-463
+    assert legacy.decompress(a["stream"], 1, 1000, 6, 0, 10)["rc"] == harness.QUOTA
+
+
+def test_legacy_api_color(legacy):
+    yuv = harness.load_boatcolor_yuv()
+    g = [c for c in GOLD if c["name"] == "boatcolor_s4_g10_A_q70000"][0]
+    a = legacy.compress(yuv, 4, 0, 10, 70000)
+    assert a["rc"] == harness.QUOTA and a["size_used"] == g["size_used"] and md5(a["stream"]) == g["stream_md5"]
+    d = legacy.decompress(a["stream"], 3, 512 * 512, 4, 0, 10)
+    assert d["rc"] == 0 and md5(b"".join(i.tobytes() for i in d["images"])) == g["decoded_md5"]
+
+
+# ---- randomised shapes / parameters vs the oracle -----------------------------------------------------------
+def test_random_images_vs_oracle(ctx9, oracle9):
+    rng = np.random.default_rng(11)
+    done = 0
+    for it in range(200):
+        w, h = int(rng.integers(5, 140)), int(rng.integers(5, 140))
+        stages = int(rng.integers(1, 6))
+        if -(-w // (1 << stages)) < 3 or -(-h // (1 << stages)) < 3:
+            continue
+        segments = int(rng.integers(1, 33))
+        hw, hh = (-(-w // (1 << (stages - 1)))) // 2, (-(-h // (1 << (stages - 1)))) // 2
+        if segments > hw * hh:
+            continue
+        filt = int(rng.integers(0, 7))
+        chan = 3 if it % 4 == 0 else 1
+        kind = it % 3
+        if kind == 0:
+            imgs = [rng.integers(0, 256, (h, w)).astype(np.uint16) for _ in range(chan)]
+        elif kind == 1:
+            base = np.add.outer(np.arange(h) * 2, np.arange(w) * 3) % 200
+            imgs = [(base + rng.integers(0, 6, (h, w))).astype(np.uint16) for _ in range(chan)]
+        else:
+            imgs = [rng.integers(0, 4096, (h, w)).astype(np.uint16) for _ in range(chan)]
+        quota = int(rng.choice([40, 500, 3000, w * h * chan, 4 * w * h * chan]))
+        key = (w, h, stages, segments, filt, chan, quota)
+        a = oracle9.compress(imgs, stages, filt, segments, quota)
+        b = ctx9.compress_batch(np.stack(imgs)[None], stages, filt, segments, quota, want_prio=True, want_coefs=True)
+        assert a["rc"] == int(b["rc"][0]), key
+        assert a["size_used"] == int(b["size_used"][0]), key
+        assert a["stream"] == b["streams"][0] and a["prio"] == b["prio"][0], key
+        if a["rc"] in (0, -5):
+            assert all((x == y).all() for x, y in zip(a["coefs"], b["coefs"][0])), key
+            if a["size_used"] > 0:
+                da = oracle9.decompress(a["stream"], chan, w * h, stages, filt, segments)
+                db = ctx9.decompress_batch([a["stream"]], chan, w, h, stages, filt, segments)
+                assert da["rc"] == int(db["rc"][0]), key
+                assert all((x.ravel() == y).all() for x, y in zip(da["images"], db["frames"][0])), key
+        done += 1
+    assert done > 60
+
+
+def test_batch_of_frames_vs_oracle(ctx9, oracle9):
+    """A batch of different frames in one call: every stream equals the oracle's single-image result."""
+    n = 12
+    frames = np.stack([oracle9.synth(256, 256, f, 20260922 + 2, f % 2) for f in range(n)])[:, None]
+    quota = 256 * 256
+    enc = ctx9.compress_batch(frames, 5, 0, 10, quota)
+    for i in range(n):
+        o = oracle9.compress([frames[i, 0]], 5, 0, 10, quota)
+        assert o["rc"] == int(enc["rc"][i]) and o["stream"] == enc["streams"][i], i
+    dec = ctx9.decompress_batch(enc["streams"], 1, 256, 256, 5, 0, 10)
+    for i in range(n):
+        o = oracle9.decompress(enc["streams"][i], 1, 256 * 256, 5, 0, 10)
+        assert int(dec["rc"][i]) == 0 and (dec["frames"][i, 0] == o["images"][0].ravel()).all(), i
+
+
+def test_scratch_retry_path(oracle9):
+    """Force the payload scratch to be too small: the encoder must retry transparently and still be bit-exact."""
+    import icer_compression_b200 as icer
+    c = icer.IcerB200(device=0)
+    c.set_scratch_bits(1)
+    fr = oracle9.synth(128, 128, 1, 7, 1)   # noise: > 1 bit / pixel / plane in the low planes
+    enc = c.compress_batch(fr[None, None], 3, 0, 6, 2 * 128 * 128)
+    o = oracle9.compress([fr], 3, 0, 6, 2 * 128 * 128)
+    assert o["stream"] == enc["streams"][0]
+    c.close()
+
+
+def test_corrupted_and_truncated_streams(ctx9, oracle9):
+    img = harness.load_boat()[:128, :160].copy()
+    s = bytearray(oracle9.compress([img], 3, 0, 5, 128 * 160)["stream"])
+    rng = np.random.default_rng(3)
+    variants = [bytes(s[: len(s) // 2]), bytes(s[: len(s) - 7]), bytes(s[100:])]
+    for _ in range(6):
+        t = bytearray(s)
+        for pos in rng.integers(0, len(t), 20):
+            t[pos] ^= int(rng.integers(1, 256))
+        variants.append(bytes(t))
+    dec = ctx9.decompress_batch(variants, 1, 160, 128, 3, 0, 5)
+    for i, v in enumerate(variants):
+        o = oracle9.decompress(v, 1, 128 * 160, 3, 0, 5)
+        assert o["rc"] == int(dec["rc"][i])
+        assert (o["images"][0].ravel() == dec["frames"][i, 0]).all(), i
+
+
+def test_error_codes(ctx9):
+    fr = np.full((1, 1, 64, 64), 65535, dtype=np.uint16)         # wavelet overflow -> ICER_INTEGER_OVERFLOW, nothing written
+    fr[0, 0, ::2, ::2] = 0
+    enc = ctx9.compress_batch(fr, 2, 0, 4, 64 * 64)
+    assert int(enc["rc"][0]) == harness.OVERFLOW and int(enc["size_used"][0]) == 0
+    enc = ctx9.compress_batch(np.zeros((1, 1, 16, 16), dtype=np.uint16), 4, 0, 2, 1000)
+    assert int(enc["rc"][0]) == harness.TOO_MANY_STAGES
+    enc = ctx9.compress_batch(np.zeros((1, 1, 16, 16), dtype=np.uint16), 2, 0, 33, 1000)
+    assert int(enc["rc"][0]) == harness.TOO_MANY_SEGMENTS
+
+
+def test_vs_reference_when_present(ctx9):
+    """If oracle/_ref/libicer_ref.so travelled to this box, compare against the reference itself."""
+    if not harness.have_ref():
+        pytest.skip("oracle/_ref not present")
+    ref = harness.Ref(False)
+    orc = harness.Oracle()
+    fr = orc.synth(512, 512, 9, 20260922 + 2, 0)
+    a = ref.compress([fr], 6, 0, 10, 512 * 512)
+    b = ctx9.compress_batch(fr[None, None], 6, 0, 10, 512 * 512)
+    assert a["rc"] == int(b["rc"][0]) and a["stream"] == b["streams"][0]
+    da = ref.decompress(a["stream"], 1, 512 * 512, 6, 0, 10)
+    db = ctx9.decompress_batch([a["stream"]], 1, 512, 512, 6, 0, 10)
+    assert (da["images"][0].ravel() == db["frames"][0, 0]).all()
