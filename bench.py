@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode throughput of the ICER hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2noise|c3|c4|c5]
+
+A "step" is one pass of the hot path over one batch of synthetic frames: batch ENCODE (forward DWT -> LL mean /
+sign-magnitude -> bit-plane context model + interleaved entropy coder -> segment assembly) followed by batch DECODE
+of the streams just produced (scan -> entropy decoder -> inverse DWT).  The metric is
+    Mpixels/s = frames * W * H / (t_encode + t_decode) / 1e6     (whole job, all ranks).
+`value`  : inputs already resident in HBM, outputs left in HBM (device pointers through the C ABI).
+`e2e`    : the same step through the C ABI with HOST (pinned) buffers; H2D of the frames, D2H of the streams,
+           H2D of the streams and D2H of the decoded frames are all inside the timed region.
+N > 1    : one process per GPU (torchrun), the batch is sharded by frame index -- frames are independent, so there
+           is no data-path collective (weak scaling: every rank encodes+decodes its own `batch` frames); time is the
+           max over ranks of the device-timed region.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/libicer_ref*.so, lib_icer compiled with its own
+-O2 flags) on the box's host cores, one forked worker per core because lib_icer is non-re-entrant.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "c2": dict(desc="batch=1024 512x512 uint8-in-uint16 gray (natural-like synthetic), 6 stages, 10 segments, 9 bit planes, filter A, quota=W*H",
+               batch=1024, w=512, h=512, chan=1, stages=6, segments=10, planes=9, max_stages=6, quota=512 * 512, kind=0, seed=20260922 + 2),
+    "c2noise": dict(desc="batch=1024 512x512 uint8 noise in uint16 gray, 6 stages, 10 segments, 9 bit planes, filter A, quota=2*W*H",
+                    batch=1024, w=512, h=512, chan=1, stages=6, segments=10, planes=9, max_stages=6, quota=2 * 512 * 512, kind=1, seed=20260922 + 2),
+    "c3": dict(desc="batch=1024 512x512 YUV planar uint16, 4 stages, 10 segments, 9 bit planes, filter A, quota=70000 B",
+               batch=1024, w=512, h=512, chan=3, stages=4, segments=10, planes=9, max_stages=6, quota=70000, kind=0, seed=20260922 + 3),
+    "c4": dict(desc="batch=64 4096x4096 12-bit-in-uint16 gray, 7 stages, 10 segments, 15 bit planes, filter A, quota=2*W*H",
+               batch=64, w=4096, h=4096, chan=1, stages=7, segments=10, planes=15, max_stages=7, quota=2 * 4096 * 4096, kind=2, seed=20260922 + 4),
+    "c5": dict(desc="batch=1024/GPU 1024x1024 uint8-in-uint16 gray, 6 stages, 10 segments, 9 bit planes, filter A, quota=W*H",
+               batch=1024, w=1024, h=1024, chan=1, stages=6, segments=10, planes=9, max_stages=6, quota=1024 * 1024, kind=0, seed=20260922 + 5),
+}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU reference leg (the only place bench.py touches oracle/)
+# ---------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    wl, frames_idx, planes15 = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness
+    ref = harness.Ref(planes15)
+    orc = harness.Oracle()
+    imgs = []
+    for f in frames_idx:
+        if wl["chan"] == 1:
+            imgs.append([orc.synth(wl["w"], wl["h"], f, wl["seed"], wl["kind"])])
+        else:
+            imgs.append([orc.synth(wl["w"], wl["h"], f + 1000 * c, wl["seed"], wl["kind"]) for c in range(3)])
+    t_enc = t_dec = 0.0
+    out = []
+    for f, im in zip(frames_idx, imgs):
+        t0 = time.perf_counter()
+        enc = ref.compress(im, wl["stages"], 0, wl["segments"], wl["quota"])
+        t1 = time.perf_counter()
+        dec = ref.decompress(enc["stream"], wl["chan"], wl["w"] * wl["h"], wl["stages"], 0, wl["segments"])
+        t2 = time.perf_counter()
+        t_enc += t1 - t0; t_dec += t2 - t1
+        out.append((f, enc["rc"], enc["stream"], b"".join(i.tobytes() for i in dec["images"])))
+    return t_enc, t_dec, out
+
+
+def cpu_reference_run(wl, frames_per_core, cores=None, keep=False):
+    """Run the compiled reference on `cores` forked workers, `frames_per_core` frames each.  Returns Mpix/s (all cores)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    planes15 = wl["planes"] == 15
+    jobs = [(wl, list(range(k * frames_per_core, (k + 1) * frames_per_core)), planes15) for k in range(cores)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    px = cores * frames_per_core * wl["w"] * wl["h"]
+    worst = max(r[0] + r[1] for r in res)
+    one_core = sum(r[0] + r[1] for r in res) / cores
+    outs = [o for r in res for o in r[2]] if keep else None
+    return dict(mpix_s=px / worst / 1e6, mpix_s_1core=frames_per_core * wl["w"] * wl["h"] / one_core / 1e6, cores=cores,
+                frames=cores * frames_per_core, wall_s=wall, enc_s=sum(r[0] for r in res) / cores, dec_s=sum(r[1] for r in res) / cores,
+                outs=outs)
+
+
+def frames_per_core_for(wl, target_s=6.0):
+    # ~0.35 us / pixel / plane-pass for encode+decode on one 2 GHz core (512^2 -> ~0.18 s, 4096^2x15 -> ~21 s)
+    est = wl["w"] * wl["h"] * wl["chan"] * wl["planes"] / 9.0 * 0.7e-6
+    return max(1, int(target_s / est))
+
+
+def run_reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    fpc = frames_per_core_for(wl)
+    vals = []
+    for it in range(args.warmup + args.steps):
+        r = cpu_reference_run(wl, fpc)
+        if it >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["mpix_s"] for r in vals]))
+    px = vals[0]["frames"] * wl["w"] * wl["h"]
+    line = {"impl": "reference", "metric": "encode+decode Mpixels/s", "value": round(v, 3), "unit": "Mpixels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * px / (v * 1e6), 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": {"workload": wl["desc"], "sample": "%d frames per step (%d per core)" % (vals[0]["frames"], fpc)},
+            "cpu_baseline": {"value": round(v, 3), "unit": "Mpixels/s", "cores": vals[0]["cores"], "kind": "reference",
+                             "sample": "%d frames of the workload per step, one forked lib_icer worker per core (oracle/_ref)" % vals[0]["frames"],
+                             "one_core_mpix_s": round(float(np.mean([r["mpix_s_1core"] for r in vals])), 3)},
+            "e2e": {"value": round(v, 3), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, wl, rank, world, local_rank):
+    import torch
+    import icer_compression_b200 as icer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = icer.IcerB200(device=local_rank, planes=wl["planes"], max_stages=wl["max_stages"])
+    n, w, h, chan, quota = wl["batch"], wl["w"], wl["h"], wl["chan"], wl["quota"]
+    params = (w, h, chan, wl["stages"], 0, wl["segments"], quota)
+    st = torch.cuda.current_stream().cuda_stream
+
+    frames = torch.empty((n, chan, h, w), dtype=torch.int16, device=dev)
+    if chan == 1:
+        ctx.synth_frames(frames, n, w, h, rank * n, wl["seed"], wl["kind"], st)
+    else:
+        tmp = torch.empty((n, h, w), dtype=torch.int16, device=dev)
+        for c in range(3):   # Y,U,V = generator frames f, f+1000, f+2000
+            ctx.synth_frames(tmp, n, w, h, rank * n + 1000 * c, wl["seed"], wl["kind"], st)
+            frames[:, c] = tmp
+        del tmp
+    out = torch.empty((n, quota), dtype=torch.uint8, device=dev)
+    used = torch.zeros(n, dtype=torch.int64, device=dev)
+    rc = torch.zeros(n, dtype=torch.int32, device=dev)
+    dec = torch.empty((n, chan, h * w), dtype=torch.int16, device=dev)
+    dims = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+    drc = torch.zeros(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        ctx.compress_batch_raw(params, frames, n, out, quota, None, None, used, rc, icer.MEM_DEVICE, st)
+        ctx.decompress_batch_raw(params, out, quota, used, n, dec, dims, drc, icer.MEM_DEVICE, st)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ctx.enable_timing(True)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    kern_enc_ms, kern_dec_ms, enc_dwt_ms = [], [], []
+    ev[0].record()
+    for k in range(args.steps):
+        ctx.compress_batch_raw(params, frames, n, out, quota, None, None, used, rc, icer.MEM_DEVICE, st)
+        ev[2 * k + 1].record()
+        kern_enc_ms.append(ctx.phase_ms(2)); enc_dwt_ms.append(ctx.phase_ms(1))
+        ctx.decompress_batch_raw(params, out, quota, used, n, dec, dims, drc, icer.MEM_DEVICE, st)
+        ev[2 * k + 2].record()
+        kern_dec_ms.append(ctx.phase_ms(2))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    enc_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)) / args.steps
+    dec_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)) / args.steps
+    if dist is not None:
+        t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, enc_ms, dec_ms = [float(x) for x in t.tolist()]
+    ms_per_step = total_ms / args.steps
+    px_step = world * n * w * h
+    value = px_step / (ms_per_step * 1e-3) / 1e6
+
+    used_h = used.cpu().numpy()
+    rc_h = rc.cpu().numpy()
+    drc_h = drc.cpu().numpy()
+    stream_bytes = int(used_h.sum())
+    ok_frames = int(((rc_h == 0) | (rc_h == -5)).sum())
+
+    # ---- round trip sanity on the device results (lossless workloads decode to the input) ---------------------
+    roundtrip = None
+    if (rc_h == 0).all() and wl["planes"] >= 9 and wl["kind"] in (0,):
+        roundtrip = bool(torch.equal(dec.view(n, chan, h, w), frames))
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        fh = torch.empty((n, chan, h, w), dtype=torch.int16).pin_memory()
+        fh.copy_(frames)
+        oh = torch.empty((n, quota), dtype=torch.uint8).pin_memory()
+        uh = torch.zeros(n, dtype=torch.int64)
+        rh = torch.zeros(n, dtype=torch.int32)
+        dh = torch.empty((n, chan, h * w), dtype=torch.int16).pin_memory()
+        dimh = torch.zeros((n, 2), dtype=torch.int32)
+        drh = torch.zeros(n, dtype=torch.int32)
+
+        def step_host():
+            ctx.compress_batch_raw(params, fh, n, oh, quota, None, None, uh, rh, icer.MEM_HOST, st)
+            ctx.decompress_batch_raw(params, oh, quota, uh, n, dh, dimh, drh, icer.MEM_HOST, st)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_host()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ksteps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(ksteps):
+            step_host()
+        e1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / ksteps
+        ev_ms = e0.elapsed_time(e1) / ksteps
+        e2e_ms = max(wall_ms, ev_ms)
+        if dist is not None:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        sb = int(uh.sum().item())
+        e2e = {"value": round(px_step / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mpixels/s", "ms_per_step": round(e2e_ms, 3),
+               "h2d_bytes_per_step": int(n * chan * h * w * 2 + n * quota), "d2h_bytes_per_step": int(sb + n * chan * h * w * 2),
+               "note": "host pinned frames -> C ABI -> host streams -> C ABI -> host frames; stream slots are uploaded whole (n*quota), only used bytes come back"}
+        del fh, oh, dh
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (K4 entropy coder) ------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = n * chan * w * h * 2 + stream_bytes            # K4: coefficients read once + streams written once
+    k4_ms = float(np.mean(kern_enc_ms))
+    k7_ms = float(np.mean(kern_dec_ms))
+    ach = alg_bytes / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
+    step_bytes = 2 * (n * chan * w * h * 2 + stream_bytes)       # encode: in + stream ; decode: stream + out
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k_encode_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "encode+decode Mpixels/s", "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": wl["desc"], "frames_per_gpu": n, "parallelism": "frames sharded across %d GPU(s), no data-path collective" % world,
+                   "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (n * chan * w * h * 2 / 1e6),
+                   "timing": "CUDA events on the launching stream, max over ranks"},
+        "encode_mpix_s": round(px_step / (enc_ms * 1e-3) / 1e6, 2), "decode_mpix_s": round(px_step / (dec_ms * 1e-3) / 1e6, 2),
+        "encode_ms": round(enc_ms, 3), "decode_ms": round(dec_ms, 3),
+        "compressed_bytes_per_step": stream_bytes, "frames_ok": ok_frames, "decode_rc_ok": int((drc_h == 0).sum()),
+        "roundtrip_lossless": roundtrip,
+        "roofline": {"bound": "hbm", "kernel": "k_encode (bit-plane context model + interleaved entropy coder)",
+                     "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5), "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(k4_ms, 3),
+                     "decode_kernel_ms": round(k7_ms, 3), "encode_dwt_ms": round(float(np.mean(enc_dwt_ms)), 3),
+                     "step_frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 5)},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    # ---- CPU baseline on a bounded sample of the same workload + bit-exactness of that sample -------------------
+    if world == 1 and not args.no_cpu:
+        fpc = frames_per_core_for(wl, 5.0)
+        cores = os.cpu_count() or 1
+        while cores * fpc > n and fpc > 1:
+            fpc -= 1
+        cores = min(cores, n)
+        r = cpu_reference_run(wl, fpc, cores=cores, keep=True)
+        # parity: the frames the reference just coded vs what the GPU produced for the same frame indices
+        idx = sorted(o[0] for o in r["outs"])
+        out_h = out[idx].cpu().numpy()
+        dec_h = dec[idx].cpu().numpy()
+        bad = 0
+        for f, rrc, rstream, rdec in r["outs"]:
+            j = idx.index(f)
+            ln = int(used_h[f])
+            if rrc != int(rc_h[f]) or bytes(out_h[j, :ln]) != rstream or dec_h[j].tobytes() != rdec:
+                bad += 1
+        line["cpu_baseline"] = {"value": round(r["mpix_s"], 3), "unit": "Mpixels/s", "cores": r["cores"], "kind": "reference",
+                                "sample": "%d frames of the workload (%d per core), lib_icer compiled -O2 (oracle/_ref), one forked worker per core"
+                                          % (r["frames"], fpc), "one_core_mpix_s": round(r["mpix_s_1core"], 3)}
+        line["parity"] = {"frames_checked": len(r["outs"]), "mismatches": bad, "against": "oracle/_ref (unmodified lib_icer)"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--batch", type=int, default=None, help="override frames per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = dict(WORKLOADS[args.workload or "c2"])
+    if args.batch:
+        wl["batch"] = args.batch
+        wl["desc"] = wl["desc"].replace("batch=1024", "batch=%d" % args.batch)
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank, world)
+    else:
+        run_ours(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

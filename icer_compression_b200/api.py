@@ -73,6 +73,7 @@ def load_library():
     L.icer_b200_enable_timing.argtypes = [vp, C.c_int]
     L.icer_b200_enable_timing.restype = None
     L.icer_b200_version.restype = C.c_char_p
+    L.icer_b200_synth_frames_u16.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
     _LIB = L
     return L
 
@@ -172,6 +173,12 @@ class IcerB200:
         rc = np.zeros(n, dtype=np.int32)
         self.decompress_batch_raw((w, h, chan, stages, filt, segments, 0), buf, stride, lens, n, frames, dims, rc, MEM_HOST)
         return dict(rc=rc, dims=dims, frames=frames)
+
+    def synth_frames(self, dst, n, w, h, first_frame, seed, kind, stream=None):
+        """Fill a DEVICE buffer (torch tensor) with n synthetic planes (bench utility)."""
+        e = self.lib.icer_b200_synth_frames_u16(self.h, _ptr(dst), n, w, h, first_frame, seed, kind, stream)
+        if e != 0:
+            raise IcerError("icer_b200_synth_frames_u16 -> %d" % e)
 
     def dwt_batch(self, planes, stages, filt, inverse=False):
         a = np.ascontiguousarray(planes, dtype=np.uint16).copy()

@@ -91,6 +91,12 @@ float icer_b200_last_phase_ms(const icer_b200_ctx *ctx, int phase);
 /* enable/disable phase timing (adds event records + one sync at the end of each batch call) */
 void icer_b200_enable_timing(icer_b200_ctx *ctx, int on);
 
+/* Benchmark utility: fill n planes of width*height uint16 in DEVICE memory with the deterministic synthetic frames of
+ * SURVEY.md 8(d) (kind 0 natural-like 8-bit, 1 noise 8-bit, 2 natural-like 12-bit, 3 noise 12-bit; plane i is frame
+ * first_frame + i).  Not part of lib_icer's interface. */
+int icer_b200_synth_frames_u16(icer_b200_ctx *ctx, uint16_t *dst_device, size_t n, uint32_t width, uint32_t height,
+                               uint32_t first_frame, uint32_t seed, int kind, void *stream);
+
 const char *icer_b200_version(void);
 
 #ifdef __cplusplus

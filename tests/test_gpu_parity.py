@@ -236,3 +236,39 @@ def test_vs_reference_when_present(ctx9):
     da = ref.decompress(a["stream"], 1, 512 * 512, 6, 0, 10)
     db = ctx9.decompress_batch([a["stream"]], 1, 512, 512, 6, 0, 10)
     assert (da["images"][0].ravel() == db["frames"][0, 0]).all()
+
+
+def test_device_synth_generator_matches_oracle(ctx9, oracle9):
+    """bench.py fills HBM with icer_b200_synth_frames_u16; it must equal the generator the CPU legs use."""
+    import torch
+    for kind, (w, h) in ((0, (96, 64)), (1, (64, 48)), (2, (80, 40)), (3, (33, 17))):
+        t = torch.empty((3, h, w), dtype=torch.int16, device="cuda:0")
+        ctx9.synth_frames(t, 3, w, h, 5, 1234, kind)
+        torch.cuda.synchronize()
+        got = t.cpu().numpy().view(np.uint16)
+        for i in range(3):
+            assert (got[i] == oracle9.synth(w, h, 5 + i, 1234, kind)).all(), (kind, i)
+
+
+def test_device_pointer_api_roundtrip(ctx9, oracle9):
+    """The batch calls with DEVICE pointers (what bench.py's `value` times) agree with the host-pointer calls."""
+    import torch
+    import icer_compression_b200 as icer
+    n, w, h = 6, 128, 96
+    fr = np.stack([oracle9.synth(w, h, f, 77, 0) for f in range(n)])[:, None]
+    host = ctx9.compress_batch(fr, 3, 0, 7, w * h)
+    d_fr = torch.from_numpy(fr.view(np.int16)).cuda()
+    out = torch.zeros((n, w * h), dtype=torch.uint8, device="cuda")
+    used = torch.zeros(n, dtype=torch.int64, device="cuda")
+    rc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ctx9.compress_batch_raw((w, h, 1, 3, 0, 7, w * h), d_fr, n, out, w * h, None, None, used, rc, icer.MEM_DEVICE)
+    torch.cuda.synchronize()
+    for i in range(n):
+        assert bytes(out[i, :int(used[i])].cpu().numpy()) == host["streams"][i]
+    dec = torch.zeros((n, 1, w * h), dtype=torch.int16, device="cuda")
+    dims = torch.zeros((n, 2), dtype=torch.int32, device="cuda")
+    drc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ctx9.decompress_batch_raw((w, h, 1, 3, 0, 7, 0), out, w * h, used, n, dec, dims, drc, icer.MEM_DEVICE)
+    torch.cuda.synchronize()
+    assert (drc.cpu().numpy() == 0).all()
+    assert torch.equal(dec.view(n, 1, h, w), d_fr)     # 8-bit natural-like data is lossless at 9 planes here
