@@ -44,6 +44,13 @@ WORKLOADS = {
 }
 
 
+def usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -123,7 +130,7 @@ def _cpu_worker(args):
 def cpu_reference_run(wl, frames_per_core, cores=None, keep=False):
     """Run the compiled reference on `cores` forked workers, `frames_per_core` frames each.  Returns Mpix/s (all cores)."""
     import multiprocessing as mp
-    cores = cores or os.cpu_count() or 1
+    cores = cores or usable_cores()
     planes15 = wl["planes"] == 15
     jobs = [(wl, list(range(k * frames_per_core, (k + 1) * frames_per_core)), planes15) for k in range(cores)]
     ctx = mp.get_context("fork")
@@ -333,7 +340,7 @@ def run_ours(args, wl, rank, world, local_rank):
     # ---- CPU baseline on a bounded sample of the same workload + bit-exactness of that sample -------------------
     if world == 1 and not args.no_cpu:
         fpc = frames_per_core_for(wl, 5.0)
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         while cores * fpc > n and fpc > 1:
             fpc -= 1
         cores = min(cores, n)
