@@ -443,11 +443,13 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, 
         da.streams = d_streams; da.stream_stride = stream_stride; da.total_bytes = total_bytes;
         da.seg_off = c->segoff.as<uint32_t>(); da.frame_ok = c->frame_ok.as<int32_t>();
         da.work_counter = c->misc.as<unsigned long long>();
+        { const char *dbg = getenv("ICER_B200_DEBUG"); da.debug_flags = dbg ? (uint32_t) atoi(dbg) : 0u; }
         if ((e = launch_decode(da, st, c->ls))) return e;
         ev_record(c, 3, st);
         // 4. from sign-magnitude + LL mean, inverse wavelet, clamp -- per frame of the group (planes are cap_px apart)
         const uint32_t llw = (uint32_t) dim_low(w, p->stages), llh = (uint32_t) dim_low(h, p->stages);
         const bool dense = (size_t) w * h == cap_px;
+        if (da.debug_flags & 4u) continue;   // debug: leave the raw sign-magnitude coefficients in the output
         if (dense && g.second.size() == n) {
             if ((e = launch_from_signmag_add_mean(d_frames, n * chan, w, h, llw, llh, c->mean.as<uint16_t>(), st, c->ls))) return e;
             if ((e = launch_dwt_inverse(d_frames, c->tmp.as<uint16_t>(), n * chan, w, h, p->stages, p->filter, true, st, c->ls))) return e;

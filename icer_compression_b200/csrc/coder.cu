@@ -1,0 +1,891 @@
+// coder.cu -- K4 (bit-plane context model + interleaved entropy ENCODER), K7 (the DECODER) and K5 (segment assembly).
+//
+// Granularity.  lib_icer resets its context model and entropy coder for every (channel, level, subband, bit plane,
+// segment) (icer_partition.c:315-322), so each such STREAM is independent on the encode side.  On the decode side
+// the planes of one segment form a chain (MSB -> LSB, icer_partition.c:427-443), but plane p only needs plane p+1
+// to be a row + 1 pixel ahead (its right/down neighbours are taken at plane p+1, icer_context_modeller.c:510-521).
+//
+// Mapping (both kernels): one LANE per stream; the lanes of a warp are the bit planes of the same few segments, so
+// they walk the same pixels (shared sectors) -- in lockstep for the encoder, as an asynchronous pipeline for the
+// decoder (every tick a lane advances one pixel if the plane above is far enough ahead; positions travel by shfl).
+// Warps fetch work dynamically, largest segments first.
+//
+// Two things keep the SIMT lanes together:
+//   * every pixel is turned into at most three micro-ops (flush-fast-run, magnitude decision, sign decision) that
+//     run through ONE code site for bin selection, ONE for codeword completion and ONE for bit emission;
+//   * the "quiet" fast path: when the 3x3 neighbourhood has no bit at or above the current plane the decision is
+//     (context 0, bit 0); runs of those only bump counters (adaptive counts, Golomb run length) until the next event
+//     (run completes a codeword, probability bin changes, counts rescale), computed in closed form.
+//
+// Reference behaviour restated (lib_icer/src): icer_context_modeller.c:312-602 (contexts, adaptive counts with the
+// discarded-ceil_div rescale), icer_encoding.c:37-189 and icer_decoding.c:46-194 (bin choice, Golomb /
+// variable-to-variable / uncoded bins, 2048-codeword interleave window with forced flush and its decoder mirror),
+// icer_util.c:48-56 (bin cut-offs), icer_partition.c:328-334 + icer_encoding.c:210-234 (segment header, quota).
+#include "common.h"
+
+namespace {
+
+constexpr int NT = 128;   // threads per block (both kernels)
+
+struct DevTables {
+    uint32_t cutoff[16];
+    uint32_t crc[256];
+    uint16_t enc[8][32];       // in_bits | out_bits << 4 | out << 8        (keyed by the gathered input word)
+    uint16_t dec[8][32];       // in_bits | out_bits << 4 | out << 8        (keyed by the received word)
+    uint16_t gol_m[17], gol_l[17], gol_i[17];
+    uint8_t flush[8][9][6];    // pad_word | pad_len << 4
+    uint8_t ctx_hv[45], ctx_hh[25], ctx_sign[25], sign_pred[25];   // icer_config.c:26-67
+};
+__constant__ DevTables c_tab;
+bool g_tables_uploaded = false;
+
+const uint8_t h_ctx_hv[45] = {0, 1, 2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 6, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7,
+                              8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8};
+const uint8_t h_ctx_hh[25] = {0, 3, 6, 8, 8, 1, 4, 7, 8, 8, 2, 5, 7, 8, 8, 2, 5, 7, 8, 8, 2, 5, 7, 8, 8};
+const uint8_t h_ctx_sign[25] = {14, 14, 15, 16, 16, 14, 14, 15, 16, 16, 13, 13, 12, 13, 13, 16, 16, 15, 14, 14, 16, 16, 15, 14, 14};
+const uint8_t h_sign_pred[25] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+int upload_tables() {
+    if (g_tables_uploaded) return ICER_RESULT_OK;
+    const HostTables &h = icer_host_tables();
+    static DevTables d;
+    for (int b = 0; b < 8; b++)
+        for (int v = 0; v < 32; v++) {
+            d.enc[b][v] = (uint16_t) (h.enc[b][v].in_bits | (h.enc[b][v].out_bits << 4) | (h.enc[b][v].out << 8));
+            d.dec[b][v] = (uint16_t) (h.dec[b][v].in_bits | (h.dec[b][v].out_bits << 4) | (h.dec[b][v].out << 8));
+        }
+    memcpy(d.flush, h.flush, sizeof d.flush);
+    for (int b = 0; b < 17; b++) { d.gol_m[b] = h.gol_m[b]; d.gol_l[b] = h.gol_l[b]; d.gol_i[b] = h.gol_i[b]; }
+    for (int b = 0; b < 16; b++) d.cutoff[b] = h.cutoff[b];
+    for (uint32_t n = 0; n < 256; n++) {
+        uint32_t c = n;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        d.crc[n] = c;
+    }
+    memcpy(d.ctx_hv, h_ctx_hv, 45); memcpy(d.ctx_hh, h_ctx_hh, 25);
+    memcpy(d.ctx_sign, h_ctx_sign, 25); memcpy(d.sign_pred, h_sign_pred, 25);
+    CUDA_TRY(cudaMemcpyToSymbol(c_tab, &d, sizeof d));
+    g_tables_uploaded = true;
+    return ICER_RESULT_OK;
+}
+
+// tables every lane needs with divergent indices: staged in shared memory once per block
+struct SmemTables {
+    uint32_t cutoff[16];
+    uint16_t v2v[8][32];
+    uint16_t gol_m[17], gol_l[17], gol_i[17];
+    uint8_t flush[8][9][6];
+    uint8_t ctx_hv[45], ctx_hh[25], ctx_sign[25], sign_pred[25];
+};
+
+__device__ __forceinline__ void load_tables(SmemTables &T, bool decoder) {
+    const int t = threadIdx.x;
+    for (int i = t; i < 8 * 32; i += NT) (&T.v2v[0][0])[i] = decoder ? (&c_tab.dec[0][0])[i] : (&c_tab.enc[0][0])[i];
+    for (int i = t; i < 8 * 9 * 6; i += NT) (&T.flush[0][0][0])[i] = (&c_tab.flush[0][0][0])[i];
+    for (int i = t; i < 45; i += NT) T.ctx_hv[i] = c_tab.ctx_hv[i];
+    for (int i = t; i < 25; i += NT) { T.ctx_hh[i] = c_tab.ctx_hh[i]; T.ctx_sign[i] = c_tab.ctx_sign[i]; T.sign_pred[i] = c_tab.sign_pred[i]; }
+    for (int i = t; i < 17; i += NT) { T.gol_m[i] = c_tab.gol_m[i]; T.gol_l[i] = c_tab.gol_l[i]; T.gol_i[i] = c_tab.gol_i[i]; }
+    for (int i = t; i < 16; i += NT) T.cutoff[i] = c_tab.cutoff[i];
+}
+
+// probability bin: number of cut-offs c with zz * 65536 >= tot * c (icer_util.c:48-56); cut-offs ascend
+__device__ __forceinline__ int bin_of(const SmemTables &T, uint32_t zz, uint32_t tot) {
+    const uint32_t lhs = zz << 16;
+    int bin = 0;
+    if (lhs >= tot * T.cutoff[7]) bin = 8;
+    if (lhs >= tot * T.cutoff[bin + 3]) bin += 4;
+    if (lhs >= tot * T.cutoff[bin + 1]) bin += 2;
+    if (lhs >= tot * T.cutoff[bin]) bin += 1;
+    if (bin == 15 && lhs >= tot * T.cutoff[15]) bin = 16;
+    return bin;
+}
+
+// number of consecutive all-zero decisions, starting at counts (z, tot), that stay in Golomb bin `bin`
+__device__ __forceinline__ uint32_t zeros_in_same_bin(const SmemTables &T, int bin, uint32_t z, uint32_t tot) {
+    if (bin >= 16) return 0x7FFFFFFFu;
+    const uint32_t cut = T.cutoff[bin];
+    const uint32_t num = tot * cut - (z << 16);       // > 0 because the cut-off test for `bin` failed
+    return (num - 1) / (65536u - cut) + 1;
+}
+
+__device__ __forceinline__ int sig(uint32_t v, int plane) { return ((v & 0x7FFF) >> plane) != 0; }
+
+// magnitude context of a pixel of category 0/1/2 (icer_context_modeller.c:355-391)
+__device__ __forceinline__ int mag_context(const SmemTables &T, int cat, int lsb, int sb, uint32_t a0, uint32_t a1, uint32_t a2,
+                                           uint32_t b0, uint32_t b2, uint32_t c0, uint32_t c1, uint32_t c2) {
+    if (cat == 2) return 11;
+    const int prev = lsb + 1;
+    int hh = sig(b0, lsb) + sig(b2, prev);
+    int vv = sig(a1, lsb) + sig(c1, prev);
+    if (cat == 1) return (hh + vv == 0) ? 9 : 10;
+    const int dd = sig(a0, lsb) + sig(a2, lsb) + sig(c0, prev) + sig(c2, prev);
+    if (sb == 1) { const int tmp = hh; hh = vv; vv = tmp; }
+    return (sb == 3) ? T.ctx_hh[(hh + vv) * 5 + dd] : T.ctx_hv[(hh * 3 + vv) * 5 + dd];
+}
+// sign context index into the 5x5 tables (icer_context_modeller.c:404-428)
+__device__ __forceinline__ int sign_index(int lsb, int sb, uint32_t a1, uint32_t b0, uint32_t b2, uint32_t c1) {
+    const int prev = lsb + 1;
+    int shh = 2 - (int) ((b0 >> 15) & sig(b0, lsb)) - (int) ((b2 >> 15) & sig(b2, prev));
+    int svv = 2 - (int) ((a1 >> 15) & sig(a1, lsb)) - (int) ((c1 >> 15) & sig(c1, prev));
+    if (sb == 1) { const int tmp = shh; shh = svv; svv = tmp; }
+    return shh * 5 + svv;
+}
+
+// =========================================================================================================
+// K4: encoder
+// =========================================================================================================
+struct EncSmem {
+    SmemTables T;
+    uint32_t crc[256];
+    uint32_t cnt[17][NT];      // zero << 16 | total, per context
+    uint32_t bseq[17][NT];     // sequence number of the codeword each bin is building
+    uint16_t bstate[17][NT];   // Golomb: zeros counted; custom: input bits gathered (first bit = bit 0)
+    uint8_t bfill[17][NT];     // custom: number of input bits gathered
+};
+
+// Interleave-window bookkeeping.  A codeword gets a sequence number when its first bit arrives (lib_icer: a ring
+// slot, icer_encoding.c:59-67); `head` is the next sequence number to emit.  Everything in [head, oldest open) is
+// complete by construction, so only codewords that complete BEHIND an older open one are parked in the ring.
+struct Enc {
+    EncSmem &S;
+    const int t;
+    uint16_t *ring;
+    uint32_t *out;
+    uint32_t cap, nwords = 0;
+    unsigned long long acc = 0;
+    int nacc = 0;
+    uint32_t crc = 0xFFFFFFFFu;
+    uint32_t head = 0, tail = 0, open_mask = 0;
+    int oldest = 0;
+    bool overflow = false;
+
+    __device__ Enc(EncSmem &s, int tid, uint16_t *r, uint32_t *o, uint32_t c) : S(s), t(tid), ring(r), out(o), cap(c) {}
+
+    __device__ __forceinline__ uint32_t golomb_word(int bin, uint32_t k, uint32_t &nb) {   // icer_encoding.c:72-77
+        const uint32_t i = S.T.gol_i[bin], l = S.T.gol_l[bin];
+        const uint32_t longer = k >= i;
+        nb = l + longer;
+        return __brev(k + (longer ? i : 0)) >> (32 - nb);
+    }
+
+    // codeword of `bin` is complete (single call site in the tick loop)
+    __device__ __forceinline__ void complete(int bin, uint32_t code, uint32_t nb) {
+        const uint32_t seq = S.bseq[bin][t];
+        open_mask &= ~(1u << bin);
+        if (seq != head) {
+            ring[seq & (ICER_RING - 1)] = (uint16_t) ((nb << 11) | code);
+            return;
+        }
+        uint32_t limit = tail;
+        const uint32_t h1 = head + 1;
+        for (uint32_t m = open_mask; m; m &= m - 1) {
+            const int b = __ffs(m) - 1;
+            const uint32_t sq = S.bseq[b][t];
+            if ((int32_t) (sq - h1) < (int32_t) (limit - h1)) { limit = sq; oldest = b; }
+        }
+        for (;;) {   // LSB-first bit packing (icer_encoding.c:114-139), CRC-32 of the payload on the fly
+            acc |= (unsigned long long) code << nacc;
+            nacc += (int) nb;
+            if (nacc >= 32) {
+                const uint32_t wv = (uint32_t) acc;
+                if (nwords < cap) out[nwords] = wv; else overflow = true;
+                nwords++;
+                uint32_t c = crc;
+                c = S.crc[(c ^ wv) & 0xFF] ^ (c >> 8);
+                c = S.crc[(c ^ (wv >> 8)) & 0xFF] ^ (c >> 8);
+                c = S.crc[(c ^ (wv >> 16)) & 0xFF] ^ (c >> 8);
+                c = S.crc[(c ^ (wv >> 24)) & 0xFF] ^ (c >> 8);
+                crc = c;
+                acc >>= 32;
+                nacc -= 32;
+            }
+            head++;
+            if (head == limit) break;
+            const uint32_t v = ring[head & (ICER_RING - 1)];
+            code = v & 0x7FF; nb = v >> 11;
+        }
+    }
+
+    // the word a forced completion gives the oldest codeword (icer_encoding.c:141-189): window full, or end of stream
+    __device__ __forceinline__ uint32_t forced_word(int bin, uint32_t &nb) {
+        if (bin > 7) {
+            const uint32_t k = S.bstate[bin][t];
+            if (k == (uint32_t) S.T.gol_m[bin] - 1) { nb = 1; return 1; }
+            return golomb_word(bin, k, nb);
+        }
+        const uint32_t pre = S.bstate[bin][t], fill = S.bfill[bin][t];
+        const uint32_t fl = S.T.flush[bin][pre][fill];
+        const uint32_t word = (pre | ((fl & 0xF) << fill)) & 0x3FF;
+        const uint32_t e = S.T.v2v[bin][word & 31];
+        nb = (e >> 4) & 0xF;
+        return e >> 8;
+    }
+    // true when `bin` needs a new codeword but 2048 are already outstanding (icer_encoding.c:59-64)
+    __device__ __forceinline__ bool window_full_for(int bin) const {
+        return !((open_mask >> bin) & 1u) && tail - head >= ICER_RING;
+    }
+
+    // make sure `bin` has an open codeword (icer_encoding.c:56-67); the caller has dealt with a full window
+    __device__ __forceinline__ void open_bin(int bin) {
+        if (open_mask & (1u << bin)) return;
+        if (open_mask == 0) oldest = bin;
+        S.bseq[bin][t] = tail++;
+        S.bstate[bin][t] = 0;
+        S.bfill[bin][t] = 0;
+        open_mask |= 1u << bin;
+    }
+
+    __device__ void finish(uint32_t &bits_out, uint32_t &crc_out) {
+        while (open_mask) {                                    // icer_context_modeller.c:452-455
+            uint32_t nb;
+            const int bin = oldest;
+            const uint32_t code = forced_word(bin, nb);
+            complete(bin, code, nb);
+        }
+        bits_out = nwords * 32u + (uint32_t) nacc;
+        const int nbytes = (nacc + 7) >> 3;
+        if (nbytes) {
+            const uint32_t wv = (uint32_t) acc;
+            if (nwords < cap) out[nwords] = wv; else overflow = true;
+            uint32_t c = crc;
+            for (int i = 0; i < nbytes; i++) c = S.crc[(c ^ (wv >> (8 * i))) & 0xFF] ^ (c >> 8);
+            crc = c;
+        }
+        crc_out = ~crc;
+    }
+};
+
+__global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
+    const int t = threadIdx.x;
+    load_tables(S.T, false);
+    for (int i = t; i < 256; i += NT) S.crc[i] = c_tab.crc[i];
+    __syncthreads();
+
+    const uint32_t nstreams = a.nunits * a.planes;
+    const unsigned long long total = (unsigned long long) a.nframes * nstreams;
+    const int lane = t & 31;
+    uint16_t *ring = a.rings + (size_t) (blockIdx.x * NT + t) * ICER_RING;
+    const size_t plane_px = (size_t) a.w * a.h;
+    const int W = (int) a.w;
+
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.work_counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        const unsigned long long sid = base + lane;
+        const bool valid = sid < total;
+        uint32_t frame = 0, s = 0;
+        Unit u;
+        u.x = u.y = u.w = u.h = 0; u.chan = u.level = u.subband = u.seg = 0; u.px = 0;
+        int lsb = 0;
+        if (valid) {
+            frame = (uint32_t) (sid / nstreams); s = (uint32_t) (sid % nstreams);
+            u = a.units[s / a.planes];
+            lsb = (int) (s % a.planes);
+        }
+        const uint16_t *seg = a.coefs + ((size_t) frame * a.chan + u.chan) * plane_px + (size_t) u.y * W + u.x;
+        Enc cd(S, t, ring, valid ? a.scratch + (size_t) frame * a.scratch_words + a.soff[s] : nullptr, valid ? a.scap[s] : 0);
+#pragma unroll
+        for (int c = 0; c < 17; c++) S.cnt[c][t] = (2u << 16) | 4u;    // icer.h:147-148
+        const int sw = u.w, sh = u.h, sb = u.subband;
+        const uint32_t px = valid ? (uint32_t) sw * (uint32_t) sh : 0;
+        uint32_t maxpx = px;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) maxpx = max(maxpx, __shfl_xor_sync(0xffffffffu, maxpx, o));
+
+        int row = 0, col = 0;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
+        uint32_t fz_left = 0, fz_run = 0;    // quiet fast path: zeros still absorbable / absorbed but not yet applied
+        int fz_bin = 0;
+
+        for (uint32_t i = 0; i < maxpx; i++) {
+            if (i < px) {
+                const uint16_t *p = seg + (size_t) row * W + col;
+                const bool up = row > 0, dn = row + 1 < sh, rt = col + 1 < sw;
+                if (col == 0) { a0 = b0 = c0 = 0; a1 = up ? p[-W] : 0; b1 = p[0]; c1 = dn ? p[W] : 0; }
+                a2 = (up && rt) ? p[1 - W] : 0;
+                b2 = rt ? p[1] : 0;
+                c2 = (dn && rt) ? p[1 + W] : 0;
+                const uint32_t v = b1;
+                const bool quiet = ((((a0 | a1 | a2 | b0 | b1 | b2 | c0 | c1 | c2) & 0x7FFF) >> lsb) == 0);
+                // micro-ops: bit0 = apply the pending fast run, bit1 = magnitude decision, bit2 = sign decision
+                uint32_t todo;
+                if (quiet && fz_left) { fz_run++; fz_left--; todo = 0; }
+                else todo = (fz_run ? 1u : 0u) | 2u;
+                int cat = 0;
+                uint32_t mbit = 0;
+                if (todo & 2u) {
+                    const int msb = 31 - __clz((v & 0x7FFF) | 1);
+                    cat = msb - lsb;                                   // icer_context_modeller.c:631-634
+                    cat = cat < 0 ? 0 : (cat > 3 ? 3 : cat);
+                    mbit = (v >> lsb) & 1;
+                    if (cat == 0 && mbit) todo |= 4u;                  // first 1 of this coefficient: its sign follows
+                }
+                while (todo) {
+                    const int st = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    bool done = false;
+                    uint32_t code = 0, nb = 0;
+                    int bin = 0;
+                    if (st == 0) {
+                        // apply `fz_run` (context 0, bit 0) decisions at once
+                        bin = fz_bin;
+                        const uint32_t zt = S.cnt[0][t];
+                        uint32_t z = (zt >> 16) + fz_run, tot = (zt & 0xFFFF) + fz_run;
+                        if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
+                        S.cnt[0][t] = (z << 16) | tot;
+                        const uint32_t k = (uint32_t) S.bstate[bin][t] + fz_run;
+                        if (k >= S.T.gol_m[bin]) { done = true; code = 1; nb = 1; }
+                        else S.bstate[bin][t] = (uint16_t) k;
+                        fz_run = 0; fz_left = 0;
+                    } else {
+                        uint32_t bit;
+                        bool coded = true;
+                        if (st == 1 && cat == 3) {
+                            bit = mbit; bin = 0; coded = false;               // p(0) = 1/2 -> uncoded bin
+                        } else {
+                            int ctx;
+                            if (st == 1) {
+                                ctx = mag_context(S.T, cat, lsb, sb, a0, a1, a2, b0, b2, c0, c1, c2);
+                                bit = mbit;
+                            } else {
+                                const int si = sign_index(lsb, sb, a1, b0, b2, c1);
+                                ctx = S.T.ctx_sign[si];
+                                bit = (S.T.sign_pred[si] ^ (v >> 15)) & 1;
+                            }
+                            const uint32_t zt = S.cnt[ctx][t];
+                            uint32_t z = zt >> 16, tot = zt & 0xFFFF;
+                            uint32_t zz = z;
+                            const bool inv = zz < (tot >> 1);
+                            if (inv) zz = tot - zz;
+                            bin = bin_of(S.T, zz, tot);
+                            if (cd.window_full_for(bin)) {
+                                // window full: force-complete the oldest codeword first, then redo this decision
+                                bin = cd.oldest;
+                                code = cd.forced_word(bin, nb);
+                                done = true;
+                                todo |= 1u << st;
+                                goto emit_site;
+                            }
+                            if (st == 1 && quiet && !inv && bin > 7) {
+                                // enter the quiet fast path: this and the following quiet pixels only bump counters
+                                cd.open_bin(bin);
+                                const uint32_t n1 = (uint32_t) S.T.gol_m[bin] - S.bstate[bin][t];
+                                const uint32_t n2 = zeros_in_same_bin(S.T, bin, z, tot);
+                                const uint32_t n3 = 500u - tot;
+                                fz_left = min(n1, min(n2, n3)) - 1;
+                                fz_run = 1;
+                                fz_bin = bin;
+                                continue;
+                            }
+                            tot++;
+                            z += bit ^ 1u;
+                            if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }   // icer_context_modeller.c:396-402
+                            S.cnt[ctx][t] = (z << 16) | tot;
+                            bit ^= inv ? 1u : 0u;
+                        }
+                        if (!coded && cd.window_full_for(0)) {
+                            bin = cd.oldest;
+                            code = cd.forced_word(bin, nb);
+                            done = true;
+                            todo |= 1u << st;
+                            goto emit_site;
+                        }
+                        cd.open_bin(bin);
+                        if (bin > 7) {                                        // Golomb run-length bins
+                            if (bit) {
+                                code = cd.golomb_word(bin, S.bstate[bin][t], nb);
+                                done = true;
+                            } else {
+                                const uint32_t k = (uint32_t) S.bstate[bin][t] + 1;
+                                S.bstate[bin][t] = (uint16_t) k;
+                                if (k >= S.T.gol_m[bin]) { code = 1; nb = 1; done = true; }
+                            }
+                        } else if (bin != 0) {                                // variable-to-variable bins
+                            const uint32_t fill = S.bfill[bin][t];
+                            const uint32_t word = S.bstate[bin][t] | (bit << fill);
+                            const uint32_t e = S.T.v2v[bin][word & 31];
+                            if ((e & 0xF) == fill + 1) { code = e >> 8; nb = (e >> 4) & 0xF; done = true; }
+                            else { S.bstate[bin][t] = (uint16_t) word; S.bfill[bin][t] = (uint8_t) (fill + 1); }
+                        } else {                                              // uncoded bin
+                            code = bit & 1; nb = 1; done = true;
+                        }
+                    }
+                emit_site:
+                    if (done) cd.complete(bin, code, nb);
+                }
+                a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
+                if (++col == sw) { col = 0; row++; }
+            }
+        }
+        if (valid) {
+            if (fz_run) {   // tail of a fast run
+                const int bin = fz_bin;
+                const uint32_t zt = S.cnt[0][t];
+                (void) zt;
+                const uint32_t k = (uint32_t) S.bstate[bin][t] + fz_run;
+                if (k >= S.T.gol_m[bin]) cd.complete(bin, 1, 1);
+                else S.bstate[bin][t] = (uint16_t) k;
+            }
+            uint32_t bits, crc;
+            cd.finish(bits, crc);
+            a.bits[(size_t) frame * nstreams + s] = bits;
+            a.crc[(size_t) frame * nstreams + s] = crc;
+            if (cd.overflow) atomicOr(a.overflow, 1);
+        }
+        __syncwarp();
+    }
+}
+
+// =========================================================================================================
+// K7: decoder
+// =========================================================================================================
+struct DecSmem {
+    SmemTables T;
+    uint32_t cnt[17][NT];
+    int32_t depth[17][NT];     // pending decoded bits per bin
+    uint32_t stamp[17][NT];    // codeword count when the bin was last refilled
+    uint8_t low[17][NT];       // the low 8 stack positions (nothing above can hold a 1)
+};
+
+struct Dec {
+    DecSmem &S;
+    const int t;
+    const uint8_t *base;        // payload start
+    const uint8_t *end;         // end of the whole stream buffer (reads beyond return 0)
+    uint32_t total_bits = 0;
+    uint32_t consumed = 0;      // bits consumed
+    uint32_t words = 0;         // codewords consumed
+
+    __device__ Dec(DecSmem &s, int tid) : S(s), t(tid), base(nullptr), end(nullptr) {}
+
+    // n <= 16 bits starting `ahead` bits after the cursor, LSB first
+    __device__ __forceinline__ uint32_t bits_at(uint32_t ahead, uint32_t n) const {
+        const uint32_t pos = consumed + ahead;
+        const uint8_t *p = base + (pos >> 3);
+        const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(ad & ~(uintptr_t) 3);
+        // bytes at or beyond `end` read as zero (exactly: the last word may be partial)
+        const ptrdiff_t left = end - reinterpret_cast<const uint8_t *>(wp);
+        uint32_t w0 = 0, w1 = 0;
+        if (left >= 8) { w0 = wp[0]; w1 = wp[1]; }
+        else if (left > 0) {
+            w0 = wp[0];
+            if (left < 4) w0 &= (1u << (8 * (int) left)) - 1u;
+            else if (left > 4) w1 = wp[1] & ((1u << (8 * (int) (left - 4))) - 1u);
+        }
+        const uint32_t sh = (uint32_t) (ad & 3) * 8 + (pos & 7);
+        return __funnelshift_r(w0, w1, sh) & ((1u << n) - 1);
+    }
+    // icer_get_bits_from_codeword / icer_pop_bits_from_codeword (icer_decoding.c:59-105): byte-chunked read that
+    // fails only when a chunk is larger than the whole segment (`decoded_bits_total` is never advanced there)
+    __device__ __forceinline__ int rd(uint32_t n, bool consume) {
+        if (total_bits < 8) {
+            uint32_t off = consumed & 7, left = n;
+            while (left) {
+                uint32_t take = 8 - off; if (take > left) take = left;
+                if (take > total_bits) return ICER_DECODER_OUT_OF_DATA;
+                left -= take; off = (off + take) & 7;
+            }
+        }
+        const int v = (int) bits_at(0, n);
+        if (consume) consumed += n;
+        return v;
+    }
+
+    // refill `bin` with the next codeword (icer_decoding.c:127-181); returns an error code or OK
+    __device__ __forceinline__ int refill(int bin, int &depth, uint32_t &low) {
+        depth = 0; low = 0;
+        if (bin > 7) {
+            const uint32_t l = S.T.gol_l[bin], gi = S.T.gol_i[bin];
+            if (bits_at(0, 1)) {
+                rd(1, true);
+                depth = S.T.gol_m[bin];
+            } else {
+                uint32_t k = (__brev((uint32_t) rd(l, false) & 0xFFFFu) >> (32 - l)) & 0xFFFFu;
+                if (k < gi) {
+                    rd(l, true);
+                } else {
+                    k = (__brev((uint32_t) rd(l + 1, true) & 0xFFFFu) >> (31 - l)) & 0xFFFFu;
+                    k = (k - gi) & 0xFFFFu;
+                }
+                depth = 1 + (int) k;
+                low = 1;
+            }
+        } else if (bin != 0) {
+            uint32_t word = 0, n = 0;
+            bool found = false;
+            do {
+                if (n + 1 >= total_bits) return ICER_DECODER_OUT_OF_DATA;
+                word |= bits_at(n, 1) << n;
+                n++;
+                if (word >= 32) return ICER_DECODED_INVALID_DATA;
+                const uint32_t e = S.T.v2v[bin][word];
+                if ((e & 0xF) == n) {
+                    low = e >> 8;
+                    depth = (int) ((e >> 4) & 0xF);
+                    if ((int) word != rd(n, true)) return ICER_DECODED_INVALID_DATA;
+                    found = true;
+                }
+            } while (!found && n < 10);
+        } else {
+            const int v = rd(1, true);
+            if (v == ICER_DECODER_OUT_OF_DATA) return v;
+            low = v != 0;
+            depth = 1;
+        }
+        words++;
+        S.stamp[bin][t] = words;
+        return ICER_RESULT_OK;
+    }
+};
+
+// One warp decodes `cpw` chains at a time; lane = chain_slot * planes + (planes-1 - lsb).
+__global__ void __launch_bounds__(NT, 4) k_decode(DecodeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecSmem &S = *reinterpret_cast<DecSmem *>(smem_raw);
+    const int t = threadIdx.x;
+    load_tables(S.T, true);
+    __syncthreads();
+
+    const int lane = t & 31;
+    const int P = (int) a.planes;
+    const int cpw = 32 / P;                         // chains per warp
+    const int slot = lane / P, j = lane % P;        // j = 0 is the most significant plane
+    const bool lane_used = slot < cpw;
+    const int lsb = P - 1 - j;
+    const unsigned long long total = (unsigned long long) a.nframes * a.nunits;
+    const uint32_t nstreams = a.nunits * a.planes;
+    const uint8_t *buf_end = a.streams + a.total_bytes;
+    const int W = (int) a.plan_w;
+
+    for (;;) {
+        unsigned long long basei = 0;
+        if (lane == 0) basei = atomicAdd(a.work_counter, (unsigned long long) cpw);
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (basei >= total) break;
+        const unsigned long long cid = basei + (unsigned) slot;
+        bool present = false;
+        Unit u;
+        u.x = u.y = u.w = u.h = 0; u.chan = u.level = u.subband = u.seg = 0; u.px = 0;
+        uint32_t frame = 0;
+        Dec dc(S, t);
+        if (lane_used && cid < total) {
+            frame = (uint32_t) (cid / a.nunits);
+            const uint32_t ui = (uint32_t) (cid % a.nunits);
+            if (a.frame_ok[frame]) {
+                u = a.units[ui];
+                const uint32_t off = a.seg_off[(size_t) frame * nstreams + ui * a.planes + lsb];
+                if (off != 0xFFFFFFFFu) {
+                    const uint8_t *hd = a.streams + (size_t) frame * a.stream_stride + off;
+                    present = true;
+                    dc.total_bits = hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24);
+                    dc.base = hd + ICER_HDR_BYTES;
+                    dc.end = buf_end;
+                }
+            }
+        }
+        // a plane is decoded only if every plane above it is present (icer_partition.c:431)
+        const uint32_t pres_mask = __ballot_sync(0xffffffffu, present);
+        const uint32_t grp = ((P >= 32) ? 0xFFFFFFFFu : ((1u << P) - 1u)) << (slot * P);
+        const uint32_t missing = ~pres_mask & grp & ((1u << lane) - 1u);      // missing planes above me in my chain
+        bool alive = present && missing == 0 && lane_used;
+
+        uint16_t *seg = a.coefs + ((size_t) frame * a.chan + u.chan) * a.cap_px + (size_t) u.y * W + u.x;
+        const int sw = u.w, sh = u.h, sb = u.subband;
+        const uint32_t px = alive ? (uint32_t) sw * (uint32_t) sh : 0;
+        const uint32_t lag = (uint32_t) sw + 1;      // plane p may run at most this far behind plane p+1
+#pragma unroll
+        for (int c = 0; c < 17; c++) { S.cnt[c][t] = (2u << 16) | 4u; S.depth[c][t] = 0; S.stamp[c][t] = 0; S.low[c][t] = 0; }
+
+        uint32_t pos = 0;
+        int row = 0, col = 0;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
+        uint32_t fz_left = 0, fz_run = 0;
+        int fz_bin = 0;
+        int err = 0;                 // this plane hit a decode error: it stops, the planes below are void
+        bool dead = false;           // a plane above hit an error
+
+        for (;;) {
+            // progress of the plane above (lane - 1 of the same chain)
+            const uint32_t up_pos = __shfl_up_sync(0xffffffffu, pos, 1);
+            const int up_err = __shfl_up_sync(0xffffffffu, (err != 0 || dead) ? 1 : 0, 1);
+            const uint32_t up_px = __shfl_up_sync(0xffffffffu, px, 1);
+            if (j > 0 && up_err) dead = true;
+            uint32_t limit = px;
+            if (j > 0 && up_pos < up_px) limit = (a.debug_flags & 2u) ? 0u : (up_pos > lag ? up_pos - lag : 0);
+            const bool running = alive && !dead && err == 0 && pos < px;
+            if (!__any_sync(0xffffffffu, running)) break;
+            if (running && pos < limit) {
+                uint16_t *p = seg + (size_t) row * W + col;
+                const bool up = row > 0, dn = row + 1 < sh, rt = col + 1 < sw;
+                if (col == 0) { a0 = b0 = c0 = 0; a1 = up ? p[-W] : 0; b1 = p[0]; c1 = dn ? p[W] : 0; }
+                a2 = (up && rt) ? p[1 - W] : 0;
+                b2 = rt ? p[1] : 0;
+                c2 = (dn && rt) ? p[1 + W] : 0;
+                uint32_t v = b1;
+                const bool quiet = ((((a0 | a1 | a2 | b0 | b1 | b2 | c0 | c1 | c2) & 0x7FFF) >> lsb) == 0);
+                uint32_t todo;
+                if (quiet && fz_left) { fz_run++; fz_left--; todo = 0; }
+                else todo = (fz_run ? 1u : 0u) | 2u;
+                int cat = 0;
+                if (todo & 2u) {
+                    const int msb = 31 - __clz((v & 0x7FFF) | 1);
+                    cat = msb - lsb;
+                    cat = cat < 0 ? 0 : (cat > 3 ? 3 : cat);
+                }
+                bool changed = false;
+                while (todo) {
+                    const int st = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    if (st == 0) {
+                        const int bin = fz_bin;
+                        const uint32_t zt = S.cnt[0][t];
+                        uint32_t z = (zt >> 16) + fz_run, tot = (zt & 0xFFFF) + fz_run;
+                        if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
+                        S.cnt[0][t] = (z << 16) | tot;
+                        S.depth[bin][t] -= (int) fz_run;
+                        fz_run = 0; fz_left = 0;
+                        continue;
+                    }
+                    int bin, ctx = -1, si = 0;
+                    bool inv = false;
+                    uint32_t z = 0, tot = 0;
+                    if (st == 1 && cat == 3) {
+                        bin = 0;
+                    } else {
+                        if (st == 1) ctx = mag_context(S.T, cat, lsb, sb, a0, a1, a2, b0, b2, c0, c1, c2);
+                        else { si = sign_index(lsb, sb, a1, b0, b2, c1); ctx = S.T.ctx_sign[si]; }
+                        const uint32_t zt = S.cnt[ctx][t];
+                        z = zt >> 16; tot = zt & 0xFFFF;
+                        uint32_t zz = z;
+                        inv = zz < (tot >> 1);
+                        if (inv) zz = tot - zz;
+                        bin = bin_of(S.T, zz, tot);
+                    }
+                    // next decoded bit of `bin` (icer_decoding.c:127, :186-192)
+                    int depth = S.depth[bin][t];
+                    uint32_t low = S.low[bin][t];
+                    if (depth <= 0 || dc.words - S.stamp[bin][t] >= ICER_RING) {
+                        const int rc = dc.refill(bin, depth, low);
+                        if (rc != ICER_RESULT_OK) { err = rc; todo = 0; break; }
+                    }
+                    if (st == 1 && quiet && !inv && bin > 7 && !(a.debug_flags & 1u)) {
+                        // quiet fast path: the run of pending zeros of this Golomb bin is taken without touching the stack
+                        const uint32_t zeros = (uint32_t) depth - (low & 1u);
+                        if (zeros > 0) {
+                            const uint32_t n2 = zeros_in_same_bin(S.T, bin, z, tot);
+                            const uint32_t n3 = 500u - tot;
+                            S.depth[bin][t] = depth; S.low[bin][t] = (uint8_t) low;
+                            fz_left = min(zeros, min(n2, n3)) - 1;
+                            fz_run = 1;
+                            fz_bin = bin;
+                            continue;
+                        }
+                    }
+                    const int top = depth - 1;
+                    uint32_t b = 0;
+                    if (top >= 0 && top < 8) { b = (low >> top) & 1u; low &= ~(1u << top); }
+                    S.depth[bin][t] = depth - 1;
+                    S.low[bin][t] = (uint8_t) low;
+                    const uint32_t bit = inv ? (b ^ 1u) : b;
+                    if (ctx >= 0) {
+                        tot++;
+                        z += bit ^ 1u;
+                        if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
+                        S.cnt[ctx][t] = (z << 16) | tot;
+                    }
+                    if (st == 1) {
+                        if (bit) { v |= 1u << lsb; changed = true; if (cat == 0) todo |= 4u; }
+                    } else {
+                        if ((bit ^ S.T.sign_pred[si]) & 1u) { v |= 0x8000u; changed = true; }
+                    }
+                }
+                if (changed) { *p = (uint16_t) v; b1 = v; }      // also stores the magnitude bit when the sign read failed
+                if (err == 0) {
+                    a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
+                    if (++col == sw) { col = 0; row++; }
+                    pos++;
+                }
+            }
+            __syncwarp();
+        }
+        // A decode error voids every plane below it (lib_icer stops the chain there and never decodes them,
+        // icer_partition.c:441).  Those planes ran ahead in the pipeline: take their bits back.
+        const uint32_t err_mask = __ballot_sync(0xffffffffu, err != 0);
+        if (err_mask) {
+            if (dead && alive) {
+                for (uint32_t n = 0; n < pos; n++) {
+                    uint16_t *q = seg + (size_t) (n / (uint32_t) sw) * W + (n % (uint32_t) sw);
+                    *q = (uint16_t) (*q & ~(1u << lsb));
+                }
+            }
+            __syncwarp();
+            // a sign bit set by a voided plane belongs to a coefficient whose magnitude is now zero
+            const uint32_t dead_mask = __ballot_sync(0xffffffffu, dead && alive);
+            const uint32_t mine = dead_mask & grp;
+            if (mine && lane == __ffs(mine) - 1) {
+                const uint32_t npx = (uint32_t) sw * (uint32_t) sh;
+                for (uint32_t n = 0; n < npx; n++) {
+                    uint16_t *q = seg + (size_t) (n / (uint32_t) sw) * W + (n % (uint32_t) sw);
+                    if ((*q & 0x7FFF) == 0) *q = 0;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// =========================================================================================================
+// K5: quota scan, then gather of header + payload into the output streams
+// =========================================================================================================
+
+// One thread per frame walks the streams in priority order with lib_icer's quota rule (SURVEY A.14;
+// icer_encoding.c:211-214, :133-135; icer_partition.c:323-326).  Then a second walk in rearranged order assigns
+// the offsets of the final stream.
+__global__ void k_quota_scan(AssembleArgs a) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.nframes) return;
+    int rc = a.plan_status;
+    for (uint32_t c = 0; c < a.chan && rc == ICER_RESULT_OK; c++)
+        if (a.ovf[(size_t) f * a.chan + c]) rc = ICER_INTEGER_OVERFLOW;
+    const uint32_t *bits = a.bits + (size_t) f * a.nstreams;
+    uint64_t *offp = a.off_prio + (size_t) f * a.nstreams;     // indexed by STREAM ID; ~0 = dropped
+    uint64_t used = 0;
+    uint32_t kept = 0;
+    if (rc == ICER_RESULT_OK) {
+        for (uint32_t i = 0; i < a.nstreams; i++) {
+            const uint32_t s = a.prio[i];
+            const uint32_t nb = bits[s];
+            const uint64_t room = a.quota - used;
+            if (room < ICER_HDR_BYTES) { rc = ICER_BYTE_QUOTA_EXCEEDED; break; }
+            if (nb > 0 && (uint64_t) (nb >> 3) >= room - ICER_HDR_BYTES) { rc = ICER_BYTE_QUOTA_EXCEEDED; break; }
+            offp[s] = used;
+            used += ICER_HDR_BYTES + ((nb + 7) >> 3);
+            kept++;
+        }
+    }
+    for (uint32_t i = kept; i < a.nstreams; i++) offp[a.prio[i]] = ~0ull;
+    uint64_t *offr = a.off_rearr + (size_t) f * a.nstreams;
+    uint64_t ro = 0;
+    for (uint32_t i = 0; i < a.nstreams; i++) {
+        const uint32_t s = a.rearr[i];
+        if (offp[s] == ~0ull) { offr[s] = ~0ull; continue; }
+        offr[s] = ro;
+        ro += ICER_HDR_BYTES + ((bits[s] + 7) >> 3);
+    }
+    a.size_used[f] = (rc == ICER_RESULT_OK || rc == ICER_BYTE_QUOTA_EXCEEDED) ? used : 0;
+    a.rc[f] = rc;
+    a.keep[f] = kept;
+}
+
+__device__ __forceinline__ uint32_t crc_bytes(const uint8_t *p, int n) {
+    uint32_t c = 0xFFFFFFFFu;
+    for (int i = 0; i < n; i++) c = c_tab.crc[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    return ~c;
+}
+
+// One warp per (frame, stream): builds the 28-byte header (icer_encoding.c:210-234, icer_partition.c:328-332)
+// and copies header + payload to the rearranged stream (and the priority-ordered one when requested).
+__global__ void __launch_bounds__(256) k_gather(AssembleArgs a) {
+    const unsigned long long wid = ((unsigned long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= (unsigned long long) a.nframes * a.nstreams) return;
+    const uint32_t f = (uint32_t) (wid / a.nstreams), s = (uint32_t) (wid % a.nstreams);
+    const uint64_t orr = a.off_rearr[(size_t) f * a.nstreams + s];
+    if (orr == ~0ull) return;
+    const uint64_t opr = a.off_prio[(size_t) f * a.nstreams + s];
+    const uint32_t nb = a.bits[(size_t) f * a.nstreams + s];
+    const uint32_t nbytes = (nb + 7) >> 3;
+    const Unit u = a.units[s / a.planes];
+    const uint32_t lsb = s % a.planes;
+    __shared__ uint8_t hdr_s[8][ICER_HDR_BYTES + 4];
+    uint8_t *hdr = hdr_s[threadIdx.x >> 5];
+    if (lane == 0) {
+        const uint32_t mean = a.mean[(size_t) f * a.chan + u.chan] & 0xFF;    // passes through a uint8_t (icer.h:270)
+        hdr[0] = 0x5B; hdr[1] = 0x60; hdr[2] = (uint8_t) mean; hdr[3] = 0;
+        hdr[4] = u.level; hdr[5] = u.subband; hdr[6] = u.seg; hdr[7] = (uint8_t) (lsb | (u.chan << 4));
+        const uint32_t w = a.w, h = a.h, dc = a.crc[(size_t) f * a.nstreams + s];
+        for (int i = 0; i < 4; i++) {
+            hdr[8 + i] = (uint8_t) (w >> (8 * i)); hdr[12 + i] = (uint8_t) (h >> (8 * i));
+            hdr[16 + i] = (uint8_t) (nb >> (8 * i)); hdr[20 + i] = (uint8_t) (dc >> (8 * i));
+        }
+        const uint32_t hc = crc_bytes(hdr, 24);
+        for (int i = 0; i < 4; i++) hdr[24 + i] = (uint8_t) (hc >> (8 * i));
+    }
+    __syncwarp();
+    const uint8_t *pay = reinterpret_cast<const uint8_t *>(a.scratch + (size_t) f * a.scratch_words + a.soff[s]);
+    uint8_t *dst = a.out + (size_t) f * a.out_stride + orr;
+    if (lane < ICER_HDR_BYTES) dst[lane] = hdr[lane];
+    for (uint32_t i = lane; i < nbytes; i += 32) dst[ICER_HDR_BYTES + i] = pay[i];
+    if (a.out_prio) {
+        uint8_t *d2 = a.out_prio + (size_t) f * a.out_stride + opr;
+        if (lane < ICER_HDR_BYTES) d2[lane] = hdr[lane];
+        for (uint32_t i = lane; i < nbytes; i += 32) d2[ICER_HDR_BYTES + i] = pay[i];
+    }
+}
+
+}  // namespace
+
+uint32_t encode_resident_threads(int device) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int bps = 0;
+    cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EncSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_encode, NT, sizeof(EncSmem));
+    if (bps < 1) bps = 1;
+    return (uint32_t) (sms * bps * NT);
+}
+
+int launch_encode(const EncodeArgs &a, cudaStream_t st, LaunchStats &ls) {
+    int rc = upload_tables();
+    if (rc) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EncSmem)));
+    const unsigned long long total = (unsigned long long) a.nframes * a.nunits * a.planes;
+    unsigned blocks = a.nring_threads / NT;
+    const unsigned long long need = (total + NT - 1) / NT;
+    if (need < blocks) blocks = (unsigned) need;
+    if (blocks == 0) return ICER_RESULT_OK;
+    k_encode<<<blocks, NT, sizeof(EncSmem), st>>>(a);
+    ls.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+
+int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls) {
+    int rc = upload_tables();
+    if (rc) return rc;
+    k_quota_scan<<<(a.nframes + 63) / 64, 64, 0, st>>>(a);
+    const unsigned long long warps = (unsigned long long) a.nframes * a.nstreams;
+    const unsigned long long blocks = (warps * 32 + 255) / 256;
+    if (blocks > 0x7FFFFFFFull) return ICER_FATAL_ERROR;
+    if (blocks) k_gather<<<(unsigned) blocks, 256, 0, st>>>(a);
+    ls.launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+
+int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls) {
+    int rc = upload_tables();
+    if (rc) return rc;
+    if (a.planes > 32) return ICER_BITPLANE_OUT_OF_RANGE;
+    CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(DecSmem)));
+    int dev = 0, sms = 148, bps = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_decode, NT, sizeof(DecSmem));
+    if (bps < 1) bps = 1;
+    const unsigned cpw = 32 / a.planes;
+    const unsigned long long total = (unsigned long long) a.nframes * a.nunits;
+    const unsigned long long warps = (total + cpw - 1) / cpw;
+    unsigned long long blocks = (warps + (NT / 32) - 1) / (NT / 32);
+    if (blocks > (unsigned long long) sms * bps) blocks = (unsigned long long) sms * bps;
+    if (blocks == 0) return ICER_RESULT_OK;
+    k_decode<<<(unsigned) blocks, NT, sizeof(DecSmem), st>>>(a);
+    ls.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}

@@ -134,5 +134,6 @@ struct DecodeArgs {
     const uint32_t *seg_off;       // [nframes][nstreams] byte offset of the segment header inside the frame's stream, 0xFFFFFFFF = absent
     const int32_t *frame_ok;       // [nframes] 0 => skip
     unsigned long long *work_counter;
+    uint32_t debug_flags;          // bit0: no quiet fast path, bit1: planes strictly one after the other
 };
 int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls);

@@ -273,3 +273,59 @@ def test_device_pointer_api_roundtrip(ctx9, oracle9):
     assert (drc.cpu().numpy() == 0).all()
     hostdec = ctx9.decompress_batch(host["streams"], 1, w, h, 3, 0, 7)
     assert (dec.cpu().numpy().view(np.uint16) == hostdec["frames"]).all()
+
+
+def _segments(stream):
+    """(offset, length) of every segment of a well-formed stream."""
+    out, off = [], 0
+    while off + 28 <= len(stream):
+        nbits = int.from_bytes(stream[off + 16:off + 20], "little")
+        ln = 28 + (nbits + 7) // 8
+        out.append((off, ln))
+        off += ln
+    return out
+
+
+def _recrc(seg):
+    import zlib
+    seg = bytearray(seg)
+    seg[20:24] = zlib.crc32(bytes(seg[28:])).to_bytes(4, "little")
+    seg[24:28] = zlib.crc32(bytes(seg[:24])).to_bytes(4, "little")
+    return bytes(seg)
+
+
+def test_crc_valid_garbage_payloads(ctx9, oracle9):
+    """Segments whose payload is garbage but whose CRCs are valid: the entropy decoder runs into invalid codewords /
+    out-of-data mid-plane; lib_icer keeps what that plane wrote so far and never decodes the planes below it
+    (icer_partition.c:441).  The pipelined GPU decoder has to reproduce exactly that."""
+    rng = np.random.default_rng(21)
+    img = harness.load_boat()[64:64 + 96, 100:100 + 128].copy()
+    base = oracle9.compress([img], 2, 0, 4, 4 * 96 * 128)["stream"]
+    segs = _segments(base)
+    variants = []
+    for trial in range(24):
+        s = bytearray(base)
+        for _ in range(int(rng.integers(1, 4))):
+            off, ln = segs[int(rng.integers(0, len(segs)))]
+            if ln <= 30:
+                continue
+            seg = bytearray(s[off:off + ln])
+            mode = trial % 3
+            if mode == 0:      # random payload bytes
+                seg[28:] = rng.integers(0, 256, ln - 28, dtype=np.uint8).tobytes()
+            elif mode == 1:    # claim fewer bits than there are (truncation inside the payload)
+                nbits = int.from_bytes(seg[16:20], "little")
+                nb2 = int(rng.integers(1, max(2, nbits // 2)))
+                seg[16:20] = nb2.to_bytes(4, "little")
+                seg = seg[:28 + (nb2 + 7) // 8]
+                s[off:off + ln] = _recrc(seg) + b"\0" * (ln - len(seg))
+                continue
+            else:              # all ones / all zeros
+                seg[28:] = (b"\xff" if trial % 2 else b"\x00") * (ln - 28)
+            s[off:off + ln] = _recrc(seg)
+        variants.append(bytes(s))
+    dec = ctx9.decompress_batch(variants, 1, 128, 96, 2, 0, 4)
+    for i, v in enumerate(variants):
+        o = oracle9.decompress(v, 1, 96 * 128, 2, 0, 4)
+        assert o["rc"] == int(dec["rc"][i]), i
+        assert (o["images"][0].ravel() == dec["frames"][i, 0]).all(), i
