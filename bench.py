@@ -45,10 +45,18 @@ WORKLOADS = {
 
 
 def usable_cores():
+    """Host cores this process may really use: affinity mask, capped by the cgroup CPU quota (cpu.max)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
 
 
 def measured_peak_gbs():

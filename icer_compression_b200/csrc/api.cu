@@ -162,12 +162,13 @@ int icer_b200_compress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, co
     size_t done = 0;
     while (done < n) {
         // chunk size under the workspace budget
-        const size_t per_frame = frame_px * 2 * 2 + pl->scratch_words * 4 + (size_t) pl->nstreams * 24 + (host ? out_stride * (out_prio ? 2 : 1) : 0) + 64;
+        const size_t per_frame = frame_px * 2 * 2 + frame_px / 8 + pl->scratch_words * 4 + (size_t) pl->nstreams * 24 + (host ? out_stride * (out_prio ? 2 : 1) : 0) + 64;
         size_t nb = std::max<size_t>(1, c->workspace_budget / per_frame);
         nb = std::min(nb, n - done);
         int e;
         if ((e = c->coefs.ensure(nb * frame_px * 2))) return e;
-        if ((e = c->tmp.ensure(nb * frame_px * 2))) return e;
+        const uint32_t ngroups = (uint32_t) ((nb + 31) / 32);
+        if ((e = c->tmp.ensure((size_t) ngroups * 32 * frame_px * 2))) return e;
         if ((e = c->bits.ensure(nb * pl->nstreams * 4))) return e;
         if ((e = c->crc.ensure(nb * pl->nstreams * 4))) return e;
         if ((e = c->offp.ensure(nb * pl->nstreams * 8))) return e;
@@ -196,13 +197,16 @@ int icer_b200_compress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, co
         if ((e = launch_ll_mean_signmag(d_coefs, nb * chan, w, h, (uint32_t) dim_low(w, p->stages), (uint32_t) dim_low(h, p->stages),
                                         c->mean.as<uint16_t>(), c->ovf.as<int>(), st, c->ls))) return e;
         if (coefs_out) if ((e = copy_out(coefs_out + done * frame_px, d_coefs, nb * frame_px * 2, mem, st))) return e;
+        // frame-interleave the coefficients for the coder (lane = frame); the wavelet scratch is free again
+        uint16_t *d_T = c->tmp.as<uint16_t>();
+        if ((e = launch_frames_to_T(d_coefs, d_T, (uint32_t) nb, ngroups, chan, w, h, st, c->ls))) return e;
         ev_record(c, 2, st);
         // entropy coder, retried with a larger payload scratch in the (rare) case a stream outgrows its slot
         for (;;) {
             if ((e = c->scratch.ensure(nb * pl->scratch_words * 4))) return e;
             CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 64, st));
             EncodeArgs ea;
-            ea.coefs = d_coefs; ea.nframes = (uint32_t) nb; ea.w = w; ea.h = h; ea.chan = chan; ea.planes = pl->planes;
+            ea.coefsT = d_T; ea.nframes = (uint32_t) nb; ea.ngroups = ngroups; ea.w = w; ea.h = h; ea.chan = chan; ea.planes = pl->planes;
             ea.units = pl->d_units; ea.nunits = (uint32_t) pl->units.size(); ea.soff = pl->d_soff; ea.scap = pl->d_scap;
             ea.scratch_words = pl->scratch_words; ea.scratch = c->scratch.as<uint32_t>(); ea.bits = c->bits.as<uint32_t>();
             ea.crc = c->crc.as<uint32_t>(); ea.rings = c->rings.as<uint16_t>(); ea.nring_threads = c->ring_threads;
@@ -395,30 +399,31 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, 
         groups[{parsed[i].w, parsed[i].h}].push_back(i);
     }
     int e;
-    if ((e = c->coefs.ensure(n * chan * cap_px * 2))) return e;
-    if ((e = c->tmp.ensure(n * chan * cap_px * 2))) return e;
+    if (host && (e = c->coefs.ensure(n * chan * cap_px * 2))) return e;
     if ((e = c->mean.ensure(n * chan * 2))) return e;
-    if ((e = c->frame_ok.ensure(n * 4))) return e;
-    if ((e = c->dims.ensure(n * 8))) return e;
     if ((e = c->misc.ensure(64))) return e;
     uint16_t *d_frames = host ? c->coefs.as<uint16_t>() : frames;
     float ms_dec = 0, ms_dwt = 0;
+    uint32_t dbg_flags = 0;
+    { const char *dbg = getenv("ICER_B200_DEBUG"); dbg_flags = dbg ? (uint32_t) atoi(dbg) : 0u; }
     for (auto &g : groups) {
         const uint32_t w = g.first.first, h = g.first.second;
         Plan *pl = get_plan(c, w, h, chan, p->stages, p->segments);
         if (pl->status == ICER_FATAL_ERROR) return ICER_FATAL_ERROR;
-        std::vector<int32_t> ok(n, 0);
         if (pl->status != ICER_RESULT_OK) {
-            // lib_icer's decoder reports the partition / stage errors per image (icer_compress.c:480, icer_wavelet.c:92-94);
-            // ICER_PACKET_COUNT_EXCEEDED cannot occur on the decode side, treat it as a plain plan failure
+            // lib_icer's decoder reports the partition / stage errors per image (icer_compress.c:480, icer_wavelet.c:92-94)
             for (size_t i : g.second) hrc[i] = pl->status;
             continue;
         }
-        // segment table of this group
+        // frames of this dimension group, 32 per coder group (lane = frame); segment table; LL means
+        const size_t plane_px = (size_t) w * h;
+        const uint32_t ngroups = (uint32_t) ((g.second.size() + 31) / 32);
+        std::vector<int32_t> frame_of((size_t) ngroups * 32, -1);
         std::vector<uint32_t> segoff(n * (size_t) pl->nstreams, 0xFFFFFFFFu);
         std::vector<uint16_t> hmean(n * chan, 0);
+        size_t k = 0;
         for (size_t i : g.second) {
-            ok[i] = 1;
+            frame_of[k++] = (int32_t) i;
             for (auto &r : parsed[i].segs) {
                 const int ch = chan == 1 ? 0 : (r.lsb_chan >> 4);
                 const int lsb = r.lsb_chan & 0x0F;
@@ -429,35 +434,38 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, 
             }
             for (uint32_t ch = 0; ch < chan; ch++) hmean[i * chan + ch] = parsed[i].mean[ch];
         }
+        const size_t t_bytes = (size_t) ngroups * 32 * chan * plane_px * 2;
+        if ((e = c->tmp.ensure(std::max(t_bytes, n * chan * plane_px * 2)))) return e;
         if ((e = c->segoff.ensure(segoff.size() * 4))) return e;
+        if ((e = c->frame_ok.ensure(frame_of.size() * 4))) return e;
         CUDA_TRY(cudaMemcpyAsync(c->segoff.p, segoff.data(), segoff.size() * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(c->mean.p, hmean.data(), hmean.size() * 2, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->frame_ok.p, ok.data(), n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->frame_ok.p, frame_of.data(), frame_of.size() * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 64, st));
-        // zero the output slots of this group's frames (icer_compress.c:470)
-        for (size_t i : g.second) CUDA_TRY(cudaMemsetAsync(d_frames + i * chan * cap_px, 0, chan * cap_px * 2, st));
+        uint16_t *d_T = c->tmp.as<uint16_t>();
+        CUDA_TRY(cudaMemsetAsync(d_T, 0, t_bytes, st));          // icer_compress.c:470: the image starts at zero
         ev_record(c, 2, st);
         DecodeArgs da;
-        da.coefs = d_frames; da.nframes = (uint32_t) n; da.chan = chan; da.planes = pl->planes; da.cap_px = cap_px;
-        da.units = pl->d_units; da.nunits = (uint32_t) pl->units.size(); da.dims = nullptr; da.plan_w = w; da.plan_h = h;
+        da.coefsT = d_T; da.ngroups = ngroups; da.chan = chan; da.planes = pl->planes;
+        da.units = pl->d_units; da.nunits = (uint32_t) pl->units.size(); da.plan_w = w; da.plan_h = h;
+        da.frame_of = c->frame_ok.as<int32_t>();
         da.streams = d_streams; da.stream_stride = stream_stride; da.total_bytes = total_bytes;
-        da.seg_off = c->segoff.as<uint32_t>(); da.frame_ok = c->frame_ok.as<int32_t>();
+        da.seg_off = c->segoff.as<uint32_t>();
         da.work_counter = c->misc.as<unsigned long long>();
-        { const char *dbg = getenv("ICER_B200_DEBUG"); da.debug_flags = dbg ? (uint32_t) atoi(dbg) : 0u; }
+        da.debug_flags = dbg_flags;
         if ((e = launch_decode(da, st, c->ls))) return e;
         ev_record(c, 3, st);
-        // 4. from sign-magnitude + LL mean, inverse wavelet, clamp -- per frame of the group (planes are cap_px apart)
+        // 4. back to planar frames (from sign-magnitude, + LL mean), inverse wavelet, clamp
         const uint32_t llw = (uint32_t) dim_low(w, p->stages), llh = (uint32_t) dim_low(h, p->stages);
-        const bool dense = (size_t) w * h == cap_px;
-        if (da.debug_flags & 4u) continue;   // debug: leave the raw sign-magnitude coefficients in the output
+        if ((e = launch_T_to_frames(d_T, d_frames, c->frame_ok.as<int32_t>(), c->mean.as<uint16_t>(), ngroups, chan, w, h, cap_px,
+                                    llw, llh, st, c->ls))) return e;
+        const bool dense = plane_px == cap_px;
         if (dense && g.second.size() == n) {
-            if ((e = launch_from_signmag_add_mean(d_frames, n * chan, w, h, llw, llh, c->mean.as<uint16_t>(), st, c->ls))) return e;
             if ((e = launch_dwt_inverse(d_frames, c->tmp.as<uint16_t>(), n * chan, w, h, p->stages, p->filter, true, st, c->ls))) return e;
         } else {
             for (size_t i : g.second)
                 for (uint32_t ch = 0; ch < chan; ch++) {
                     uint16_t *pp = d_frames + (i * chan + ch) * cap_px;
-                    if ((e = launch_from_signmag_add_mean(pp, 1, w, h, llw, llh, c->mean.as<uint16_t>() + i * chan + ch, st, c->ls))) return e;
                     if ((e = launch_dwt_inverse(pp, c->tmp.as<uint16_t>(), 1, w, h, p->stages, p->filter, true, st, c->ls))) return e;
                 }
         }

@@ -132,6 +132,59 @@ __device__ __forceinline__ int sign_index(int lsb, int sb, uint32_t a1, uint32_t
 }
 
 // =========================================================================================================
+// Frame-interleaved coefficient layout ("T" layout)
+// =========================================================================================================
+// The coder kernels give every LANE of a warp the same stream of a different FRAME (32 consecutive frames = one
+// group): identical geometry, so all loop bounds and edge tests are warp-uniform, and similar statistics, so the
+// lanes mostly take the same branches.  To make their pixel accesses one coalesced 64-byte line, the sign-magnitude
+// coefficients are stored as  T[group][channel][y][x][lane]  (uint16).  These two kernels convert between the planar
+// frame layout the wavelet kernels use and T; the decode-side one also undoes sign-magnitude and adds the LL mean
+// (icer_compress.c:520-531).
+
+__global__ void __launch_bounds__(256) k_frames_to_T(const uint16_t *__restrict__ src, uint16_t *__restrict__ T, uint32_t nframes,
+                                                     uint32_t chan, uint32_t plane_px) {
+    // block: 32 frames (one group) x 32 consecutive pixels of one channel
+    __shared__ uint16_t tile[32][34];
+    const uint32_t g = blockIdx.z, c = blockIdx.y;
+    const size_t px0 = (size_t) blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32
+    for (int f = ty; f < 32; f += 8) {
+        const uint32_t frame = g * 32 + f;
+        const size_t px = px0 + tx;
+        tile[f][tx] = (frame < nframes && px < plane_px) ? src[((size_t) frame * chan + c) * plane_px + px] : (uint16_t) 0;
+    }
+    __syncthreads();
+    for (int q = ty; q < 32; q += 8) {
+        const size_t px = px0 + q;
+        if (px < plane_px) T[(((size_t) g * chan + c) * plane_px + px) * 32 + tx] = tile[tx][q];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_T_to_frames(const uint16_t *__restrict__ T, uint16_t *__restrict__ dst,
+                                                     const int32_t *__restrict__ frame_of, const uint16_t *__restrict__ mean,
+                                                     uint32_t chan, uint32_t plane_px, uint64_t cap_px, int W, int llw, int llh) {
+    __shared__ uint16_t tile[32][34];
+    const uint32_t g = blockIdx.z, c = blockIdx.y;
+    const size_t px0 = (size_t) blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int q = ty; q < 32; q += 8) {
+        const size_t px = px0 + q;
+        tile[q][tx] = px < plane_px ? T[(((size_t) g * chan + c) * plane_px + px) * 32 + tx] : (uint16_t) 0;
+    }
+    __syncthreads();
+    for (int f = ty; f < 32; f += 8) {
+        const int32_t frame = frame_of[g * 32 + f];
+        const size_t px = px0 + tx;
+        if (frame < 0 || px >= plane_px) continue;
+        uint32_t v = tile[tx][f];
+        v = (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;                      // icer_wavelet.c:880-886
+        const int r = (int) (px / (size_t) W), cc = (int) (px % (size_t) W);
+        if (r < llh && cc < llw) v = (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + (int) (int16_t) mean[(size_t) frame * chan + c]);
+        dst[((size_t) frame * chan + c) * cap_px + px] = (uint16_t) v;
+    }
+}
+
+// =========================================================================================================
 // K4: encoder
 // =========================================================================================================
 struct EncSmem {
@@ -139,8 +192,7 @@ struct EncSmem {
     uint32_t crc[256];
     uint32_t cnt[17][NT];      // zero << 16 | total, per context
     uint32_t bseq[17][NT];     // sequence number of the codeword each bin is building
-    uint16_t bstate[17][NT];   // Golomb: zeros counted; custom: input bits gathered (first bit = bit 0)
-    uint8_t bfill[17][NT];     // custom: number of input bits gathered
+    uint32_t bst[17][NT];      // Golomb: zeros counted; custom: input word (first bit = bit 0) | bits gathered << 16
 };
 
 // Interleave-window bookkeeping.  A codeword gets a sequence number when its first bit arrives (lib_icer: a ring
@@ -168,7 +220,7 @@ struct Enc {
         return __brev(k + (longer ? i : 0)) >> (32 - nb);
     }
 
-    // codeword of `bin` is complete (single call site in the tick loop)
+    // codeword of `bin` is complete (single call site in the pixel loop)
     __device__ __forceinline__ void complete(int bin, uint32_t code, uint32_t nb) {
         const uint32_t seq = S.bseq[bin][t];
         open_mask &= ~(1u << bin);
@@ -208,12 +260,12 @@ struct Enc {
 
     // the word a forced completion gives the oldest codeword (icer_encoding.c:141-189): window full, or end of stream
     __device__ __forceinline__ uint32_t forced_word(int bin, uint32_t &nb) {
+        const uint32_t st = S.bst[bin][t];
         if (bin > 7) {
-            const uint32_t k = S.bstate[bin][t];
-            if (k == (uint32_t) S.T.gol_m[bin] - 1) { nb = 1; return 1; }
-            return golomb_word(bin, k, nb);
+            if (st == (uint32_t) S.T.gol_m[bin] - 1) { nb = 1; return 1; }
+            return golomb_word(bin, st, nb);
         }
-        const uint32_t pre = S.bstate[bin][t], fill = S.bfill[bin][t];
+        const uint32_t pre = st & 0xFFFF, fill = st >> 16;
         const uint32_t fl = S.T.flush[bin][pre][fill];
         const uint32_t word = (pre | ((fl & 0xF) << fill)) & 0x3FF;
         const uint32_t e = S.T.v2v[bin][word & 31];
@@ -224,14 +276,12 @@ struct Enc {
     __device__ __forceinline__ bool window_full_for(int bin) const {
         return !((open_mask >> bin) & 1u) && tail - head >= ICER_RING;
     }
-
     // make sure `bin` has an open codeword (icer_encoding.c:56-67); the caller has dealt with a full window
     __device__ __forceinline__ void open_bin(int bin) {
         if (open_mask & (1u << bin)) return;
         if (open_mask == 0) oldest = bin;
         S.bseq[bin][t] = tail++;
-        S.bstate[bin][t] = 0;
-        S.bfill[bin][t] = 0;
+        S.bst[bin][t] = 0;
         open_mask |= 1u << bin;
     }
 
@@ -255,6 +305,7 @@ struct Enc {
     }
 };
 
+// One warp per (frame group, stream); lane = frame of the group.
 __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
@@ -264,51 +315,41 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
     __syncthreads();
 
     const uint32_t nstreams = a.nunits * a.planes;
-    const unsigned long long total = (unsigned long long) a.nframes * nstreams;
+    const unsigned long long total = (unsigned long long) a.ngroups * nstreams;
     const int lane = t & 31;
     uint16_t *ring = a.rings + (size_t) (blockIdx.x * NT + t) * ICER_RING;
     const size_t plane_px = (size_t) a.w * a.h;
     const int W = (int) a.w;
+    const int RS = W * 32;     // row stride of the T layout, in elements
 
     for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.work_counter, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= total) break;
-        const unsigned long long sid = base + lane;
-        const bool valid = sid < total;
-        uint32_t frame = 0, s = 0;
-        Unit u;
-        u.x = u.y = u.w = u.h = 0; u.chan = u.level = u.subband = u.seg = 0; u.px = 0;
-        int lsb = 0;
-        if (valid) {
-            frame = (uint32_t) (sid / nstreams); s = (uint32_t) (sid % nstreams);
-            u = a.units[s / a.planes];
-            lsb = (int) (s % a.planes);
-        }
-        const uint16_t *seg = a.coefs + ((size_t) frame * a.chan + u.chan) * plane_px + (size_t) u.y * W + u.x;
+        unsigned long long wid = 0;
+        if (lane == 0) wid = atomicAdd(a.work_counter, 1ull);
+        wid = __shfl_sync(0xffffffffu, wid, 0);
+        if (wid >= total) break;
+        const uint32_t g = (uint32_t) (wid / nstreams), s = (uint32_t) (wid % nstreams);
+        const Unit u = a.units[s / a.planes];
+        const int lsb = (int) (s % a.planes);
+        const uint32_t frame = g * 32 + lane;
+        const bool valid = frame < a.nframes;
+        const uint16_t *seg = a.coefsT + (((size_t) g * a.chan + u.chan) * plane_px + (size_t) u.y * W + u.x) * 32 + lane;
         Enc cd(S, t, ring, valid ? a.scratch + (size_t) frame * a.scratch_words + a.soff[s] : nullptr, valid ? a.scap[s] : 0);
 #pragma unroll
         for (int c = 0; c < 17; c++) S.cnt[c][t] = (2u << 16) | 4u;    // icer.h:147-148
         const int sw = u.w, sh = u.h, sb = u.subband;
-        const uint32_t px = valid ? (uint32_t) sw * (uint32_t) sh : 0;
-        uint32_t maxpx = px;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) maxpx = max(maxpx, __shfl_xor_sync(0xffffffffu, maxpx, o));
 
-        int row = 0, col = 0;
-        uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
         uint32_t fz_left = 0, fz_run = 0;    // quiet fast path: zeros still absorbable / absorbed but not yet applied
         int fz_bin = 0;
 
-        for (uint32_t i = 0; i < maxpx; i++) {
-            if (i < px) {
-                const uint16_t *p = seg + (size_t) row * W + col;
-                const bool up = row > 0, dn = row + 1 < sh, rt = col + 1 < sw;
-                if (col == 0) { a0 = b0 = c0 = 0; a1 = up ? p[-W] : 0; b1 = p[0]; c1 = dn ? p[W] : 0; }
-                a2 = (up && rt) ? p[1 - W] : 0;
-                b2 = rt ? p[1] : 0;
-                c2 = (dn && rt) ? p[1 + W] : 0;
+        for (int row = 0; row < sh; row++) {
+            const bool up = row > 0, dn = row + 1 < sh;
+            const uint16_t *p = seg + (size_t) row * RS;
+            uint32_t a0 = 0, a1 = up ? p[-RS] : 0, a2, b0 = 0, b1 = p[0], b2, c0 = 0, c1 = dn ? p[RS] : 0, c2;
+            for (int col = 0; col < sw; col++, p += 32) {
+                const bool rt = col + 1 < sw;
+                a2 = (up && rt) ? p[32 - RS] : 0;
+                b2 = rt ? p[32] : 0;
+                c2 = (dn && rt) ? p[32 + RS] : 0;
                 const uint32_t v = b1;
                 const bool quiet = ((((a0 | a1 | a2 | b0 | b1 | b2 | c0 | c1 | c2) & 0x7FFF) >> lsb) == 0);
                 // micro-ops: bit0 = apply the pending fast run, bit1 = magnitude decision, bit2 = sign decision
@@ -337,15 +378,18 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
                         uint32_t z = (zt >> 16) + fz_run, tot = (zt & 0xFFFF) + fz_run;
                         if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
                         S.cnt[0][t] = (z << 16) | tot;
-                        const uint32_t k = (uint32_t) S.bstate[bin][t] + fz_run;
+                        const uint32_t k = S.bst[bin][t] + fz_run;
                         if (k >= S.T.gol_m[bin]) { done = true; code = 1; nb = 1; }
-                        else S.bstate[bin][t] = (uint16_t) k;
+                        else S.bst[bin][t] = k;
                         fz_run = 0; fz_left = 0;
                     } else {
                         uint32_t bit;
-                        bool coded = true;
                         if (st == 1 && cat == 3) {
-                            bit = mbit; bin = 0; coded = false;               // p(0) = 1/2 -> uncoded bin
+                            bit = mbit; bin = 0;                              // p(0) = 1/2 -> uncoded bin
+                            if (cd.window_full_for(0)) {
+                                bin = cd.oldest; code = cd.forced_word(bin, nb); done = true; todo |= 1u << st;
+                                goto emit_site;
+                            }
                         } else {
                             int ctx;
                             if (st == 1) {
@@ -364,16 +408,13 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
                             bin = bin_of(S.T, zz, tot);
                             if (cd.window_full_for(bin)) {
                                 // window full: force-complete the oldest codeword first, then redo this decision
-                                bin = cd.oldest;
-                                code = cd.forced_word(bin, nb);
-                                done = true;
-                                todo |= 1u << st;
+                                bin = cd.oldest; code = cd.forced_word(bin, nb); done = true; todo |= 1u << st;
                                 goto emit_site;
                             }
                             if (st == 1 && quiet && !inv && bin > 7) {
                                 // enter the quiet fast path: this and the following quiet pixels only bump counters
                                 cd.open_bin(bin);
-                                const uint32_t n1 = (uint32_t) S.T.gol_m[bin] - S.bstate[bin][t];
+                                const uint32_t n1 = (uint32_t) S.T.gol_m[bin] - S.bst[bin][t];
                                 const uint32_t n2 = zeros_in_same_bin(S.T, bin, z, tot);
                                 const uint32_t n3 = 500u - tot;
                                 fz_left = min(n1, min(n2, n3)) - 1;
@@ -387,29 +428,23 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
                             S.cnt[ctx][t] = (z << 16) | tot;
                             bit ^= inv ? 1u : 0u;
                         }
-                        if (!coded && cd.window_full_for(0)) {
-                            bin = cd.oldest;
-                            code = cd.forced_word(bin, nb);
-                            done = true;
-                            todo |= 1u << st;
-                            goto emit_site;
-                        }
                         cd.open_bin(bin);
                         if (bin > 7) {                                        // Golomb run-length bins
                             if (bit) {
-                                code = cd.golomb_word(bin, S.bstate[bin][t], nb);
+                                code = cd.golomb_word(bin, S.bst[bin][t], nb);
                                 done = true;
                             } else {
-                                const uint32_t k = (uint32_t) S.bstate[bin][t] + 1;
-                                S.bstate[bin][t] = (uint16_t) k;
+                                const uint32_t k = S.bst[bin][t] + 1;
+                                S.bst[bin][t] = k;
                                 if (k >= S.T.gol_m[bin]) { code = 1; nb = 1; done = true; }
                             }
                         } else if (bin != 0) {                                // variable-to-variable bins
-                            const uint32_t fill = S.bfill[bin][t];
-                            const uint32_t word = S.bstate[bin][t] | (bit << fill);
+                            const uint32_t stt = S.bst[bin][t];
+                            const uint32_t fill = stt >> 16;
+                            const uint32_t word = (stt & 0xFFFF) | (bit << fill);
                             const uint32_t e = S.T.v2v[bin][word & 31];
                             if ((e & 0xF) == fill + 1) { code = e >> 8; nb = (e >> 4) & 0xF; done = true; }
-                            else { S.bstate[bin][t] = (uint16_t) word; S.bfill[bin][t] = (uint8_t) (fill + 1); }
+                            else S.bst[bin][t] = word | ((fill + 1) << 16);
                         } else {                                              // uncoded bin
                             code = bit & 1; nb = 1; done = true;
                         }
@@ -418,20 +453,17 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
                     if (done) cd.complete(bin, code, nb);
                 }
                 a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
-                if (++col == sw) { col = 0; row++; }
             }
         }
+        if (fz_run) {   // tail of a fast run
+            const int bin = fz_bin;
+            const uint32_t k = S.bst[bin][t] + fz_run;
+            if (k >= S.T.gol_m[bin]) cd.complete(bin, 1, 1);
+            else S.bst[bin][t] = k;
+        }
+        uint32_t bits, crc;
+        cd.finish(bits, crc);
         if (valid) {
-            if (fz_run) {   // tail of a fast run
-                const int bin = fz_bin;
-                const uint32_t zt = S.cnt[0][t];
-                (void) zt;
-                const uint32_t k = (uint32_t) S.bstate[bin][t] + fz_run;
-                if (k >= S.T.gol_m[bin]) cd.complete(bin, 1, 1);
-                else S.bstate[bin][t] = (uint16_t) k;
-            }
-            uint32_t bits, crc;
-            cd.finish(bits, crc);
             a.bits[(size_t) frame * nstreams + s] = bits;
             a.crc[(size_t) frame * nstreams + s] = crc;
             if (cd.overflow) atomicOr(a.overflow, 1);
@@ -443,24 +475,31 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
 // =========================================================================================================
 // K7: decoder
 // =========================================================================================================
-struct DecSmem {
+// One BLOCK per (frame group, chain): warp j decodes bit plane (planes-1-j) of the chain for the 32 frames of the
+// group.  The warps form a pipeline: warp j may process pixel n once warp j-1 has finished pixel n + w + 1 (its
+// right/down neighbours are taken one plane up).  Progress is published in shared memory; a warp advances only when
+// all of its live lanes can, so its position -- and therefore every address and edge test -- stays warp-uniform.
+struct DecShared {
     SmemTables T;
-    uint32_t cnt[17][NT];
-    int32_t depth[17][NT];     // pending decoded bits per bin
-    uint32_t stamp[17][NT];    // codeword count when the bin was last refilled
-    uint8_t low[17][NT];       // the low 8 stack positions (nothing above can hold a 1)
+    volatile uint32_t prog[16];          // pixels completed per plane-warp
+    volatile uint8_t deadf[16][32];      // lane's plane is void because a plane above it hit a decode error
+    volatile uint8_t errf[16][32];
+    uint8_t pres[16][32];
+    unsigned long long work;
 };
+// followed in dynamic shared memory by: cnt[17][BT], depth[17][BT], stlow[17][BT]  (BT = blockDim.x)
 
 struct Dec {
-    DecSmem &S;
-    const int t;
+    const SmemTables &T;
+    uint32_t *stlow;            // [17][BT]: codeword count at last refill (24 bits) | low 8 stack positions << 24
+    const int t, BT;
     const uint8_t *base;        // payload start
     const uint8_t *end;         // end of the whole stream buffer (reads beyond return 0)
     uint32_t total_bits = 0;
     uint32_t consumed = 0;      // bits consumed
     uint32_t words = 0;         // codewords consumed
 
-    __device__ Dec(DecSmem &s, int tid) : S(s), t(tid), base(nullptr), end(nullptr) {}
+    __device__ Dec(const SmemTables &tt, uint32_t *sl, int tid, int bt) : T(tt), stlow(sl), t(tid), BT(bt), base(nullptr), end(nullptr) {}
 
     // n <= 16 bits starting `ahead` bits after the cursor, LSB first
     __device__ __forceinline__ uint32_t bits_at(uint32_t ahead, uint32_t n) const {
@@ -500,10 +539,10 @@ struct Dec {
     __device__ __forceinline__ int refill(int bin, int &depth, uint32_t &low) {
         depth = 0; low = 0;
         if (bin > 7) {
-            const uint32_t l = S.T.gol_l[bin], gi = S.T.gol_i[bin];
+            const uint32_t l = T.gol_l[bin], gi = T.gol_i[bin];
             if (bits_at(0, 1)) {
                 rd(1, true);
-                depth = S.T.gol_m[bin];
+                depth = T.gol_m[bin];
             } else {
                 uint32_t k = (__brev((uint32_t) rd(l, false) & 0xFFFFu) >> (32 - l)) & 0xFFFFu;
                 if (k < gi) {
@@ -523,7 +562,7 @@ struct Dec {
                 word |= bits_at(n, 1) << n;
                 n++;
                 if (word >= 32) return ICER_DECODED_INVALID_DATA;
-                const uint32_t e = S.T.v2v[bin][word];
+                const uint32_t e = T.v2v[bin][word];
                 if ((e & 0xF) == n) {
                     low = e >> 8;
                     depth = (int) ((e >> 4) & 0xF);
@@ -538,204 +577,223 @@ struct Dec {
             depth = 1;
         }
         words++;
-        S.stamp[bin][t] = words;
         return ICER_RESULT_OK;
     }
 };
 
-// One warp decodes `cpw` chains at a time; lane = chain_slot * planes + (planes-1 - lsb).
-__global__ void __launch_bounds__(NT, 4) k_decode(DecodeArgs a) {
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DecSmem &S = *reinterpret_cast<DecSmem *>(smem_raw);
-    const int t = threadIdx.x;
-    load_tables(S.T, true);
-    __syncthreads();
-
+    DecShared &S = *reinterpret_cast<DecShared *>(smem_raw);
+    const int t = threadIdx.x, BT = blockDim.x;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(DecShared) + 15) & ~(size_t) 15));
+    int32_t *depthA = reinterpret_cast<int32_t *>(cnt + 17 * BT);
+    uint32_t *stlow = reinterpret_cast<uint32_t *>(depthA + 17 * BT);
+    {   // tables
+        for (int i = t; i < 8 * 32; i += BT) (&S.T.v2v[0][0])[i] = (&c_tab.dec[0][0])[i];
+        for (int i = t; i < 45; i += BT) S.T.ctx_hv[i] = c_tab.ctx_hv[i];
+        for (int i = t; i < 25; i += BT) { S.T.ctx_hh[i] = c_tab.ctx_hh[i]; S.T.ctx_sign[i] = c_tab.ctx_sign[i]; S.T.sign_pred[i] = c_tab.sign_pred[i]; }
+        for (int i = t; i < 17; i += BT) { S.T.gol_m[i] = c_tab.gol_m[i]; S.T.gol_l[i] = c_tab.gol_l[i]; S.T.gol_i[i] = c_tab.gol_i[i]; }
+        for (int i = t; i < 16; i += BT) S.T.cutoff[i] = c_tab.cutoff[i];
+    }
     const int lane = t & 31;
+    const int j = t >> 5;                            // warp index = plane index from the top
     const int P = (int) a.planes;
-    const int cpw = 32 / P;                         // chains per warp
-    const int slot = lane / P, j = lane % P;        // j = 0 is the most significant plane
-    const bool lane_used = slot < cpw;
     const int lsb = P - 1 - j;
-    const unsigned long long total = (unsigned long long) a.nframes * a.nunits;
+    const unsigned long long total = (unsigned long long) a.ngroups * a.nunits;
     const uint32_t nstreams = a.nunits * a.planes;
     const uint8_t *buf_end = a.streams + a.total_bytes;
     const int W = (int) a.plan_w;
+    const int RS = W * 32;
+    const size_t plane_px = (size_t) a.plan_w * a.plan_h;
+    const bool fast_ok = !(a.debug_flags & 1u);
 
     for (;;) {
-        unsigned long long basei = 0;
-        if (lane == 0) basei = atomicAdd(a.work_counter, (unsigned long long) cpw);
-        basei = __shfl_sync(0xffffffffu, basei, 0);
-        if (basei >= total) break;
-        const unsigned long long cid = basei + (unsigned) slot;
+        __syncthreads();
+        if (t == 0) S.work = atomicAdd(a.work_counter, 1ull);
+        if (t < 16) S.prog[t] = 0;
+        __syncthreads();
+        const unsigned long long wid = S.work;
+        if (wid >= total) break;
+        const uint32_t g = (uint32_t) (wid / a.nunits), ui = (uint32_t) (wid % a.nunits);
+        const Unit u = a.units[ui];
+        const int32_t frame = a.frame_of[g * 32 + lane];
         bool present = false;
-        Unit u;
-        u.x = u.y = u.w = u.h = 0; u.chan = u.level = u.subband = u.seg = 0; u.px = 0;
-        uint32_t frame = 0;
-        Dec dc(S, t);
-        if (lane_used && cid < total) {
-            frame = (uint32_t) (cid / a.nunits);
-            const uint32_t ui = (uint32_t) (cid % a.nunits);
-            if (a.frame_ok[frame]) {
-                u = a.units[ui];
-                const uint32_t off = a.seg_off[(size_t) frame * nstreams + ui * a.planes + lsb];
-                if (off != 0xFFFFFFFFu) {
-                    const uint8_t *hd = a.streams + (size_t) frame * a.stream_stride + off;
-                    present = true;
-                    dc.total_bits = hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24);
-                    dc.base = hd + ICER_HDR_BYTES;
-                    dc.end = buf_end;
-                }
+        Dec dc(S.T, stlow, t, BT);
+        if (frame >= 0) {
+            const uint32_t off = a.seg_off[(size_t) frame * nstreams + ui * a.planes + lsb];
+            if (off != 0xFFFFFFFFu) {
+                const uint8_t *hd = a.streams + (size_t) frame * a.stream_stride + off;
+                present = true;
+                dc.total_bits = hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24);
+                dc.base = hd + ICER_HDR_BYTES;
+                dc.end = buf_end;
             }
         }
+        S.pres[j][lane] = present ? 1 : 0;
+        S.deadf[j][lane] = 0;
+        S.errf[j][lane] = 0;
+        __syncthreads();
         // a plane is decoded only if every plane above it is present (icer_partition.c:431)
-        const uint32_t pres_mask = __ballot_sync(0xffffffffu, present);
-        const uint32_t grp = ((P >= 32) ? 0xFFFFFFFFu : ((1u << P) - 1u)) << (slot * P);
-        const uint32_t missing = ~pres_mask & grp & ((1u << lane) - 1u);      // missing planes above me in my chain
-        bool alive = present && missing == 0 && lane_used;
+        bool alive = present;
+        for (int q = 0; q < j; q++) alive = alive && S.pres[q][lane];
 
-        uint16_t *seg = a.coefs + ((size_t) frame * a.chan + u.chan) * a.cap_px + (size_t) u.y * W + u.x;
+        uint16_t *seg = a.coefsT + (((size_t) g * a.chan + u.chan) * plane_px + (size_t) u.y * W + u.x) * 32 + lane;
         const int sw = u.w, sh = u.h, sb = u.subband;
-        const uint32_t px = alive ? (uint32_t) sw * (uint32_t) sh : 0;
+        const uint32_t px = (uint32_t) sw * (uint32_t) sh;
         const uint32_t lag = (uint32_t) sw + 1;      // plane p may run at most this far behind plane p+1
 #pragma unroll
-        for (int c = 0; c < 17; c++) { S.cnt[c][t] = (2u << 16) | 4u; S.depth[c][t] = 0; S.stamp[c][t] = 0; S.low[c][t] = 0; }
+        for (int c = 0; c < 17; c++) { cnt[c * BT + t] = (2u << 16) | 4u; depthA[c * BT + t] = 0; stlow[c * BT + t] = 0; }
 
-        uint32_t pos = 0;
+        uint32_t pos = 0;                  // warp-uniform
         int row = 0, col = 0;
         uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
         uint32_t fz_left = 0, fz_run = 0;
         int fz_bin = 0;
-        int err = 0;                 // this plane hit a decode error: it stops, the planes below are void
-        bool dead = false;           // a plane above hit an error
+        bool run = alive;                  // this lane still decodes
+        bool dead = false;                 // voided by an error in a plane above
+        uint32_t done_px = 0;              // pixels this lane has (possibly) written
 
-        for (;;) {
-            // progress of the plane above (lane - 1 of the same chain)
-            const uint32_t up_pos = __shfl_up_sync(0xffffffffu, pos, 1);
-            const int up_err = __shfl_up_sync(0xffffffffu, (err != 0 || dead) ? 1 : 0, 1);
-            const uint32_t up_px = __shfl_up_sync(0xffffffffu, px, 1);
-            if (j > 0 && up_err) dead = true;
+        while (pos < px && __any_sync(0xffffffffu, run)) {
             uint32_t limit = px;
-            if (j > 0 && up_pos < up_px) limit = (a.debug_flags & 2u) ? 0u : (up_pos > lag ? up_pos - lag : 0);
-            const bool running = alive && !dead && err == 0 && pos < px;
-            if (!__any_sync(0xffffffffu, running)) break;
-            if (running && pos < limit) {
-                uint16_t *p = seg + (size_t) row * W + col;
-                const bool up = row > 0, dn = row + 1 < sh, rt = col + 1 < sw;
-                if (col == 0) { a0 = b0 = c0 = 0; a1 = up ? p[-W] : 0; b1 = p[0]; c1 = dn ? p[W] : 0; }
-                a2 = (up && rt) ? p[1 - W] : 0;
-                b2 = rt ? p[1] : 0;
-                c2 = (dn && rt) ? p[1 + W] : 0;
-                uint32_t v = b1;
-                const bool quiet = ((((a0 | a1 | a2 | b0 | b1 | b2 | c0 | c1 | c2) & 0x7FFF) >> lsb) == 0);
-                uint32_t todo;
-                if (quiet && fz_left) { fz_run++; fz_left--; todo = 0; }
-                else todo = (fz_run ? 1u : 0u) | 2u;
-                int cat = 0;
-                if (todo & 2u) {
-                    const int msb = 31 - __clz((v & 0x7FFF) | 1);
-                    cat = msb - lsb;
-                    cat = cat < 0 ? 0 : (cat > 3 ? 3 : cat);
-                }
-                bool changed = false;
-                while (todo) {
-                    const int st = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    if (st == 0) {
-                        const int bin = fz_bin;
-                        const uint32_t zt = S.cnt[0][t];
-                        uint32_t z = (zt >> 16) + fz_run, tot = (zt & 0xFFFF) + fz_run;
-                        if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
-                        S.cnt[0][t] = (z << 16) | tot;
-                        S.depth[bin][t] -= (int) fz_run;
-                        fz_run = 0; fz_left = 0;
-                        continue;
+            if (j > 0) {
+                if (run && S.deadf[j - 1][lane] | S.errf[j - 1][lane]) { run = false; dead = true; S.deadf[j][lane] = 1; }
+                const uint32_t up = S.prog[j - 1];
+                __threadfence_block();
+                if (up < px) limit = (a.debug_flags & 2u) ? 0u : (up > lag ? up - lag : 0u);
+                if (run && S.deadf[j - 1][lane] | S.errf[j - 1][lane]) { run = false; dead = true; S.deadf[j][lane] = 1; }
+            }
+            if (pos >= limit) { __nanosleep(64); continue; }
+            uint32_t stop = pos + 16 < limit ? pos + 16 : limit;      // re-check progress every 16 pixels
+            for (; pos < stop; pos++) {
+                uint16_t *p = seg + (size_t) row * RS + (size_t) col * 32;
+                const bool up_ = row > 0, dn = row + 1 < sh, rt = col + 1 < sw;
+                if (col == 0) { a0 = b0 = c0 = 0; a1 = up_ ? p[-RS] : 0; b1 = p[0]; c1 = dn ? p[RS] : 0; }
+                a2 = (up_ && rt) ? p[32 - RS] : 0;
+                b2 = rt ? p[32] : 0;
+                c2 = (dn && rt) ? p[32 + RS] : 0;
+                if (run) {
+                    uint32_t v = b1;
+                    const bool quiet = ((((a0 | a1 | a2 | b0 | b1 | b2 | c0 | c1 | c2) & 0x7FFF) >> lsb) == 0);
+                    uint32_t todo;
+                    if (quiet && fz_left) { fz_run++; fz_left--; todo = 0; }
+                    else todo = (fz_run ? 1u : 0u) | 2u;
+                    int cat = 0;
+                    if (todo & 2u) {
+                        const int msb = 31 - __clz((v & 0x7FFF) | 1);
+                        cat = msb - lsb;
+                        cat = cat < 0 ? 0 : (cat > 3 ? 3 : cat);
                     }
-                    int bin, ctx = -1, si = 0;
-                    bool inv = false;
-                    uint32_t z = 0, tot = 0;
-                    if (st == 1 && cat == 3) {
-                        bin = 0;
-                    } else {
-                        if (st == 1) ctx = mag_context(S.T, cat, lsb, sb, a0, a1, a2, b0, b2, c0, c1, c2);
-                        else { si = sign_index(lsb, sb, a1, b0, b2, c1); ctx = S.T.ctx_sign[si]; }
-                        const uint32_t zt = S.cnt[ctx][t];
-                        z = zt >> 16; tot = zt & 0xFFFF;
-                        uint32_t zz = z;
-                        inv = zz < (tot >> 1);
-                        if (inv) zz = tot - zz;
-                        bin = bin_of(S.T, zz, tot);
-                    }
-                    // next decoded bit of `bin` (icer_decoding.c:127, :186-192)
-                    int depth = S.depth[bin][t];
-                    uint32_t low = S.low[bin][t];
-                    if (depth <= 0 || dc.words - S.stamp[bin][t] >= ICER_RING) {
-                        const int rc = dc.refill(bin, depth, low);
-                        if (rc != ICER_RESULT_OK) { err = rc; todo = 0; break; }
-                    }
-                    if (st == 1 && quiet && !inv && bin > 7 && !(a.debug_flags & 1u)) {
-                        // quiet fast path: the run of pending zeros of this Golomb bin is taken without touching the stack
-                        const uint32_t zeros = (uint32_t) depth - (low & 1u);
-                        if (zeros > 0) {
-                            const uint32_t n2 = zeros_in_same_bin(S.T, bin, z, tot);
-                            const uint32_t n3 = 500u - tot;
-                            S.depth[bin][t] = depth; S.low[bin][t] = (uint8_t) low;
-                            fz_left = min(zeros, min(n2, n3)) - 1;
-                            fz_run = 1;
-                            fz_bin = bin;
+                    bool changed = false;
+                    while (todo) {
+                        const int st = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        if (st == 0) {
+                            const int bin = fz_bin;
+                            const uint32_t zt = cnt[t];
+                            uint32_t z = (zt >> 16) + fz_run, tot = (zt & 0xFFFF) + fz_run;
+                            if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
+                            cnt[t] = (z << 16) | tot;
+                            depthA[bin * BT + t] -= (int) fz_run;
+                            fz_run = 0; fz_left = 0;
                             continue;
                         }
+                        int bin, ctx = -1, si = 0;
+                        bool inv = false;
+                        uint32_t z = 0, tot = 0;
+                        if (st == 1 && cat == 3) {
+                            bin = 0;
+                        } else {
+                            if (st == 1) ctx = mag_context(S.T, cat, lsb, sb, a0, a1, a2, b0, b2, c0, c1, c2);
+                            else { si = sign_index(lsb, sb, a1, b0, b2, c1); ctx = S.T.ctx_sign[si]; }
+                            const uint32_t zt = cnt[ctx * BT + t];
+                            z = zt >> 16; tot = zt & 0xFFFF;
+                            uint32_t zz = z;
+                            inv = zz < (tot >> 1);
+                            if (inv) zz = tot - zz;
+                            bin = bin_of(S.T, zz, tot);
+                        }
+                        // next decoded bit of `bin` (icer_decoding.c:127, :186-192)
+                        int depth = depthA[bin * BT + t];
+                        const uint32_t sl = stlow[bin * BT + t];
+                        uint32_t low = sl >> 24;
+                        bool refilled = false;
+                        if (depth <= 0 || dc.words - (sl & 0xFFFFFFu) >= ICER_RING) {
+                            const int rc = dc.refill(bin, depth, low);
+                            if (rc != ICER_RESULT_OK) { run = false; S.errf[j][lane] = 1; todo = 0; break; }
+                            refilled = true;
+                        }
+                        const uint32_t stamp = refilled ? (dc.words & 0xFFFFFFu) : (sl & 0xFFFFFFu);
+                        if (st == 1 && quiet && !inv && bin > 7 && fast_ok) {
+                            // quiet fast path: the run of pending zeros of this Golomb bin is taken without touching the stack
+                            const uint32_t zeros = (uint32_t) depth - (low & 1u);
+                            if (zeros > 0) {
+                                const uint32_t n2 = zeros_in_same_bin(S.T, bin, z, tot);
+                                const uint32_t n3 = 500u - tot;
+                                depthA[bin * BT + t] = depth;
+                                stlow[bin * BT + t] = stamp | (low << 24);
+                                fz_left = min(zeros, min(n2, n3)) - 1;
+                                fz_run = 1;
+                                fz_bin = bin;
+                                continue;
+                            }
+                        }
+                        const int top = depth - 1;
+                        uint32_t b = 0;
+                        if (top >= 0 && top < 8) { b = (low >> top) & 1u; low &= ~(1u << top); }
+                        depthA[bin * BT + t] = depth - 1;
+                        stlow[bin * BT + t] = stamp | (low << 24);
+                        const uint32_t bit = inv ? (b ^ 1u) : b;
+                        if (ctx >= 0) {
+                            tot++;
+                            z += bit ^ 1u;
+                            if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
+                            cnt[ctx * BT + t] = (z << 16) | tot;
+                        }
+                        if (st == 1) {
+                            if (bit) { v |= 1u << lsb; changed = true; if (cat == 0) todo |= 4u; }
+                        } else {
+                            if ((bit ^ S.T.sign_pred[si]) & 1u) { v |= 0x8000u; changed = true; }
+                        }
                     }
-                    const int top = depth - 1;
-                    uint32_t b = 0;
-                    if (top >= 0 && top < 8) { b = (low >> top) & 1u; low &= ~(1u << top); }
-                    S.depth[bin][t] = depth - 1;
-                    S.low[bin][t] = (uint8_t) low;
-                    const uint32_t bit = inv ? (b ^ 1u) : b;
-                    if (ctx >= 0) {
-                        tot++;
-                        z += bit ^ 1u;
-                        if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
-                        S.cnt[ctx][t] = (z << 16) | tot;
-                    }
-                    if (st == 1) {
-                        if (bit) { v |= 1u << lsb; changed = true; if (cat == 0) todo |= 4u; }
-                    } else {
-                        if ((bit ^ S.T.sign_pred[si]) & 1u) { v |= 0x8000u; changed = true; }
-                    }
+                    if (changed) { *p = (uint16_t) v; b1 = v; }      // also stores the magnitude bit when the sign read failed
+                    done_px = pos + 1;
                 }
-                if (changed) { *p = (uint16_t) v; b1 = v; }      // also stores the magnitude bit when the sign read failed
-                if (err == 0) {
-                    a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
-                    if (++col == sw) { col = 0; row++; }
-                    pos++;
-                }
+                a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
+                if (++col == sw) { col = 0; row++; }
             }
+            __threadfence_block();
             __syncwarp();
+            if (lane == 0) S.prog[j] = pos;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) S.prog[j] = 0xFFFFFFFFu;            // finished (or nothing left to do): never hold the planes below
+        // lanes that never started because a plane above died before they looked
+        __syncthreads();
+        if (j > 0 && alive && !dead && (S.deadf[j - 1][lane] | S.errf[j - 1][lane])) dead = true;
+        // propagate "dead" down the chain (a plane may have finished before the plane above it failed)
+        for (int q = 1; q < P; q++) {
+            if (j == q && alive && (S.deadf[q - 1][lane] | S.errf[q - 1][lane])) { dead = true; S.deadf[q][lane] = 1; }
+            __syncthreads();
         }
         // A decode error voids every plane below it (lib_icer stops the chain there and never decodes them,
         // icer_partition.c:441).  Those planes ran ahead in the pipeline: take their bits back.
-        const uint32_t err_mask = __ballot_sync(0xffffffffu, err != 0);
-        if (err_mask) {
-            if (dead && alive) {
-                for (uint32_t n = 0; n < pos; n++) {
-                    uint16_t *q = seg + (size_t) (n / (uint32_t) sw) * W + (n % (uint32_t) sw);
-                    *q = (uint16_t) (*q & ~(1u << lsb));
-                }
-            }
-            __syncwarp();
-            // a sign bit set by a voided plane belongs to a coefficient whose magnitude is now zero
-            const uint32_t dead_mask = __ballot_sync(0xffffffffu, dead && alive);
-            const uint32_t mine = dead_mask & grp;
-            if (mine && lane == __ffs(mine) - 1) {
-                const uint32_t npx = (uint32_t) sw * (uint32_t) sh;
-                for (uint32_t n = 0; n < npx; n++) {
-                    uint16_t *q = seg + (size_t) (n / (uint32_t) sw) * W + (n % (uint32_t) sw);
-                    if ((*q & 0x7FFF) == 0) *q = 0;
-                }
+        if (dead && alive) {
+            for (uint32_t n = 0; n < done_px; n++) {
+                uint16_t *q = seg + (size_t) (n / (uint32_t) sw) * RS + (size_t) (n % (uint32_t) sw) * 32;
+                *q = (uint16_t) (*q & ~(1u << lsb));
             }
         }
-        __syncwarp();
+        __syncthreads();
+        // a sign bit set by a voided plane belongs to a coefficient whose magnitude is now zero; the highest voided
+        // plane of each frame cleans up
+        if (dead && alive && !(j > 0 && S.deadf[j - 1][lane])) {
+            for (uint32_t n = 0; n < px; n++) {
+                uint16_t *q = seg + (size_t) (n / (uint32_t) sw) * RS + (size_t) (n % (uint32_t) sw) * 32;
+                if ((*q & 0x7FFF) == 0 && *q != 0) *q = 0;
+            }
+        }
     }
 }
 
@@ -840,13 +898,43 @@ uint32_t encode_resident_threads(int device) {
     return (uint32_t) (sms * bps * NT);
 }
 
+int launch_frames_to_T(const uint16_t *frames, uint16_t *T, uint32_t nframes, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h,
+                       cudaStream_t st, LaunchStats &ls) {
+    const size_t plane_px = (size_t) w * h;
+    for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
+        const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
+        dim3 grid((unsigned) ((plane_px + 31) / 32), chan, cnt);
+        const uint32_t f0 = g0 * 32;
+        k_frames_to_T<<<grid, 256, 0, st>>>(frames + (size_t) f0 * chan * plane_px, T + (size_t) g0 * chan * plane_px * 32,
+                                            nframes - f0, chan, (uint32_t) plane_px);
+        ls.launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+
+int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame_of, const uint16_t *mean, uint32_t ngroups,
+                       uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, uint32_t llw, uint32_t llh, cudaStream_t st,
+                       LaunchStats &ls) {
+    const size_t plane_px = (size_t) w * h;
+    for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
+        const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
+        dim3 grid((unsigned) ((plane_px + 31) / 32), chan, cnt);
+        k_T_to_frames<<<grid, 256, 0, st>>>(T + (size_t) g0 * chan * plane_px * 32, frames, frame_of + (size_t) g0 * 32, mean, chan,
+                                            (uint32_t) plane_px, cap_px, (int) w, (int) llw, (int) llh);
+        ls.launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+
 int launch_encode(const EncodeArgs &a, cudaStream_t st, LaunchStats &ls) {
     int rc = upload_tables();
     if (rc) return rc;
     CUDA_TRY(cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EncSmem)));
-    const unsigned long long total = (unsigned long long) a.nframes * a.nunits * a.planes;
+    const unsigned long long total = (unsigned long long) a.ngroups * a.nunits * a.planes;   // warps of work
     unsigned blocks = a.nring_threads / NT;
-    const unsigned long long need = (total + NT - 1) / NT;
+    const unsigned long long need = (total + (NT / 32) - 1) / (NT / 32);
     if (need < blocks) blocks = (unsigned) need;
     if (blocks == 0) return ICER_RESULT_OK;
     k_encode<<<blocks, NT, sizeof(EncSmem), st>>>(a);
@@ -871,20 +959,22 @@ int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls) {
 int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls) {
     int rc = upload_tables();
     if (rc) return rc;
-    if (a.planes > 32) return ICER_BITPLANE_OUT_OF_RANGE;
-    CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(DecSmem)));
+    if (a.planes < 1 || a.planes > 15) return ICER_BITPLANE_OUT_OF_RANGE;
+    const int BT = (int) a.planes * 32;
+    const size_t smem = ((sizeof(DecShared) + 15) & ~(size_t) 15) + (size_t) 3 * 17 * BT * 4;
+    // two register budgets: up to 9 planes (288 threads, 3 blocks / SM) and up to 15 planes (480 threads)
+    void (*kern)(DecodeArgs) = a.planes <= 9 ? k_decode<288, 3> : k_decode<480, 1>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int dev = 0, sms = 148, bps = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_decode, NT, sizeof(DecSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BT, smem);
     if (bps < 1) bps = 1;
-    const unsigned cpw = 32 / a.planes;
-    const unsigned long long total = (unsigned long long) a.nframes * a.nunits;
-    const unsigned long long warps = (total + cpw - 1) / cpw;
-    unsigned long long blocks = (warps + (NT / 32) - 1) / (NT / 32);
+    const unsigned long long total = (unsigned long long) a.ngroups * a.nunits;
+    unsigned long long blocks = total;
     if (blocks > (unsigned long long) sms * bps) blocks = (unsigned long long) sms * bps;
     if (blocks == 0) return ICER_RESULT_OK;
-    k_decode<<<(unsigned) blocks, NT, sizeof(DecSmem), st>>>(a);
+    kern<<<(unsigned) blocks, BT, smem, st>>>(a);
     ls.launches++;
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;

@@ -88,8 +88,8 @@ int launch_from_signmag_add_mean(uint16_t *planes, size_t nplanes, uint32_t w, u
                                  const uint16_t *d_mean, cudaStream_t st, LaunchStats &ls);
 
 struct EncodeArgs {
-    const uint16_t *coefs;     // [nframes][chan][h][w] sign-magnitude
-    uint32_t nframes, w, h, chan, planes;
+    const uint16_t *coefsT;    // [ngroups][chan][h][w][32] sign-magnitude, frame-interleaved (32 frames per group)
+    uint32_t nframes, ngroups, w, h, chan, planes;
     const Unit *units; uint32_t nunits;
     const uint32_t *soff, *scap;   // per stream
     uint64_t scratch_words;        // per frame
@@ -124,16 +124,21 @@ struct AssembleArgs {
 int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls);
 
 struct DecodeArgs {
-    uint16_t *coefs;               // [nframes][chan][cap_px] zero-initialised, receives sign-magnitude
-    uint32_t nframes, chan, planes;
-    uint64_t cap_px;               // pixels per channel slot
+    uint16_t *coefsT;              // [ngroups][chan][h][w][32] zero-initialised, receives sign-magnitude (frame-interleaved)
+    uint32_t ngroups, chan, planes;
     const Unit *units; uint32_t nunits;
-    const uint32_t *dims;          // [nframes][2] actual (w,h); frames whose dims differ from the plan are skipped
     uint32_t plan_w, plan_h;
+    const int32_t *frame_of;       // [ngroups*32] batch index of each lane's frame, -1 = padding
     const uint8_t *streams; uint64_t stream_stride; uint64_t total_bytes;
-    const uint32_t *seg_off;       // [nframes][nstreams] byte offset of the segment header inside the frame's stream, 0xFFFFFFFF = absent
-    const int32_t *frame_ok;       // [nframes] 0 => skip
+    const uint32_t *seg_off;       // [batch frames][nstreams] byte offset of the segment header inside the frame's stream, 0xFFFFFFFF = absent
     unsigned long long *work_counter;
     uint32_t debug_flags;          // bit0: no quiet fast path, bit1: planes strictly one after the other
 };
 int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls);
+// planar frames [n][chan][h][w]  <->  frame-interleaved T layout [ngroups][chan][h][w][32]
+int launch_frames_to_T(const uint16_t *frames, uint16_t *T, uint32_t nframes, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h,
+                       cudaStream_t st, LaunchStats &ls);
+// also undoes sign-magnitude and adds the header LL mean; frame_of maps (group, lane) to the batch index (-1 = none)
+int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame_of, const uint16_t *mean, uint32_t ngroups,
+                       uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, uint32_t llw, uint32_t llh, cudaStream_t st,
+                       LaunchStats &ls);
