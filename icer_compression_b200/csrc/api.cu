@@ -209,7 +209,7 @@ int icer_b200_compress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, co
             ea.coefsT = d_T; ea.nframes = (uint32_t) nb; ea.ngroups = ngroups; ea.w = w; ea.h = h; ea.chan = chan; ea.planes = pl->planes;
             ea.units = pl->d_units; ea.nunits = (uint32_t) pl->units.size(); ea.soff = pl->d_soff; ea.scap = pl->d_scap;
             ea.scratch_words = pl->scratch_words; ea.scratch = c->scratch.as<uint32_t>(); ea.bits = c->bits.as<uint32_t>();
-            ea.crc = c->crc.as<uint32_t>(); ea.rings = c->rings.as<uint16_t>(); ea.nring_threads = c->ring_threads;
+            ea.rings = c->rings.as<uint16_t>(); ea.nring_threads = c->ring_threads;
             ea.work_counter = c->misc.as<unsigned long long>(); ea.overflow = c->misc.as<int>() + 4;
             if ((e = launch_encode(ea, st, c->ls))) return e;
             int ovf = 0;

@@ -32,6 +32,7 @@ struct DevTables {
     uint32_t crc[256];
     uint16_t enc[8][32];       // in_bits | out_bits << 4 | out << 8        (keyed by the gathered input word)
     uint16_t dec[8][32];       // in_bits | out_bits << 4 | out << 8        (keyed by the received word)
+    uint16_t dlut[8][32];      // keyed by the NEXT 5 stream bits: codeword length | out_bits << 4 | out << 8 (0 = none)
     uint16_t gol_m[17], gol_l[17], gol_i[17];
     uint8_t flush[8][9][6];    // pad_word | pad_len << 4
     uint8_t ctx_hv[45], ctx_hh[25], ctx_sign[25], sign_pred[25];   // icer_config.c:26-67
@@ -55,6 +56,16 @@ int upload_tables() {
             d.dec[b][v] = (uint16_t) (h.dec[b][v].in_bits | (h.dec[b][v].out_bits << 4) | (h.dec[b][v].out << 8));
         }
     memcpy(d.flush, h.flush, sizeof d.flush);
+    // the variable-to-variable codes are complete prefix codes of at most 5 bits: the next 5 stream bits select the
+    // codeword directly (same first-match order as the bit-by-bit loop of icer_decoding.c:155-177)
+    for (int b = 0; b < 8; b++)
+        for (int x = 0; x < 32; x++) {
+            d.dlut[b][x] = 0;
+            for (int L = 1; L <= 5; L++) {
+                const V2VEntry &e = h.dec[b][x & ((1 << L) - 1)];
+                if (e.in_bits == L) { d.dlut[b][x] = (uint16_t) (L | (e.out_bits << 4) | (e.out << 8)); break; }
+            }
+        }
     for (int b = 0; b < 17; b++) { d.gol_m[b] = h.gol_m[b]; d.gol_l[b] = h.gol_l[b]; d.gol_i[b] = h.gol_i[b]; }
     for (int b = 0; b < 16; b++) d.cutoff[b] = h.cutoff[b];
     for (uint32_t n = 0; n < 256; n++) {
@@ -80,7 +91,7 @@ struct SmemTables {
 
 __device__ __forceinline__ void load_tables(SmemTables &T, bool decoder) {
     const int t = threadIdx.x;
-    for (int i = t; i < 8 * 32; i += NT) (&T.v2v[0][0])[i] = decoder ? (&c_tab.dec[0][0])[i] : (&c_tab.enc[0][0])[i];
+    for (int i = t; i < 8 * 32; i += NT) (&T.v2v[0][0])[i] = decoder ? (&c_tab.dlut[0][0])[i] : (&c_tab.enc[0][0])[i];
     for (int i = t; i < 8 * 9 * 6; i += NT) (&T.flush[0][0][0])[i] = (&c_tab.flush[0][0][0])[i];
     for (int i = t; i < 45; i += NT) T.ctx_hv[i] = c_tab.ctx_hv[i];
     for (int i = t; i < 25; i += NT) { T.ctx_hh[i] = c_tab.ctx_hh[i]; T.ctx_sign[i] = c_tab.ctx_sign[i]; T.sign_pred[i] = c_tab.sign_pred[i]; }
@@ -189,7 +200,6 @@ __global__ void __launch_bounds__(256) k_T_to_frames(const uint16_t *__restrict_
 // =========================================================================================================
 struct EncSmem {
     SmemTables T;
-    uint32_t crc[256];
     uint32_t cnt[17][NT];      // zero << 16 | total, per context
     uint32_t bseq[17][NT];     // sequence number of the codeword each bin is building
     uint32_t bst[17][NT];      // Golomb: zeros counted; custom: input word (first bit = bit 0) | bits gathered << 16
@@ -206,8 +216,8 @@ struct Enc {
     uint32_t cap, nwords = 0;
     unsigned long long acc = 0;
     int nacc = 0;
-    uint32_t crc = 0xFFFFFFFFu;
-    uint32_t head = 0, tail = 0, open_mask = 0;
+    uint32_t head = 0, tail = 0, open_mask = 0;   // head: first sequence number that is not complete yet (lib_icer's head)
+    uint32_t emit_pos = 0;                        // next sequence number to pack into the payload (<= head)
     int oldest = 0;
     bool overflow = false;
 
@@ -220,14 +230,13 @@ struct Enc {
         return __brev(k + (longer ? i : 0)) >> (32 - nb);
     }
 
-    // codeword of `bin` is complete (single call site in the pixel loop)
+    // codeword of `bin` is complete (single call site in the pixel loop): park it in the ring; if it was the oldest
+    // one, everything up to the next open codeword is now ready for emission
     __device__ __forceinline__ void complete(int bin, uint32_t code, uint32_t nb) {
         const uint32_t seq = S.bseq[bin][t];
         open_mask &= ~(1u << bin);
-        if (seq != head) {
-            ring[seq & (ICER_RING - 1)] = (uint16_t) ((nb << 11) | code);
-            return;
-        }
+        ring[seq & (ICER_RING - 1)] = (uint16_t) ((nb << 11) | code);
+        if (seq != head) return;
         uint32_t limit = tail;
         const uint32_t h1 = head + 1;
         for (uint32_t m = open_mask; m; m &= m - 1) {
@@ -235,26 +244,22 @@ struct Enc {
             const uint32_t sq = S.bseq[b][t];
             if ((int32_t) (sq - h1) < (int32_t) (limit - h1)) { limit = sq; oldest = b; }
         }
-        for (;;) {   // LSB-first bit packing (icer_encoding.c:114-139), CRC-32 of the payload on the fly
-            acc |= (unsigned long long) code << nacc;
-            nacc += (int) nb;
-            if (nacc >= 32) {
-                const uint32_t wv = (uint32_t) acc;
-                if (nwords < cap) out[nwords] = wv; else overflow = true;
-                nwords++;
-                uint32_t c = crc;
-                c = S.crc[(c ^ wv) & 0xFF] ^ (c >> 8);
-                c = S.crc[(c ^ (wv >> 8)) & 0xFF] ^ (c >> 8);
-                c = S.crc[(c ^ (wv >> 16)) & 0xFF] ^ (c >> 8);
-                c = S.crc[(c ^ (wv >> 24)) & 0xFF] ^ (c >> 8);
-                crc = c;
-                acc >>= 32;
-                nacc -= 32;
-            }
-            head++;
-            if (head == limit) break;
-            const uint32_t v = ring[head & (ICER_RING - 1)];
-            code = v & 0x7FF; nb = v >> 11;
+        head = limit;
+    }
+
+    // pack one ready codeword into the payload, LSB first (icer_encoding.c:114-139).  Called from ONE convergent site
+    // per pixel so that the lanes of a warp emit together instead of each draining its backlog alone.
+    __device__ __forceinline__ void pump() {
+        if (emit_pos == head) return;
+        const uint32_t v = ring[emit_pos & (ICER_RING - 1)];
+        emit_pos++;
+        acc |= (unsigned long long) (v & 0x7FF) << nacc;
+        nacc += (int) (v >> 11);
+        if (nacc >= 32) {
+            if (nwords < cap) out[nwords] = (uint32_t) acc; else overflow = true;
+            nwords++;
+            acc >>= 32;
+            nacc -= 32;
         }
     }
 
@@ -279,29 +284,23 @@ struct Enc {
     // make sure `bin` has an open codeword (icer_encoding.c:56-67); the caller has dealt with a full window
     __device__ __forceinline__ void open_bin(int bin) {
         if (open_mask & (1u << bin)) return;
+        while (tail - emit_pos >= ICER_RING) pump();       // physical ring space (emission may lag behind `head`)
         if (open_mask == 0) oldest = bin;
         S.bseq[bin][t] = tail++;
         S.bst[bin][t] = 0;
         open_mask |= 1u << bin;
     }
 
-    __device__ void finish(uint32_t &bits_out, uint32_t &crc_out) {
+    __device__ void finish(uint32_t &bits_out) {
         while (open_mask) {                                    // icer_context_modeller.c:452-455
             uint32_t nb;
             const int bin = oldest;
             const uint32_t code = forced_word(bin, nb);
             complete(bin, code, nb);
         }
+        while (emit_pos != head) pump();
         bits_out = nwords * 32u + (uint32_t) nacc;
-        const int nbytes = (nacc + 7) >> 3;
-        if (nbytes) {
-            const uint32_t wv = (uint32_t) acc;
-            if (nwords < cap) out[nwords] = wv; else overflow = true;
-            uint32_t c = crc;
-            for (int i = 0; i < nbytes; i++) c = S.crc[(c ^ (wv >> (8 * i))) & 0xFF] ^ (c >> 8);
-            crc = c;
-        }
-        crc_out = ~crc;
+        if (nacc > 0) { if (nwords < cap) out[nwords] = (uint32_t) acc; else overflow = true; }
     }
 };
 
@@ -311,7 +310,6 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
     const int t = threadIdx.x;
     load_tables(S.T, false);
-    for (int i = t; i < 256; i += NT) S.crc[i] = c_tab.crc[i];
     __syncthreads();
 
     const uint32_t nstreams = a.nunits * a.planes;
@@ -452,6 +450,8 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
                 emit_site:
                     if (done) cd.complete(bin, code, nb);
                 }
+                cd.pump();       // up to two codewords can start per pixel, so two emissions keep pace
+                cd.pump();
                 a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
             }
         }
@@ -461,11 +461,10 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
             if (k >= S.T.gol_m[bin]) cd.complete(bin, 1, 1);
             else S.bst[bin][t] = k;
         }
-        uint32_t bits, crc;
-        cd.finish(bits, crc);
+        uint32_t bits;
+        cd.finish(bits);
         if (valid) {
             a.bits[(size_t) frame * nstreams + s] = bits;
-            a.crc[(size_t) frame * nstreams + s] = crc;
             if (cd.overflow) atomicOr(a.overflow, 1);
         }
         __syncwarp();
@@ -491,34 +490,38 @@ struct DecShared {
 
 struct Dec {
     const SmemTables &T;
-    uint32_t *stlow;            // [17][BT]: codeword count at last refill (24 bits) | low 8 stack positions << 24
-    const int t, BT;
-    const uint8_t *base;        // payload start
-    const uint8_t *end;         // end of the whole stream buffer (reads beyond return 0)
+    const uint32_t *wp = nullptr;   // next aligned stream word to load
+    const uint8_t *end = nullptr;   // end of the whole stream buffer (bytes at or beyond it read as zero)
+    unsigned long long bb = 0;      // bit buffer, LSB = next stream bit
+    int bbn = 0;                    // bits in bb that came from loads (zeros beyond)
     uint32_t total_bits = 0;
-    uint32_t consumed = 0;      // bits consumed
-    uint32_t words = 0;         // codewords consumed
+    uint32_t consumed = 0;          // bits consumed
+    uint32_t words = 0;             // codewords consumed
 
-    __device__ Dec(const SmemTables &tt, uint32_t *sl, int tid, int bt) : T(tt), stlow(sl), t(tid), BT(bt), base(nullptr), end(nullptr) {}
+    __device__ Dec(const SmemTables &tt) : T(tt) {}
 
-    // n <= 16 bits starting `ahead` bits after the cursor, LSB first
-    __device__ __forceinline__ uint32_t bits_at(uint32_t ahead, uint32_t n) const {
-        const uint32_t pos = consumed + ahead;
-        const uint8_t *p = base + (pos >> 3);
-        const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(ad & ~(uintptr_t) 3);
-        // bytes at or beyond `end` read as zero (exactly: the last word may be partial)
+    __device__ __forceinline__ uint32_t load_word() {
         const ptrdiff_t left = end - reinterpret_cast<const uint8_t *>(wp);
-        uint32_t w0 = 0, w1 = 0;
-        if (left >= 8) { w0 = wp[0]; w1 = wp[1]; }
-        else if (left > 0) {
-            w0 = wp[0];
-            if (left < 4) w0 &= (1u << (8 * (int) left)) - 1u;
-            else if (left > 4) w1 = wp[1] & ((1u << (8 * (int) (left - 4))) - 1u);
-        }
-        const uint32_t sh = (uint32_t) (ad & 3) * 8 + (pos & 7);
-        return __funnelshift_r(w0, w1, sh) & ((1u << n) - 1);
+        uint32_t w = 0;
+        if (left >= 4) w = *wp;
+        else if (left > 0) w = *wp & ((1u << (8 * (int) left)) - 1u);
+        wp++;
+        return w;
     }
+    __device__ __forceinline__ void start(const uint8_t *base, const uint8_t *e, uint32_t nbits) {
+        end = e; total_bits = nbits;
+        const uintptr_t ad = reinterpret_cast<uintptr_t>(base);
+        wp = reinterpret_cast<const uint32_t *>(ad & ~(uintptr_t) 3);
+        const int sh = (int) (ad & 3) * 8;
+        bb = (unsigned long long) (load_word() >> sh);
+        bbn = 32 - sh;
+    }
+    __device__ __forceinline__ void fill() {           // afterwards at least 33 valid bits are buffered
+        if (bbn <= 32) { bb |= (unsigned long long) load_word() << bbn; bbn += 32; }
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t) bb & ((1u << n) - 1u); }
+    __device__ __forceinline__ void skip(uint32_t n) { bb >>= n; bbn -= (int) n; consumed += n; }
+
     // icer_get_bits_from_codeword / icer_pop_bits_from_codeword (icer_decoding.c:59-105): byte-chunked read that
     // fails only when a chunk is larger than the whole segment (`decoded_bits_total` is never advanced there)
     __device__ __forceinline__ int rd(uint32_t n, bool consume) {
@@ -530,17 +533,18 @@ struct Dec {
                 left -= take; off = (off + take) & 7;
             }
         }
-        const int v = (int) bits_at(0, n);
-        if (consume) consumed += n;
+        const int v = (int) peek(n);
+        if (consume) skip(n);
         return v;
     }
 
     // refill `bin` with the next codeword (icer_decoding.c:127-181); returns an error code or OK
     __device__ __forceinline__ int refill(int bin, int &depth, uint32_t &low) {
         depth = 0; low = 0;
+        fill();
         if (bin > 7) {
             const uint32_t l = T.gol_l[bin], gi = T.gol_i[bin];
-            if (bits_at(0, 1)) {
+            if (peek(1)) {
                 rd(1, true);
                 depth = T.gol_m[bin];
             } else {
@@ -555,21 +559,14 @@ struct Dec {
                 low = 1;
             }
         } else if (bin != 0) {
-            uint32_t word = 0, n = 0;
-            bool found = false;
-            do {
-                if (n + 1 >= total_bits) return ICER_DECODER_OUT_OF_DATA;
-                word |= bits_at(n, 1) << n;
-                n++;
-                if (word >= 32) return ICER_DECODED_INVALID_DATA;
-                const uint32_t e = T.v2v[bin][word];
-                if ((e & 0xF) == n) {
-                    low = e >> 8;
-                    depth = (int) ((e >> 4) & 0xF);
-                    if ((int) word != rd(n, true)) return ICER_DECODED_INVALID_DATA;
-                    found = true;
-                }
-            } while (!found && n < 10);
+            const uint32_t e = T.v2v[bin][peek(5)];
+            const uint32_t L = e & 0xF;
+            if (L == 0) return ICER_DECODED_INVALID_DATA;          // cannot happen: the codes are complete
+            if (L >= total_bits) return ICER_DECODER_OUT_OF_DATA;  // the reference checks n + 1 >= total for every bit it reads
+            low = e >> 8;
+            depth = (int) ((e >> 4) & 0xF);
+            const int word = (int) peek(L);
+            if (word != rd(L, true)) return ICER_DECODED_INVALID_DATA;
         } else {
             const int v = rd(1, true);
             if (v == ICER_DECODER_OUT_OF_DATA) return v;
@@ -590,7 +587,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
     int32_t *depthA = reinterpret_cast<int32_t *>(cnt + 17 * BT);
     uint32_t *stlow = reinterpret_cast<uint32_t *>(depthA + 17 * BT);
     {   // tables
-        for (int i = t; i < 8 * 32; i += BT) (&S.T.v2v[0][0])[i] = (&c_tab.dec[0][0])[i];
+        for (int i = t; i < 8 * 32; i += BT) (&S.T.v2v[0][0])[i] = (&c_tab.dlut[0][0])[i];
         for (int i = t; i < 45; i += BT) S.T.ctx_hv[i] = c_tab.ctx_hv[i];
         for (int i = t; i < 25; i += BT) { S.T.ctx_hh[i] = c_tab.ctx_hh[i]; S.T.ctx_sign[i] = c_tab.ctx_sign[i]; S.T.sign_pred[i] = c_tab.sign_pred[i]; }
         for (int i = t; i < 17; i += BT) { S.T.gol_m[i] = c_tab.gol_m[i]; S.T.gol_l[i] = c_tab.gol_l[i]; S.T.gol_i[i] = c_tab.gol_i[i]; }
@@ -619,15 +616,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
         const Unit u = a.units[ui];
         const int32_t frame = a.frame_of[g * 32 + lane];
         bool present = false;
-        Dec dc(S.T, stlow, t, BT);
+        Dec dc(S.T);
         if (frame >= 0) {
             const uint32_t off = a.seg_off[(size_t) frame * nstreams + ui * a.planes + lsb];
             if (off != 0xFFFFFFFFu) {
                 const uint8_t *hd = a.streams + (size_t) frame * a.stream_stride + off;
                 present = true;
-                dc.total_bits = hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24);
-                dc.base = hd + ICER_HDR_BYTES;
-                dc.end = buf_end;
+                dc.start(hd + ICER_HDR_BYTES, buf_end, hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24));
             }
         }
         S.pres[j][lane] = present ? 1 : 0;
@@ -801,6 +796,31 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
 // K5: quota scan, then gather of header + payload into the output streams
 // =========================================================================================================
 
+// CRC-32 of every payload (icer_partition.c:330, icer_util.c:64-66): one thread per stream, word loads
+__global__ void __launch_bounds__(128) k_payload_crc(AssembleArgs a) {
+    __shared__ uint32_t crc[256];
+    for (int i = threadIdx.x; i < 256; i += 128) crc[i] = c_tab.crc[i];
+    __syncthreads();
+    const unsigned long long id = (unsigned long long) blockIdx.x * 128 + threadIdx.x;
+    if (id >= (unsigned long long) a.nframes * a.nstreams) return;
+    const uint32_t f = (uint32_t) (id / a.nstreams), s = (uint32_t) (id % a.nstreams);
+    const uint32_t nbytes = (a.bits[id] + 7) >> 3;
+    const uint32_t *w = a.scratch + (size_t) f * a.scratch_words + a.soff[s];
+    uint32_t c = 0xFFFFFFFFu, i = 0;
+    for (; i + 4 <= nbytes; i += 4) {
+        const uint32_t v = w[i >> 2];
+        c = crc[(c ^ v) & 0xFF] ^ (c >> 8);
+        c = crc[(c ^ (v >> 8)) & 0xFF] ^ (c >> 8);
+        c = crc[(c ^ (v >> 16)) & 0xFF] ^ (c >> 8);
+        c = crc[(c ^ (v >> 24)) & 0xFF] ^ (c >> 8);
+    }
+    if (i < nbytes) {
+        const uint32_t v = w[i >> 2];
+        for (uint32_t k = 0; i < nbytes; i++, k++) c = crc[(c ^ (v >> (8 * k))) & 0xFF] ^ (c >> 8);
+    }
+    a.crc[id] = ~c;
+}
+
 // One thread per frame walks the streams in priority order with lib_icer's quota rule (SURVEY A.14;
 // icer_encoding.c:211-214, :133-135; icer_partition.c:323-326).  Then a second walk in rearranged order assigns
 // the offsets of the final stream.
@@ -946,12 +966,14 @@ int launch_encode(const EncodeArgs &a, cudaStream_t st, LaunchStats &ls) {
 int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls) {
     int rc = upload_tables();
     if (rc) return rc;
+    const unsigned long long nst = (unsigned long long) a.nframes * a.nstreams;
+    if (nst) k_payload_crc<<<(unsigned) ((nst + 127) / 128), 128, 0, st>>>(a);
     k_quota_scan<<<(a.nframes + 63) / 64, 64, 0, st>>>(a);
     const unsigned long long warps = (unsigned long long) a.nframes * a.nstreams;
     const unsigned long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0x7FFFFFFFull) return ICER_FATAL_ERROR;
     if (blocks) k_gather<<<(unsigned) blocks, 256, 0, st>>>(a);
-    ls.launches += 2;
+    ls.launches += 3;
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;
 }

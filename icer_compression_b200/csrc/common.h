@@ -95,7 +95,6 @@ struct EncodeArgs {
     uint64_t scratch_words;        // per frame
     uint32_t *scratch;             // [nframes][scratch_words]
     uint32_t *bits;                // [nframes][nstreams] payload length in bits
-    uint32_t *crc;                 // [nframes][nstreams] crc32 of the payload bytes
     uint16_t *rings;               // [resident threads][2048]
     uint32_t nring_threads;
     unsigned long long *work_counter;  // dynamic work fetch, pre-zeroed
@@ -110,7 +109,8 @@ struct AssembleArgs {
     const uint32_t *prio, *rearr;  // stream id orders
     const uint32_t *soff;
     uint64_t scratch_words;
-    const uint32_t *scratch, *bits, *crc;
+    const uint32_t *scratch, *bits;
+    uint32_t *crc;                 // [nframes][nstreams] payload CRC-32, filled by the assemble step
     const uint16_t *mean;          // [nframes][chan]
     const int *ovf;                // [nframes][chan] wavelet/mean overflow
     int plan_status;

@@ -1,0 +1,200 @@
+// parse.cu -- K6: the byte-stream scanner on the device.
+//
+// lib_icer's decoder first walks the stream byte by byte looking for segments (icer_compress.c:443-459 calling
+// icer_find_packet_in_bytestream :569-588): at offset o a segment is accepted iff the 16-bit preamble is 0x605B, the
+// CRC-32 of the 24 header bytes matches, the payload length fits in what is left of the stream and the payload CRC-32
+// matches; then o jumps past the segment, otherwise o advances by one byte.  The last accepted header supplies the
+// image dimensions and (per channel) the LL mean; for duplicate (channel, level, subband, segment, plane) entries the
+// last one wins.
+//
+// Device formulation (exactly equivalent):
+//   k_scan    every byte offset is tested independently for "a valid segment COULD start here" (preamble, header CRC,
+//             length) -> candidate list per frame (unordered, atomics)
+//   k_verify  payload CRC of every candidate (one thread each)
+//   k_walk    one block per frame: bitonic sort of the candidates by offset, then thread 0 replays the sequential
+//             walk over them -- a candidate is accepted iff it starts at or after the end of the previously accepted
+//             one; offsets that are not valid candidates only ever advance the reference's cursor by one byte
+//   k_table   per dimension group: accepted segments -> [frame][stream] offset table through the plan's unit LUT
+#include "common.h"
+
+namespace {
+
+__constant__ uint32_t c_crc[256];
+bool g_crc_uploaded = false;
+
+int upload_crc() {
+    if (g_crc_uploaded) return ICER_RESULT_OK;
+    uint32_t tab[256];
+    for (uint32_t n = 0; n < 256; n++) {
+        uint32_t c = n;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        tab[n] = c;
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(c_crc, tab, sizeof tab));
+    g_crc_uploaded = true;
+    return ICER_RESULT_OK;
+}
+
+__device__ __forceinline__ uint32_t ld32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t) p[3] << 24); }
+
+__global__ void __launch_bounds__(256) k_scan(ParseArgs a) {
+    __shared__ uint32_t crc[256];
+    crc[threadIdx.x] = c_crc[threadIdx.x];
+    __syncthreads();
+    const uint32_t frame = blockIdx.y;
+    const uint64_t len = a.lens[frame] < a.stride ? a.lens[frame] : a.stride;
+    const uint8_t *s = a.streams + (size_t) frame * a.stride;
+    const uint64_t o0 = ((uint64_t) blockIdx.x * 256 + threadIdx.x) * 8;
+    if (o0 >= len) return;
+    uint8_t b[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) b[k] = (o0 + k < len) ? s[o0 + k] : 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (b[k] != 0x5B || b[k + 1] != 0x60) continue;
+        const uint64_t o = o0 + k;
+        if (len - o < ICER_HDR_BYTES) continue;
+        const uint8_t *h = s + o;
+        uint32_t c = 0xFFFFFFFFu;
+        for (int i = 0; i < 24; i++) c = crc[(c ^ h[i]) & 0xFF] ^ (c >> 8);
+        if (~c != ld32(h + 24)) continue;
+        const uint32_t nbits = ld32(h + 16);
+        const uint64_t nbytes = ((uint64_t) nbits + 7) >> 3;
+        if (nbytes > len - o - ICER_HDR_BYTES) continue;
+        const uint32_t slot = atomicAdd(&a.ncand[frame], 1u);
+        if (slot < a.cap) a.cand[(size_t) frame * a.cap + slot] = make_uint2((uint32_t) o, (uint32_t) nbytes);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_verify(ParseArgs a) {
+    __shared__ uint32_t crc[256];
+    for (int i = threadIdx.x; i < 256; i += 128) crc[i] = c_crc[i];
+    __syncthreads();
+    const uint32_t frame = blockIdx.y;
+    const uint32_t k = blockIdx.x * 128 + threadIdx.x;
+    uint32_t cnt = a.ncand[frame];
+    if (cnt > a.cap) cnt = a.cap;
+    if (k >= cnt) return;
+    uint2 cd = a.cand[(size_t) frame * a.cap + k];
+    const uint8_t *h = a.streams + (size_t) frame * a.stride + cd.x;
+    const uint8_t *p = h + ICER_HDR_BYTES;
+    uint32_t c = 0xFFFFFFFFu;
+    uint32_t n = cd.y, i = 0;
+    // bytes up to a 4-byte boundary, then words
+    while (i < n && ((uintptr_t) (p + i) & 3)) { c = crc[(c ^ p[i]) & 0xFF] ^ (c >> 8); i++; }
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(p + i);
+        c = crc[(c ^ w) & 0xFF] ^ (c >> 8);
+        c = crc[(c ^ (w >> 8)) & 0xFF] ^ (c >> 8);
+        c = crc[(c ^ (w >> 16)) & 0xFF] ^ (c >> 8);
+        c = crc[(c ^ (w >> 24)) & 0xFF] ^ (c >> 8);
+    }
+    for (; i < n; i++) c = crc[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    if (~c != ld32(h + 20)) a.cand[(size_t) frame * a.cap + k].y = 0xFFFFFFFFu;   // payload CRC mismatch: not a segment
+}
+
+// one block per frame; dynamic shared memory: keys[np2], vals[np2]
+__global__ void __launch_bounds__(256) k_walk(ParseArgs a) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t frame = blockIdx.x;
+    uint32_t cnt = a.ncand[frame];
+    ParseInfo info;
+    info.w = info.h = 0; info.mean[0] = info.mean[1] = info.mean[2] = 0; info.any = 0; info.overflow = 0; info.naccepted = 0;
+    if (cnt > a.cap) {           // too many candidates for the device path: the host scans this frame
+        if (threadIdx.x == 0) { info.overflow = 1; a.info[frame] = info; }
+        return;
+    }
+    uint32_t np2 = 1;
+    while (np2 < cnt) np2 <<= 1;
+    uint32_t *keys = sm, *vals = sm + a.cap_pow2;
+    uint2 *cand = a.cand + (size_t) frame * a.cap;
+    for (uint32_t i = threadIdx.x; i < np2; i += 256) {
+        if (i < cnt) { const uint2 c = cand[i]; keys[i] = c.x; vals[i] = c.y; }
+        else { keys[i] = 0xFFFFFFFFu; vals[i] = 0xFFFFFFFFu; }
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= np2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < np2; i += 256) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const bool asc = (i & k) == 0;
+                    const uint32_t ki = keys[i], kl = keys[l];
+                    if ((ki > kl) == asc) { keys[i] = kl; keys[l] = ki; const uint32_t t = vals[i]; vals[i] = vals[l]; vals[l] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        const uint8_t *s = a.streams + (size_t) frame * a.stride;
+        uint64_t cur = 0;
+        uint32_t nacc = 0;
+        for (uint32_t i = 0; i < cnt; i++) {
+            if (vals[i] == 0xFFFFFFFFu) continue;        // failed the payload CRC
+            const uint32_t off = keys[i];
+            if (off < cur) continue;                      // inside a segment that was accepted before it
+            const uint8_t *h = s + off;
+            info.w = ld32(h + 8); info.h = ld32(h + 12);  // the LAST accepted header wins (icer_compress.c:454-456)
+            const uint32_t ch = a.chan == 1 ? 0 : (h[7] >> 4);
+            if (ch < 3) info.mean[ch] = (uint16_t) (h[2] | (h[3] << 8));
+            info.any = 1;
+            cand[nacc++] = make_uint2(off, vals[i]);      // accepted segments, in stream order
+            cur = (uint64_t) off + ICER_HDR_BYTES + vals[i];
+        }
+        info.naccepted = nacc;
+        a.info[frame] = info;
+    }
+}
+
+// accepted segments of the frames of one dimension group -> segment table.  One thread per frame, in stream order so
+// that a later duplicate overwrites an earlier one exactly like lib_icer's table assignment (icer_compress.c:453).
+__global__ void k_table(TableArgs t) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= t.nlist) return;
+    const uint32_t frame = t.list[k];
+    const uint2 *acc = t.cand + (size_t) frame * t.cap;
+    const uint8_t *s = t.streams + (size_t) frame * t.stride;
+    uint32_t *row = t.seg_off + (size_t) frame * t.nstreams;
+    const uint32_t n = t.info[frame].naccepted;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t off = acc[i].x;
+        const uint8_t *h = s + off;
+        const uint32_t level = h[4], sb = h[5], seg = h[6], lsb = h[7] & 0x0F, ch = t.chan == 1 ? 0 : (h[7] >> 4);
+        if (lsb >= t.planes || ch >= t.chan || level > t.max_level || sb > 3 || seg > ICER_MAX_SEGMENTS) continue;
+        const uint32_t unit = t.unit_lut[((ch * (t.max_level + 1) + level) * 4 + sb) * (ICER_MAX_SEGMENTS + 1) + seg];
+        if (unit == 0xFFFFFFFFu) continue;
+        row[unit * t.planes + lsb] = off;
+    }
+}
+
+}  // namespace
+
+int launch_parse(const ParseArgs &a, cudaStream_t st, LaunchStats &ls) {
+    int rc = upload_crc();
+    if (rc) return rc;
+    if (a.n == 0) return ICER_RESULT_OK;
+    CUDA_TRY(cudaMemsetAsync(a.ncand, 0, (size_t) a.n * 4, st));
+    for (uint32_t f0 = 0; f0 < a.n; f0 += 32768) {
+        ParseArgs b = a;
+        const uint32_t cnt = a.n - f0 < 32768 ? a.n - f0 : 32768;
+        b.streams += (size_t) f0 * a.stride; b.lens += f0; b.cand += (size_t) f0 * a.cap; b.ncand += f0; b.info += f0; b.n = cnt;
+        dim3 g1((unsigned) ((a.stride + 256 * 8 - 1) / (256 * 8)), cnt);
+        k_scan<<<g1, 256, 0, st>>>(b);
+        dim3 g2((a.cap + 127) / 128, cnt);
+        k_verify<<<g2, 128, 0, st>>>(b);
+        const size_t smem = (size_t) a.cap_pow2 * 8;
+        CUDA_TRY(cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        k_walk<<<cnt, 256, smem, st>>>(b);
+        ls.launches += 3;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+
+int launch_table(const TableArgs &t, cudaStream_t st, LaunchStats &ls) {
+    if (t.nlist == 0) return ICER_RESULT_OK;
+    k_table<<<(t.nlist + 63) / 64, 64, 0, st>>>(t);
+    ls.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
