@@ -35,7 +35,7 @@ struct icer_b200_ctx {
     std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int>, Plan *> plans;
     LaunchStats ls;
     DevBuf coefs, tmp, scratch, bits, crc, rings, out, out_prio, size_used, rc, keep, offp, offr, mean, ovf, misc,
-        streams, segoff, dims, frame_ok;
+        streams, segoff, dims, frame_ok, cand, ncand, pinfo, list;
     uint32_t ring_threads = 0;
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -106,7 +106,8 @@ void icer_b200_destroy(icer_b200_ctx *c) {
     cudaSetDevice(c->device);
     for (auto &kv : c->plans) { free_plan_device(*kv.second); delete kv.second; }
     DevBuf *all[] = {&c->coefs, &c->tmp, &c->scratch, &c->bits, &c->crc, &c->rings, &c->out, &c->out_prio, &c->size_used, &c->rc,
-                     &c->keep, &c->offp, &c->offr, &c->mean, &c->ovf, &c->misc, &c->streams, &c->segoff, &c->dims, &c->frame_ok};
+                     &c->keep, &c->offp, &c->offr, &c->mean, &c->ovf, &c->misc, &c->streams, &c->segoff, &c->dims, &c->frame_ok,
+                     &c->cand, &c->ncand, &c->pinfo, &c->list};
     for (auto b : all) b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -353,39 +354,54 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, 
     const size_t cap_px = (size_t) p->width * p->height;
     ev_record(c, 0, st);
 
-    // 1. the streams on the host (scanner) and on the device (decoder)
-    std::vector<uint64_t> lens(n);
-    std::vector<uint8_t> hstage;
-    const uint8_t *hs = streams;
+    // 1. the streams and their lengths on the device
+    int e;
     const uint8_t *d_streams = streams;
+    const uint64_t *d_lens = stream_len;
     const size_t total_bytes = n * stream_stride;
     if (host) {
-        memcpy(lens.data(), stream_len, n * 8);
-        int e;
         if ((e = c->streams.ensure(total_bytes + 16))) return e;
+        if ((e = c->dims.ensure(n * 8))) return e;
         CUDA_TRY(cudaMemcpyAsync(c->streams.p, streams, total_bytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->dims.p, stream_len, n * 8, cudaMemcpyHostToDevice, st));
         d_streams = c->streams.as<uint8_t>();
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(lens.data(), stream_len, n * 8, cudaMemcpyDeviceToHost, st));
-        hstage.resize(total_bytes);
-        CUDA_TRY(cudaMemcpyAsync(hstage.data(), streams, total_bytes, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        hs = hstage.data();
+        d_lens = c->dims.as<uint64_t>();
     }
-    // 2. scan every stream for CRC-valid segments (parallel over frames)
-    std::vector<Parsed> parsed(n);
-    {
-        unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 32));
-        if (n < 4) nt = 1;
-        std::vector<std::thread> th;
-        for (unsigned k = 0; k < nt; k++)
-            th.emplace_back([&, k]() {
-                for (size_t i = k; i < n; i += nt) {
-                    size_t len = std::min<uint64_t>(lens[i], stream_stride);
-                    parse_stream(hs + i * stream_stride, len, chan, parsed[i]);
-                }
-            });
-        for (auto &t : th) t.join();
+    // 2. scan every stream for CRC-valid segments on the device (parse.cu)
+    uint32_t cap = (uint32_t) std::min<uint64_t>(8192, stream_stride / ICER_HDR_BYTES + 1);
+    { const char *pc = getenv("ICER_B200_PARSE_CAP"); if (pc && atoi(pc) > 0) cap = (uint32_t) atoi(pc); }   // test hook
+    uint32_t cap_pow2 = 1;
+    while (cap_pow2 < cap) cap_pow2 <<= 1;
+    if ((e = c->cand.ensure((size_t) n * cap * 8))) return e;
+    if ((e = c->ncand.ensure(n * 4))) return e;
+    if ((e = c->pinfo.ensure(n * sizeof(ParseInfo)))) return e;
+    ParseArgs pa;
+    pa.streams = d_streams; pa.stride = stream_stride; pa.lens = d_lens; pa.n = (uint32_t) n; pa.chan = chan;
+    pa.cand = c->cand.as<uint2>(); pa.cap = cap; pa.cap_pow2 = cap_pow2; pa.ncand = c->ncand.as<uint32_t>();
+    pa.info = c->pinfo.as<ParseInfo>();
+    if ((e = launch_parse(pa, st, c->ls))) return e;
+    std::vector<ParseInfo> info(n);
+    CUDA_TRY(cudaMemcpyAsync(info.data(), c->pinfo.p, n * sizeof(ParseInfo), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // frames with more candidates than the device path holds are scanned on the host (never seen with real streams)
+    std::map<size_t, Parsed> host_parsed;
+    for (size_t i = 0; i < n; i++) {
+        if (!info[i].overflow) continue;
+        std::vector<uint8_t> tmp;
+        const uint8_t *hs = streams + i * stream_stride;
+        uint64_t len_i = 0;
+        if (host) len_i = stream_len[i];
+        else {
+            CUDA_TRY(cudaMemcpy(&len_i, stream_len + i, 8, cudaMemcpyDeviceToHost));
+            tmp.resize(stream_stride);
+            CUDA_TRY(cudaMemcpy(tmp.data(), streams + i * stream_stride, stream_stride, cudaMemcpyDeviceToHost));
+            hs = tmp.data();
+        }
+        Parsed ps;
+        parse_stream(hs, (size_t) std::min<uint64_t>(len_i, stream_stride), chan, ps);
+        info[i].w = ps.w; info[i].h = ps.h; info[i].any = ps.any;
+        for (int k = 0; k < 3; k++) info[i].mean[k] = ps.mean[k];
+        host_parsed[i] = std::move(ps);
     }
     ev_record(c, 1, st);
     // 3. per-frame status; frames are grouped by their header dimensions (one plan per group)
@@ -393,12 +409,11 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, 
     std::vector<uint32_t> hdims(n * 2, 0);
     std::map<std::pair<uint32_t, uint32_t>, std::vector<size_t>> groups;
     for (size_t i = 0; i < n; i++) {
-        hdims[2 * i] = parsed[i].w; hdims[2 * i + 1] = parsed[i].h;
-        if (!parsed[i].any) { hrc[i] = ICER_DECODER_OUT_OF_DATA; continue; }   // lib_icer: dimensions left uninitialised
-        if (cap_px < (size_t) parsed[i].w * parsed[i].h) { hrc[i] = ICER_BYTE_QUOTA_EXCEEDED; continue; }   // icer_compress.c:461-463
-        groups[{parsed[i].w, parsed[i].h}].push_back(i);
+        hdims[2 * i] = info[i].w; hdims[2 * i + 1] = info[i].h;
+        if (!info[i].any) { hrc[i] = ICER_DECODER_OUT_OF_DATA; continue; }   // lib_icer: dimensions left uninitialised
+        if (cap_px < (size_t) info[i].w * info[i].h) { hrc[i] = ICER_BYTE_QUOTA_EXCEEDED; continue; }   // icer_compress.c:461-463
+        groups[{info[i].w, info[i].h}].push_back(i);
     }
-    int e;
     if (host && (e = c->coefs.ensure(n * chan * cap_px * 2))) return e;
     if ((e = c->mean.ensure(n * chan * 2))) return e;
     if ((e = c->misc.ensure(64))) return e;
@@ -419,26 +434,42 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, 
         const size_t plane_px = (size_t) w * h;
         const uint32_t ngroups = (uint32_t) ((g.second.size() + 31) / 32);
         std::vector<int32_t> frame_of((size_t) ngroups * 32, -1);
-        std::vector<uint32_t> segoff(n * (size_t) pl->nstreams, 0xFFFFFFFFu);
+        std::vector<uint32_t> list;
         std::vector<uint16_t> hmean(n * chan, 0);
         size_t k = 0;
         for (size_t i : g.second) {
             frame_of[k++] = (int32_t) i;
-            for (auto &r : parsed[i].segs) {
+            if (!info[i].overflow) list.push_back((uint32_t) i);
+            for (uint32_t ch = 0; ch < chan; ch++) hmean[i * chan + ch] = info[i].mean[ch];
+        }
+        const size_t t_bytes = (size_t) ngroups * 32 * chan * plane_px * 2;
+        if ((e = c->tmp.ensure(std::max(t_bytes, n * chan * plane_px * 2)))) return e;
+        if ((e = c->segoff.ensure(n * (size_t) pl->nstreams * 4))) return e;
+        if ((e = c->frame_ok.ensure(frame_of.size() * 4))) return e;
+        if ((e = c->list.ensure(list.size() * 4 + 4))) return e;
+        CUDA_TRY(cudaMemsetAsync(c->segoff.p, 0xFF, n * (size_t) pl->nstreams * 4, st));       // 0xFFFFFFFF = absent
+        CUDA_TRY(cudaMemcpyAsync(c->list.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
+        TableArgs ta;
+        ta.list = c->list.as<uint32_t>(); ta.nlist = (uint32_t) list.size(); ta.cand = c->cand.as<uint2>(); ta.cap = cap;
+        ta.streams = d_streams; ta.stride = stream_stride; ta.info = c->pinfo.as<ParseInfo>();
+        ta.seg_off = c->segoff.as<uint32_t>(); ta.nstreams = pl->nstreams; ta.planes = pl->planes; ta.chan = chan;
+        ta.max_level = pl->max_stages; ta.unit_lut = pl->d_unit_lut;
+        if ((e = launch_table(ta, st, c->ls))) return e;
+        for (size_t i : g.second) {     // host-scanned frames (overflow fallback): their table rows come from the host
+            auto hp = host_parsed.find(i);
+            if (hp == host_parsed.end()) continue;
+            std::vector<uint32_t> rowv(pl->nstreams, 0xFFFFFFFFu);
+            for (auto &r : hp->second.segs) {
                 const int ch = chan == 1 ? 0 : (r.lsb_chan >> 4);
                 const int lsb = r.lsb_chan & 0x0F;
                 if (lsb >= (int) pl->planes) continue;
                 auto it = pl->unit_of.find(std::make_tuple(ch, (int) r.level, (int) r.subband, (int) r.seg));
                 if (it == pl->unit_of.end()) continue;
-                segoff[i * pl->nstreams + it->second * pl->planes + lsb] = r.off;
+                rowv[it->second * pl->planes + lsb] = r.off;
             }
-            for (uint32_t ch = 0; ch < chan; ch++) hmean[i * chan + ch] = parsed[i].mean[ch];
+            CUDA_TRY(cudaMemcpyAsync(c->segoff.as<uint32_t>() + i * pl->nstreams, rowv.data(), rowv.size() * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
         }
-        const size_t t_bytes = (size_t) ngroups * 32 * chan * plane_px * 2;
-        if ((e = c->tmp.ensure(std::max(t_bytes, n * chan * plane_px * 2)))) return e;
-        if ((e = c->segoff.ensure(segoff.size() * 4))) return e;
-        if ((e = c->frame_ok.ensure(frame_of.size() * 4))) return e;
-        CUDA_TRY(cudaMemcpyAsync(c->segoff.p, segoff.data(), segoff.size() * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(c->mean.p, hmean.data(), hmean.size() * 2, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(c->frame_ok.p, frame_of.data(), frame_of.size() * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 64, st));

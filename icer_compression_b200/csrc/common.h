@@ -59,6 +59,8 @@ struct Plan {
     // device copies
     Unit *d_units = nullptr;
     uint32_t *d_prio = nullptr, *d_rearr = nullptr, *d_soff = nullptr, *d_scap = nullptr;
+    std::vector<uint32_t> unit_lut;      // [chan][max_stages+1][4][ICER_MAX_SEGMENTS+1] -> unit index or ~0 (device scanner)
+    uint32_t *d_unit_lut = nullptr;
     // lookup (chan, level, subband, seg) -> unit index, for the decoder's segment table
     std::map<std::tuple<int, int, int, int>, uint32_t> unit_of;
 };
@@ -142,3 +144,28 @@ int launch_frames_to_T(const uint16_t *frames, uint16_t *T, uint32_t nframes, ui
 int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame_of, const uint16_t *mean, uint32_t ngroups,
                        uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, uint32_t llw, uint32_t llh, cudaStream_t st,
                        LaunchStats &ls);
+
+// ---- K6: device stream scanner (parse.cu) ------------------------------------------------------------
+struct ParseInfo {               // per frame, what lib_icer's scan loop leaves behind (icer_compress.c:443-459)
+    uint32_t w, h;               // from the LAST accepted header
+    uint16_t mean[3];            // LL mean per channel, last accepted header of that channel
+    uint8_t any, overflow;       // any segment found; too many candidates for the device path
+    uint32_t naccepted;
+};
+struct ParseArgs {
+    const uint8_t *streams; uint64_t stride; const uint64_t *lens; uint32_t n, chan;
+    uint2 *cand;                 // [n][cap] (offset, payload bytes); after k_walk: the accepted segments in stream order
+    uint32_t cap, cap_pow2;
+    uint32_t *ncand;             // [n]
+    ParseInfo *info;             // [n]
+};
+int launch_parse(const ParseArgs &a, cudaStream_t st, LaunchStats &ls);
+struct TableArgs {
+    const uint32_t *list; uint32_t nlist;      // batch indices of the frames of one dimension group
+    const uint2 *cand; uint32_t cap;
+    const uint8_t *streams; uint64_t stride;
+    const ParseInfo *info;
+    uint32_t *seg_off; uint32_t nstreams, planes, chan, max_level;
+    const uint32_t *unit_lut;
+};
+int launch_table(const TableArgs &t, cudaStream_t st, LaunchStats &ls);

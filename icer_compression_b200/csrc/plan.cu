@@ -174,6 +174,11 @@ int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages,
                 }
             }
     pl.nstreams = (uint32_t) pl.units.size() * planes;
+    pl.unit_lut.assign((size_t) chan * (max_stages + 1) * 4 * (ICER_MAX_SEGMENTS + 1), 0xFFFFFFFFu);
+    for (size_t k = 0; k < pl.units.size(); k++) {
+        const Unit &q = pl.units[k];
+        pl.unit_lut[(((size_t) q.chan * (max_stages + 1) + q.level) * 4 + q.subband) * (ICER_MAX_SEGMENTS + 1) + q.seg] = (uint32_t) k;
+    }
 
     // packets in the reference's insertion order, then a stable sort by (priority desc, subband asc)
     std::vector<Packet> pk;
@@ -245,7 +250,8 @@ int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages,
 }
 
 void free_plan_device(Plan &pl) {
-    cudaFree(pl.d_units); cudaFree(pl.d_prio); cudaFree(pl.d_rearr); cudaFree(pl.d_soff); cudaFree(pl.d_scap);
+    cudaFree(pl.d_units); cudaFree(pl.d_prio); cudaFree(pl.d_rearr); cudaFree(pl.d_soff); cudaFree(pl.d_scap); cudaFree(pl.d_unit_lut);
+    pl.d_unit_lut = nullptr;
     pl.d_units = nullptr; pl.d_prio = pl.d_rearr = pl.d_soff = pl.d_scap = nullptr;
 }
 
@@ -262,5 +268,7 @@ int upload_plan(Plan &pl) {
     CUDA_TRY(cudaMemcpy(pl.d_rearr, pl.rearr_order.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(pl.d_soff, pl.scratch_off.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(pl.d_scap, pl.scratch_cap.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&pl.d_unit_lut, pl.unit_lut.size() * 4));
+    CUDA_TRY(cudaMemcpy(pl.d_unit_lut, pl.unit_lut.data(), pl.unit_lut.size() * 4, cudaMemcpyHostToDevice));
     return ICER_RESULT_OK;
 }

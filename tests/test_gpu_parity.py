@@ -329,3 +329,33 @@ def test_crc_valid_garbage_payloads(ctx9, oracle9):
         o = oracle9.decompress(v, 1, 96 * 128, 2, 0, 4)
         assert o["rc"] == int(dec["rc"][i]), i
         assert (o["images"][0].ravel() == dec["frames"][i, 0]).all(), i
+
+
+def test_scanner_overflow_fallback(ctx9, oracle9):
+    """More segment candidates than the device scanner holds -> that frame is scanned on the host; same result."""
+    img = harness.load_boat()[:128, :160].copy()
+    s = oracle9.compress([img], 3, 0, 5, 128 * 160)["stream"]
+    ref = ctx9.decompress_batch([s, s[: len(s) // 2]], 1, 160, 128, 3, 0, 5)
+    os.environ["ICER_B200_PARSE_CAP"] = "16"
+    try:
+        got = ctx9.decompress_batch([s, s[: len(s) // 2]], 1, 160, 128, 3, 0, 5)
+    finally:
+        del os.environ["ICER_B200_PARSE_CAP"]
+    assert (ref["rc"] == got["rc"]).all() and (ref["frames"] == got["frames"]).all()
+    o = oracle9.decompress(s, 1, 128 * 160, 3, 0, 5)
+    assert (o["images"][0].ravel() == got["frames"][0, 0]).all()
+
+
+def test_mixed_dimensions_in_one_batch(ctx9, oracle9):
+    """Streams of different image sizes in one decode call: dimensions come from the headers, like lib_icer."""
+    a = oracle9.synth(96, 64, 1, 5, 0)
+    b = oracle9.synth(64, 80, 2, 5, 1)
+    sa = oracle9.compress([a], 3, 0, 4, 96 * 64)["stream"]
+    sb = oracle9.compress([b], 3, 0, 4, 64 * 80)["stream"]
+    dec = ctx9.decompress_batch([sa, sb, sa, b"", sb], 1, 100, 80, 3, 0, 4)     # capacity 8000 px per slot
+    assert list(dec["rc"]) == [0, 0, 0, -7, 0]
+    assert [tuple(d) for d in dec["dims"]] == [(96, 64), (64, 80), (96, 64), (0, 0), (64, 80)]
+    oa = oracle9.decompress(sa, 1, 8000, 3, 0, 4)["images"][0].ravel()
+    ob = oracle9.decompress(sb, 1, 8000, 3, 0, 4)["images"][0].ravel()
+    assert (dec["frames"][0, 0][:oa.size] == oa).all() and (dec["frames"][2, 0][:oa.size] == oa).all()
+    assert (dec["frames"][1, 0][:ob.size] == ob).all() and (dec["frames"][4, 0][:ob.size] == ob).all()
