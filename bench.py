@@ -252,10 +252,8 @@ def run_ours(args, wl, rank, world, local_rank):
     total_ms = ev[0].elapsed_time(ev[-1])
     enc_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)) / args.steps
     dec_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)) / args.steps
-    if dist is not None:
-        t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, enc_ms, dec_ms = [float(x) for x in t.tolist()]
+    from icer_compression_b200.shard import max_over_ranks
+    total_ms, enc_ms, dec_ms = max_over_ranks([total_ms, enc_ms, dec_ms], device=dev)   # the slowest rank defines the step
     ms_per_step = total_ms / args.steps
     px_step = world * n * w * h
     value = px_step / (ms_per_step * 1e-3) / 1e6
@@ -301,10 +299,7 @@ def run_ours(args, wl, rank, world, local_rank):
         wall_ms = (time.perf_counter() - t0) * 1e3 / ksteps
         ev_ms = e0.elapsed_time(e1) / ksteps
         e2e_ms = max(wall_ms, ev_ms)
-        if dist is not None:
-            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
+        e2e_ms = max_over_ranks([e2e_ms], device=dev)[0]
         sb = int(uh.sum().item())
         e2e = {"value": round(px_step / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mpixels/s", "ms_per_step": round(e2e_ms, 3),
                "h2d_bytes_per_step": int(n * chan * h * w * 2 + n * quota), "d2h_bytes_per_step": int(sb + n * chan * h * w * 2),
