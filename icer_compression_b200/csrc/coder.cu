@@ -484,6 +484,7 @@ struct DecShared {
     volatile uint8_t deadf[16][32];      // lane's plane is void because a plane above it hit a decode error
     volatile uint8_t errf[16][32];
     uint8_t pres[16][32];
+    volatile uint32_t anyerr;            // some lane of this block hit a decode error (rare): only then are deadf/errf consulted
     unsigned long long work;
 };
 // followed in dynamic shared memory by: cnt[17][BT], depth[17][BT], stlow[17][BT]  (BT = blockDim.x)
@@ -609,6 +610,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
         __syncthreads();
         if (t == 0) S.work = atomicAdd(a.work_counter, 1ull);
         if (t < 16) S.prog[t] = 0;
+        if (t == 0) S.anyerr = 0;
         __syncthreads();
         const unsigned long long wid = S.work;
         if (wid >= total) break;
@@ -652,14 +654,20 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
         while (pos < px && __any_sync(0xffffffffu, run)) {
             uint32_t limit = px;
             if (j > 0) {
-                if (run && S.deadf[j - 1][lane] | S.errf[j - 1][lane]) { run = false; dead = true; S.deadf[j][lane] = 1; }
                 const uint32_t up = S.prog[j - 1];
                 __threadfence_block();
+                if (S.anyerr) {     // an error above voids this plane for that frame
+                    if (run && (S.deadf[j - 1][lane] | S.errf[j - 1][lane])) { run = false; dead = true; S.deadf[j][lane] = 1; }
+                }
                 if (up < px) limit = (a.debug_flags & 2u) ? 0u : (up > lag ? up - lag : 0u);
-                if (run && S.deadf[j - 1][lane] | S.errf[j - 1][lane]) { run = false; dead = true; S.deadf[j][lane] = 1; }
             }
-            if (pos >= limit) { __nanosleep(64); continue; }
-            uint32_t stop = pos + 16 < limit ? pos + 16 : limit;      // re-check progress every 16 pixels
+            if (pos >= limit) {
+                // the plane above is not far enough ahead yet: sleep roughly as long as it needs for the missing pixels
+                const uint32_t missing = pos + 1 - limit + (limit == 0 ? lag : 0);
+                __nanosleep(missing > 16 ? 2000 : 200);
+                continue;
+            }
+            uint32_t stop = pos + 32 < limit ? pos + 32 : limit;      // re-check progress every 32 pixels
             for (; pos < stop; pos++) {
                 uint16_t *p = seg + (size_t) row * RS + (size_t) col * 32;
                 const bool up_ = row > 0, dn = row + 1 < sh, rt = col + 1 < sw;
@@ -715,7 +723,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
                         bool refilled = false;
                         if (depth <= 0 || dc.words - (sl & 0xFFFFFFu) >= ICER_RING) {
                             const int rc = dc.refill(bin, depth, low);
-                            if (rc != ICER_RESULT_OK) { run = false; S.errf[j][lane] = 1; todo = 0; break; }
+                            if (rc != ICER_RESULT_OK) { run = false; S.errf[j][lane] = 1; S.anyerr = 1; todo = 0; break; }
                             refilled = true;
                         }
                         const uint32_t stamp = refilled ? (dc.words & 0xFFFFFFu) : (sl & 0xFFFFFFu);
