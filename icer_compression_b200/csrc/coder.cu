@@ -343,11 +343,14 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
             const bool up = row > 0, dn = row + 1 < sh;
             const uint16_t *p = seg + (size_t) row * RS;
             uint32_t a0 = 0, a1 = up ? p[-RS] : 0, a2, b0 = 0, b1 = p[0], b2, c0 = 0, c1 = dn ? p[RS] : 0, c2;
+            // the column after next is fetched one pixel early so that the loads overlap the coding of this pixel
+            uint32_t a2n = (up && sw > 1) ? p[32 - RS] : 0, b2n = sw > 1 ? p[32] : 0, c2n = (dn && sw > 1) ? p[32 + RS] : 0;
             for (int col = 0; col < sw; col++, p += 32) {
-                const bool rt = col + 1 < sw;
-                a2 = (up && rt) ? p[32 - RS] : 0;
-                b2 = rt ? p[32] : 0;
-                c2 = (dn && rt) ? p[32 + RS] : 0;
+                a2 = a2n; b2 = b2n; c2 = c2n;
+                const bool rt2 = col + 2 < sw;
+                a2n = (up && rt2) ? p[64 - RS] : 0;
+                b2n = rt2 ? p[64] : 0;
+                c2n = (dn && rt2) ? p[64 + RS] : 0;
                 const uint32_t v = b1;
                 const bool quiet = ((((a0 | a1 | a2 | b0 | b1 | b2 | c0 | c1 | c2) & 0x7FFF) >> lsb) == 0);
                 // micro-ops: bit0 = apply the pending fast run, bit1 = magnitude decision, bit2 = sign decision
@@ -478,16 +481,34 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
 // group.  The warps form a pipeline: warp j may process pixel n once warp j-1 has finished pixel n + w + 1 (its
 // right/down neighbours are taken one plane up).  Progress is published in shared memory; a warp advances only when
 // all of its live lanes can, so its position -- and therefore every address and edge test -- stays warp-uniform.
+// Work items of the decoder are TASKS (chain, bit plane).  A block is a pool of DEC_WARPS warps that take tasks in
+// order (chain-major, most significant plane first); task (c, p) may process pixel n of frame f once task (c, p+1)
+// has finished pixel n + w + 1 of that frame (its right/down neighbours are taken one plane up).  A task with a
+// smaller number has always been taken by some warp already, so waiting on it cannot deadlock; there is no block
+// barrier anywhere, so the quick (quiet) upper planes run ahead into the next chains while the dense lower planes are
+// still being decoded.  Chains in flight occupy one of DEC_SLOTS slots of progress / flag state in shared memory.
+constexpr int DEC_WARPS = 8;
+constexpr int DEC_BT = DEC_WARPS * 32;
+constexpr int DEC_SLOTS = 4;
+
+struct DecSlot {
+    volatile uint32_t chain;             // chain ordinal (within this block) that owns the slot; ~0 = never used
+    volatile uint32_t freed;             // all planes done and cleaned up: the slot may be re-used
+    volatile uint32_t done;              // planes finished
+    volatile uint32_t anyerr;            // some lane hit a decode error (rare): only then are deadf / errf consulted
+    volatile unsigned long long wid;     // global work id = group * nunits + unit
+    volatile uint32_t prog[15];          // pixels completed per plane (warp-uniform position)
+    volatile uint32_t posd[15][32];      // per lane: pixels it has (possibly) written -- needed to undo a voided plane
+    volatile uint8_t deadf[15][32];      // lane's plane is void because a plane above it hit a decode error
+    volatile uint8_t errf[15][32];       // lane hit a decode error in this plane
+};
 struct DecShared {
     SmemTables T;
-    volatile uint32_t prog[16];          // pixels completed per plane-warp
-    volatile uint8_t deadf[16][32];      // lane's plane is void because a plane above it hit a decode error
-    volatile uint8_t errf[16][32];
-    uint8_t pres[16][32];
-    volatile uint32_t anyerr;            // some lane of this block hit a decode error (rare): only then are deadf/errf consulted
-    unsigned long long work;
+    DecSlot slot[DEC_SLOTS];
+    uint32_t next_task;
+    volatile uint32_t k_end;             // first chain ordinal that does not exist (work exhausted)
 };
-// followed in dynamic shared memory by: cnt[17][BT], depth[17][BT], stlow[17][BT]  (BT = blockDim.x)
+// followed in dynamic shared memory by: cnt[17][DEC_BT], depth[17][DEC_BT], stlow[17][DEC_BT]
 
 struct Dec {
     const SmemTables &T;
@@ -579,25 +600,26 @@ struct Dec {
     }
 };
 
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
+__global__ void __launch_bounds__(DEC_BT, 3) k_decode(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecShared &S = *reinterpret_cast<DecShared *>(smem_raw);
-    const int t = threadIdx.x, BT = blockDim.x;
+    const int t = threadIdx.x;
+    constexpr int BT = DEC_BT;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(DecShared) + 15) & ~(size_t) 15));
     int32_t *depthA = reinterpret_cast<int32_t *>(cnt + 17 * BT);
     uint32_t *stlow = reinterpret_cast<uint32_t *>(depthA + 17 * BT);
-    {   // tables
+    {   // tables + pool state
         for (int i = t; i < 8 * 32; i += BT) (&S.T.v2v[0][0])[i] = (&c_tab.dlut[0][0])[i];
         for (int i = t; i < 45; i += BT) S.T.ctx_hv[i] = c_tab.ctx_hv[i];
         for (int i = t; i < 25; i += BT) { S.T.ctx_hh[i] = c_tab.ctx_hh[i]; S.T.ctx_sign[i] = c_tab.ctx_sign[i]; S.T.sign_pred[i] = c_tab.sign_pred[i]; }
         for (int i = t; i < 17; i += BT) { S.T.gol_m[i] = c_tab.gol_m[i]; S.T.gol_l[i] = c_tab.gol_l[i]; S.T.gol_i[i] = c_tab.gol_i[i]; }
         for (int i = t; i < 16; i += BT) S.T.cutoff[i] = c_tab.cutoff[i];
+        if (t < DEC_SLOTS) { S.slot[t].chain = 0xFFFFFFFFu; S.slot[t].freed = 1; S.slot[t].done = 0; S.slot[t].anyerr = 0; }
+        if (t == 0) { S.next_task = 0; S.k_end = 0xFFFFFFFFu; }
     }
+    __syncthreads();
     const int lane = t & 31;
-    const int j = t >> 5;                            // warp index = plane index from the top
     const int P = (int) a.planes;
-    const int lsb = P - 1 - j;
     const unsigned long long total = (unsigned long long) a.ngroups * a.nunits;
     const uint32_t nstreams = a.nunits * a.planes;
     const uint8_t *buf_end = a.streams + a.total_bytes;
@@ -607,44 +629,70 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
     const bool fast_ok = !(a.debug_flags & 1u);
 
     for (;;) {
-        __syncthreads();
-        if (t == 0) S.work = atomicAdd(a.work_counter, 1ull);
-        if (t < 16) S.prog[t] = 0;
-        if (t == 0) S.anyerr = 0;
-        __syncthreads();
-        const unsigned long long wid = S.work;
-        if (wid >= total) break;
+        uint32_t task = 0;
+        if (lane == 0) task = atomicAdd(&S.next_task, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        const uint32_t k = task / (uint32_t) P;          // chain ordinal within this block
+        const int j = (int) (task % (uint32_t) P);       // plane index from the top
+        const int lsb = P - 1 - j;
+        DecSlot &sl = S.slot[k % DEC_SLOTS];
+        // ---- claim / find the slot of chain k ------------------------------------------------------------
+        if (j == 0) {
+            // the first task of a chain recycles the slot of chain k - DEC_SLOTS and fetches the global work item
+            bool gone = false;
+            if (lane == 0 && k >= (uint32_t) DEC_SLOTS)
+                while (!(sl.chain == k - DEC_SLOTS && sl.freed)) { if (S.k_end <= k) { gone = true; break; } __nanosleep(200); }
+            gone = __shfl_sync(0xffffffffu, gone ? 1 : 0, 0) != 0;
+            if (gone) break;
+            __threadfence_block();
+            for (int q = 0; q < 15; q++) { sl.deadf[q][lane] = 0; sl.errf[q][lane] = 0; sl.posd[q][lane] = 0; }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned long long wid = atomicAdd(a.work_counter, 1ull);
+                for (int q = 0; q < 15; q++) sl.prog[q] = 0;
+                sl.done = 0; sl.anyerr = 0; sl.freed = 0; sl.wid = wid;
+                if (wid >= total && S.k_end > k) S.k_end = k;
+                __threadfence_block();
+                sl.chain = k;
+            }
+            __syncwarp();
+        } else {
+            bool gone = false;
+            if (lane == 0) while (sl.chain != k) { if (S.k_end <= k) { gone = true; break; } __nanosleep(100); }
+            gone = __shfl_sync(0xffffffffu, gone ? 1 : 0, 0) != 0;
+            if (gone) break;
+        }
+        __threadfence_block();
+        const unsigned long long wid = sl.wid;
+        if (wid >= total) break;                         // no more chains: every later task is void as well
         const uint32_t g = (uint32_t) (wid / a.nunits), ui = (uint32_t) (wid % a.nunits);
         const Unit u = a.units[ui];
         const int32_t frame = a.frame_of[g * 32 + lane];
-        bool present = false;
+        bool alive = false;
         Dec dc(S.T);
         if (frame >= 0) {
-            const uint32_t off = a.seg_off[(size_t) frame * nstreams + ui * a.planes + lsb];
-            if (off != 0xFFFFFFFFu) {
+            // a plane is decoded only if it and every plane above it are present (icer_partition.c:431)
+            const uint32_t *row = a.seg_off + (size_t) frame * nstreams + ui * a.planes;
+            alive = true;
+            for (int q = P - 1; q > lsb; q--) alive = alive && row[q] != 0xFFFFFFFFu;
+            const uint32_t off = row[lsb];
+            if (off == 0xFFFFFFFFu) alive = false;
+            if (alive) {
                 const uint8_t *hd = a.streams + (size_t) frame * a.stream_stride + off;
-                present = true;
                 dc.start(hd + ICER_HDR_BYTES, buf_end, hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24));
             }
         }
-        S.pres[j][lane] = present ? 1 : 0;
-        S.deadf[j][lane] = 0;
-        S.errf[j][lane] = 0;
-        __syncthreads();
-        // a plane is decoded only if every plane above it is present (icer_partition.c:431)
-        bool alive = present;
-        for (int q = 0; q < j; q++) alive = alive && S.pres[q][lane];
-
         uint16_t *seg = a.coefsT + (((size_t) g * a.chan + u.chan) * plane_px + (size_t) u.y * W + u.x) * 32 + lane;
         const int sw = u.w, sh = u.h, sb = u.subband;
         const uint32_t px = (uint32_t) sw * (uint32_t) sh;
-        const uint32_t lag = (uint32_t) sw + 1;      // plane p may run at most this far behind plane p+1
+        const uint32_t lag = (uint32_t) sw + 2;      // plane p stays this far behind plane p+1 (needs pixel n + w + 1, prefetches n + w + 2)
 #pragma unroll
         for (int c = 0; c < 17; c++) { cnt[c * BT + t] = (2u << 16) | 4u; depthA[c * BT + t] = 0; stlow[c * BT + t] = 0; }
 
         uint32_t pos = 0;                  // warp-uniform
         int row = 0, col = 0;
-        uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0, a2n = 0, b2n = 0, c2n = 0;
         uint32_t fz_left = 0, fz_run = 0;
         int fz_bin = 0;
         bool run = alive;                  // this lane still decodes
@@ -654,27 +702,29 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
         while (pos < px && __any_sync(0xffffffffu, run)) {
             uint32_t limit = px;
             if (j > 0) {
-                const uint32_t up = S.prog[j - 1];
+                const uint32_t up = sl.prog[j - 1];
                 __threadfence_block();
-                if (S.anyerr) {     // an error above voids this plane for that frame
-                    if (run && (S.deadf[j - 1][lane] | S.errf[j - 1][lane])) { run = false; dead = true; S.deadf[j][lane] = 1; }
+                if (sl.anyerr) {     // an error above voids this plane for that frame
+                    if (run && (sl.deadf[j - 1][lane] | sl.errf[j - 1][lane])) { run = false; dead = true; sl.deadf[j][lane] = 1; }
                 }
                 if (up < px) limit = (a.debug_flags & 2u) ? 0u : (up > lag ? up - lag : 0u);
             }
-            if (pos >= limit) {
-                // the plane above is not far enough ahead yet: sleep roughly as long as it needs for the missing pixels
-                const uint32_t missing = pos + 1 - limit + (limit == 0 ? lag : 0);
-                __nanosleep(missing > 16 ? 2000 : 200);
-                continue;
-            }
+            if (pos >= limit) { __nanosleep(300); continue; }   // the plane above is not far enough ahead yet
             uint32_t stop = pos + 32 < limit ? pos + 32 : limit;      // re-check progress every 32 pixels
             for (; pos < stop; pos++) {
                 uint16_t *p = seg + (size_t) row * RS + (size_t) col * 32;
                 const bool up_ = row > 0, dn = row + 1 < sh, rt = col + 1 < sw;
-                if (col == 0) { a0 = b0 = c0 = 0; a1 = up_ ? p[-RS] : 0; b1 = p[0]; c1 = dn ? p[RS] : 0; }
-                a2 = (up_ && rt) ? p[32 - RS] : 0;
-                b2 = rt ? p[32] : 0;
-                c2 = (dn && rt) ? p[32 + RS] : 0;
+                if (col == 0) {
+                    a0 = b0 = c0 = 0; a1 = up_ ? p[-RS] : 0; b1 = p[0]; c1 = dn ? p[RS] : 0;
+                    a2n = (up_ && rt) ? p[32 - RS] : 0; b2n = rt ? p[32] : 0; c2n = (dn && rt) ? p[32 + RS] : 0;
+                }
+                a2 = a2n; b2 = b2n; c2 = c2n;
+                {   // fetch the column after next one pixel early (overlaps the coding of this pixel)
+                    const bool rt2 = col + 2 < sw;
+                    a2n = (up_ && rt2) ? p[64 - RS] : 0;
+                    b2n = rt2 ? p[64] : 0;
+                    c2n = (dn && rt2) ? p[64 + RS] : 0;
+                }
                 if (run) {
                     uint32_t v = b1;
                     const bool quiet = ((((a0 | a1 | a2 | b0 | b1 | b2 | c0 | c1 | c2) & 0x7FFF) >> lsb) == 0);
@@ -718,15 +768,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
                         }
                         // next decoded bit of `bin` (icer_decoding.c:127, :186-192)
                         int depth = depthA[bin * BT + t];
-                        const uint32_t sl = stlow[bin * BT + t];
-                        uint32_t low = sl >> 24;
+                        const uint32_t slw = stlow[bin * BT + t];
+                        uint32_t low = slw >> 24;
                         bool refilled = false;
-                        if (depth <= 0 || dc.words - (sl & 0xFFFFFFu) >= ICER_RING) {
+                        if (depth <= 0 || dc.words - (slw & 0xFFFFFFu) >= ICER_RING) {
                             const int rc = dc.refill(bin, depth, low);
-                            if (rc != ICER_RESULT_OK) { run = false; S.errf[j][lane] = 1; S.anyerr = 1; todo = 0; break; }
+                            if (rc != ICER_RESULT_OK) { run = false; sl.errf[j][lane] = 1; sl.anyerr = 1; todo = 0; break; }
                             refilled = true;
                         }
-                        const uint32_t stamp = refilled ? (dc.words & 0xFFFFFFu) : (sl & 0xFFFFFFu);
+                        const uint32_t stamp = refilled ? (dc.words & 0xFFFFFFu) : (slw & 0xFFFFFFu);
                         if (st == 1 && quiet && !inv && bin > 7 && fast_ok) {
                             // quiet fast path: the run of pending zeros of this Golomb bin is taken without touching the stack
                             const uint32_t zeros = (uint32_t) depth - (low & 1u);
@@ -767,35 +817,46 @@ __global__ void __launch_bounds__(MAXT, MINB) k_decode(DecodeArgs a) {
             }
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) S.prog[j] = pos;
+            if (lane == 0) sl.prog[j] = pos;
         }
+        // ---- task finished -------------------------------------------------------------------------------
+        sl.posd[j][lane] = done_px;
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) S.prog[j] = 0xFFFFFFFFu;            // finished (or nothing left to do): never hold the planes below
-        // lanes that never started because a plane above died before they looked
-        __syncthreads();
-        if (j > 0 && alive && !dead && (S.deadf[j - 1][lane] | S.errf[j - 1][lane])) dead = true;
-        // propagate "dead" down the chain (a plane may have finished before the plane above it failed)
-        for (int q = 1; q < P; q++) {
-            if (j == q && alive && (S.deadf[q - 1][lane] | S.errf[q - 1][lane])) { dead = true; S.deadf[q][lane] = 1; }
-            __syncthreads();
+        uint32_t old = 0;
+        if (lane == 0) {
+            sl.prog[j] = 0xFFFFFFFFu;                 // never hold the planes below
+            __threadfence_block();
+            old = atomicAdd((uint32_t *) &sl.done, 1u);
         }
-        // A decode error voids every plane below it (lib_icer stops the chain there and never decodes them,
-        // icer_partition.c:441).  Those planes ran ahead in the pipeline: take their bits back.
-        if (dead && alive) {
-            for (uint32_t n = 0; n < done_px; n++) {
-                uint16_t *q = seg + (size_t) (n / (uint32_t) sw) * RS + (size_t) (n % (uint32_t) sw) * 32;
-                *q = (uint16_t) (*q & ~(1u << lsb));
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == (uint32_t) P - 1) {
+            // last plane of the chain to finish.  A decode error voids every plane below it (lib_icer stops the chain
+            // there and never decodes them, icer_partition.c:441); those planes ran ahead in the pipeline: take their
+            // bits back, then clear the sign of coefficients whose magnitude is now zero.  Lane = frame.
+            __threadfence_block();
+            if (sl.anyerr) {
+                bool voided = false, any_void = false;
+                for (int q = 0; q < P; q++) {
+                    if (q > 0 && (voided || sl.errf[q - 1][lane])) voided = true;     // everything below an error
+                    if (!voided) continue;
+                    const uint32_t npx = sl.posd[q][lane];
+                    if (npx) any_void = true;
+                    const uint32_t bitm = ~(1u << (P - 1 - q));
+                    for (uint32_t n = 0; n < npx; n++) {
+                        uint16_t *qq = seg + (size_t) (n / (uint32_t) sw) * RS + (size_t) (n % (uint32_t) sw) * 32;
+                        *qq = (uint16_t) (*qq & bitm);
+                    }
+                }
+                if (any_void)
+                    for (uint32_t n = 0; n < px; n++) {
+                        uint16_t *qq = seg + (size_t) (n / (uint32_t) sw) * RS + (size_t) (n % (uint32_t) sw) * 32;
+                        if ((*qq & 0x7FFF) == 0 && *qq != 0) *qq = 0;
+                    }
             }
-        }
-        __syncthreads();
-        // a sign bit set by a voided plane belongs to a coefficient whose magnitude is now zero; the highest voided
-        // plane of each frame cleans up
-        if (dead && alive && !(j > 0 && S.deadf[j - 1][lane])) {
-            for (uint32_t n = 0; n < px; n++) {
-                uint16_t *q = seg + (size_t) (n / (uint32_t) sw) * RS + (size_t) (n % (uint32_t) sw) * 32;
-                if ((*q & 0x7FFF) == 0 && *q != 0) *q = 0;
-            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) sl.freed = 1;
         }
     }
 }
@@ -990,21 +1051,19 @@ int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls) {
     int rc = upload_tables();
     if (rc) return rc;
     if (a.planes < 1 || a.planes > 15) return ICER_BITPLANE_OUT_OF_RANGE;
-    const int BT = (int) a.planes * 32;
-    const size_t smem = ((sizeof(DecShared) + 15) & ~(size_t) 15) + (size_t) 3 * 17 * BT * 4;
-    // two register budgets: up to 9 planes (288 threads, 3 blocks / SM) and up to 15 planes (480 threads)
-    void (*kern)(DecodeArgs) = a.planes <= 9 ? k_decode<288, 3> : k_decode<480, 1>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const size_t smem = ((sizeof(DecShared) + 15) & ~(size_t) 15) + (size_t) 3 * 17 * DEC_BT * 4;
+    CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int dev = 0, sms = 148, bps = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BT, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_decode, DEC_BT, smem);
     if (bps < 1) bps = 1;
+    // a block of DEC_WARPS warps keeps about DEC_WARPS / planes chains in flight
     const unsigned long long total = (unsigned long long) a.ngroups * a.nunits;
-    unsigned long long blocks = total;
+    unsigned long long blocks = (total * a.planes + DEC_WARPS - 1) / DEC_WARPS;
     if (blocks > (unsigned long long) sms * bps) blocks = (unsigned long long) sms * bps;
     if (blocks == 0) return ICER_RESULT_OK;
-    kern<<<(unsigned) blocks, BT, smem, st>>>(a);
+    k_decode<<<(unsigned) blocks, DEC_BT, smem, st>>>(a);
     ls.launches++;
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;
