@@ -6,8 +6,8 @@
 Writes (all small):
   boat512.u8.gz            512x512 gray of /root/reference/boat.512.bmp (stb's 3->1 channel conversion,
                            example/inc/stb_image.h:1747-1750), the input of BASELINE config 1
-  boatcolor512.yuv.u8.gz   Y,Cb,Cr planes of boatcolor.512.bmp after the tools' conversion
-                           (example/inc/color_util.h:27-29, example/src/icer_util.c:69-92)
+  boatcolor512.rgb.u8.gz   RGB pixels of boatcolor.512.bmp (tests derive Y,Cb,Cr with the tools' integer conversion,
+                           example/inc/color_util.h:27-29, example/src/icer_util.c:69-92)
   golden.json              for a list of (input, params): rc, size_used, md5 of the rearranged stream,
                            md5 of the decoded image(s), md5 of the coefficient array the reference leaves
                            in the caller's buffer -- all produced by oracle/_ref/libicer_ref{,15}.so
@@ -60,8 +60,8 @@ def main():
     cb = clip(((36962 * (b - y)) >> 16) + 128)
     cr = clip(((46727 * (r - y)) >> 16) + 128)
     yuv = np.stack([y, cb, cr]).astype(np.uint8)
-    with gzip.GzipFile(os.path.join(HERE, "boatcolor512.yuv.u8.gz"), "wb", mtime=0) as f:
-        f.write(yuv.tobytes())
+    with gzip.GzipFile(os.path.join(HERE, "boatcolor512.rgb.u8.gz"), "wb", mtime=0) as f:
+        f.write(rgb.astype(np.uint8).tobytes())
 
     ref9 = harness.Ref(False)
     ref15 = harness.Ref(True)

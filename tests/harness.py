@@ -224,9 +224,37 @@ def load_boat():
         return np.frombuffer(f.read(), dtype=np.uint8).reshape(512, 512).astype(np.uint16)
 
 
+def load_boatcolor_rgb():
+    """512x512x3 RGB pixels of the reference's boatcolor.512.bmp (tests/golden/boatcolor512.rgb.u8.gz)."""
+    import gzip
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "boatcolor512.rgb.u8.gz"), "rb") as f:
+        return np.frombuffer(f.read(), dtype=np.uint8).reshape(512, 512, 3)
+
+
+def rgb_to_yuv(rgb):
+    """The reference tools' integer RGB -> YCbCr (example/inc/color_util.h:27-29, example/src/icer_util.c:69-92)."""
+    x = rgb.astype(np.int64)
+    r, g, b = x[..., 0], x[..., 1], x[..., 2]
+    clip = lambda v: np.clip(v, 0, 255)
+    y = clip((19595 * r + 38470 * g + 7471 * b) >> 16)
+    cb = clip(((36962 * (b - y)) >> 16) + 128)
+    cr = clip(((46727 * (r - y)) >> 16) + 128)
+    return [y.astype(np.uint16), cb.astype(np.uint16), cr.astype(np.uint16)]
+
+
 def load_boatcolor_yuv():
     """512x512 Y,U,V planes (uint16) of the reference's boatcolor.512.bmp after the tools' RGB->YCbCr."""
-    import gzip
-    with gzip.open(os.path.join(ROOT, "tests", "golden", "boatcolor512.yuv.u8.gz"), "rb") as f:
-        a = np.frombuffer(f.read(), dtype=np.uint8).reshape(3, 512, 512).astype(np.uint16)
-    return [a[0], a[1], a[2]]
+    return rgb_to_yuv(load_boatcolor_rgb())
+
+
+def write_bmp24(path, rgb):
+    """24-bit bottom-up BMP (what stb_image reads back verbatim)."""
+    h, w, _ = rgb.shape
+    stride = (w * 3 + 3) & ~3
+    rows = np.zeros((h, stride), dtype=np.uint8)
+    rows[:, :w * 3] = rgb[::-1, :, ::-1].reshape(h, w * 3)
+    hdr = b"BM" + (54 + stride * h).to_bytes(4, "little") + b"\0\0\0\0" + (54).to_bytes(4, "little")
+    hdr += (40).to_bytes(4, "little") + w.to_bytes(4, "little") + h.to_bytes(4, "little") + (1).to_bytes(2, "little")
+    hdr += (24).to_bytes(2, "little") + b"\0" * 4 + (stride * h).to_bytes(4, "little") + (2835).to_bytes(4, "little") * 2 + b"\0" * 8
+    with open(path, "wb") as f:
+        f.write(hdr + rows.tobytes())
