@@ -13,6 +13,7 @@ ICER_BYTE_QUOTA_EXCEEDED = -5
 ICER_FATAL_ERROR = -10
 FILTERS = dict(A=0, B=1, C=2, D=3, E=4, F=5, Q=6)
 MEM_HOST, MEM_DEVICE = 0, 1
+PIX_U16, PIX_U8, PIX_RGB888 = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -65,6 +66,8 @@ def load_library():
     L.icer_b200_set_scratch_bits.argtypes = [vp, C.c_int]
     L.icer_b200_compress_batch_u16.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, vp, C.c_size_t, vp, vp, vp, vp, C.c_int, vp]
     L.icer_b200_decompress_batch_u16.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, vp, C.c_size_t, vp, vp, vp, C.c_int, vp]
+    L.icer_b200_compress_batch_pix.argtypes = [vp, C.POINTER(_Params), vp, C.c_int, C.c_size_t, vp, C.c_size_t, vp, vp, C.c_int, vp]
+    L.icer_b200_decompress_batch_pix.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, vp, C.c_size_t, vp, C.c_int, vp, vp, C.c_int, vp]
     L.icer_b200_dwt_batch_u16.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_int, vp]
     L.icer_b200_launch_count.argtypes = [vp]
     L.icer_b200_launch_count.restype = C.c_uint64
@@ -172,6 +175,38 @@ class IcerB200:
         dims = np.zeros((n, 2), dtype=np.uint32)
         rc = np.zeros(n, dtype=np.int32)
         self.decompress_batch_raw((w, h, chan, stages, filt, segments, 0), buf, stride, lens, n, frames, dims, rc, MEM_HOST)
+        return dict(rc=rc, dims=dims, frames=frames)
+
+    # ---- 8-bit / RGB frames at the boundary (widening and colour conversion on the device) -------------------------
+    def compress_batch_pix(self, frames, pixfmt, w, h, chan, stages, filt, segments, quota):
+        """frames: uint8 [n, chan, h, w] (PIX_U8) or uint8 [n, h, w, 3] (PIX_RGB888)."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        n = frames.shape[0]
+        out = np.zeros((n, quota), dtype=np.uint8)
+        used = np.zeros(n, dtype=np.uint64)
+        rc = np.zeros(n, dtype=np.int32)
+        p = _Params(w, h, chan, stages, filt, segments, quota)
+        e = self.lib.icer_b200_compress_batch_pix(self.h, C.byref(p), _ptr(frames), pixfmt, n, _ptr(out), quota, _ptr(used), _ptr(rc), MEM_HOST, None)
+        if e != 0:
+            raise IcerError("icer_b200_compress_batch_pix -> %d" % e)
+        return dict(rc=rc, size_used=used, streams=[bytes(out[i, :int(used[i])]) for i in range(n)])
+
+    def decompress_batch_pix(self, streams, pixfmt, chan, w, h, stages, filt, segments):
+        n = len(streams)
+        stride = max(max((len(s) for s in streams), default=1), 1)
+        buf = np.zeros((n, stride), dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.uint64)
+        for i, s in enumerate(streams):
+            buf[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+            lens[i] = len(s)
+        frames = np.zeros((n, h * w, 3) if pixfmt == PIX_RGB888 else (n, chan, h * w), dtype=np.uint8)
+        dims = np.zeros((n, 2), dtype=np.uint32)
+        rc = np.zeros(n, dtype=np.int32)
+        p = _Params(w, h, chan, stages, filt, segments, 0)
+        e = self.lib.icer_b200_decompress_batch_pix(self.h, C.byref(p), _ptr(buf), stride, _ptr(lens), n, _ptr(frames), pixfmt, _ptr(dims),
+                                                    _ptr(rc), MEM_HOST, None)
+        if e != 0:
+            raise IcerError("icer_b200_decompress_batch_pix -> %d" % e)
         return dict(rc=rc, dims=dims, frames=frames)
 
     def synth_frames(self, dst, n, w, h, first_frame, seed, kind, stream=None):

@@ -35,7 +35,7 @@ struct icer_b200_ctx {
     std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int>, Plan *> plans;
     LaunchStats ls;
     DevBuf coefs, tmp, scratch, bits, crc, rings, out, out_prio, size_used, rc, keep, offp, offr, mean, ovf, misc,
-        streams, segoff, dims, frame_ok, cand, ncand, pinfo, list;
+        streams, segoff, dims, frame_ok, cand, ncand, pinfo, list, pix;
     uint32_t ring_threads = 0;
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -107,7 +107,7 @@ void icer_b200_destroy(icer_b200_ctx *c) {
     for (auto &kv : c->plans) { free_plan_device(*kv.second); delete kv.second; }
     DevBuf *all[] = {&c->coefs, &c->tmp, &c->scratch, &c->bits, &c->crc, &c->rings, &c->out, &c->out_prio, &c->size_used, &c->rc,
                      &c->keep, &c->offp, &c->offr, &c->mean, &c->ovf, &c->misc, &c->streams, &c->segoff, &c->dims, &c->frame_ok,
-                     &c->cand, &c->ncand, &c->pinfo, &c->list};
+                     &c->cand, &c->ncand, &c->pinfo, &c->list, &c->pix};
     for (auto b : all) b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -134,9 +134,12 @@ void icer_b200_enable_timing(icer_b200_ctx *c, int on) { if (c) c->timing = on !
 // ---------------------------------------------------------------------------------------------------------
 // batch encode
 // ---------------------------------------------------------------------------------------------------------
-int icer_b200_compress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, const uint16_t *frames, size_t n, uint8_t *out,
-                                 size_t out_stride, uint8_t *out_prio, uint16_t *coefs_out, uint64_t *size_used, int32_t *rc,
-                                 int mem, void *stream) {
+static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const void *frames_any, int pixfmt, size_t n, uint8_t *out,
+                              size_t out_stride, uint8_t *out_prio, uint16_t *coefs_out, uint64_t *size_used, int32_t *rc,
+                              int mem, void *stream) {
+    const uint16_t *frames = (const uint16_t *) frames_any;
+    if (pixfmt != ICER_B200_PIX_U16 && pixfmt != ICER_B200_PIX_U8 && pixfmt != ICER_B200_PIX_RGB888) return ICER_INVALID_INPUT;
+    if (pixfmt == ICER_B200_PIX_RGB888 && p && p->channels != 3) return ICER_INVALID_INPUT;
     if (!c || !p || !frames || !out || !size_used || !rc) return ICER_INVALID_INPUT;
     if (p->channels != 1 && p->channels != 3) return ICER_INVALID_INPUT;
     if (out_stride < p->byte_quota) return ICER_OUTPUT_BUF_TOO_SMALL;
@@ -191,7 +194,20 @@ int icer_b200_compress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, co
             d_used = c->size_used.as<uint64_t>(); d_rc = c->rc.as<int32_t>();
         }
         uint16_t *d_coefs = c->coefs.as<uint16_t>();
-        if ((e = copy_in(d_coefs, frames + done * frame_px, nb * frame_px * 2, mem, st))) return e;
+        if (pixfmt == ICER_B200_PIX_U16) {
+            if ((e = copy_in(d_coefs, frames + done * frame_px, nb * frame_px * 2, mem, st))) return e;
+        } else {
+            // 8-bit samples / packed RGB: one byte per sample crosses PCIe, widening / colour conversion happen here
+            const uint8_t *src8 = (const uint8_t *) frames_any + done * frame_px;
+            if (host) {
+                if ((e = c->pix.ensure(nb * frame_px))) return e;
+                CUDA_TRY(cudaMemcpyAsync(c->pix.p, src8, nb * frame_px, cudaMemcpyHostToDevice, st));
+                src8 = c->pix.as<uint8_t>();
+            }
+            if (pixfmt == ICER_B200_PIX_U8) e = launch_u8_to_u16(src8, d_coefs, nb * frame_px, st, c->ls);
+            else e = launch_rgb_to_yuv(src8, d_coefs, nb, plane_px, st, c->ls);
+            if (e) return e;
+        }
         CUDA_TRY(cudaMemsetAsync(c->ovf.p, 0, nb * chan * 4, st));
         ev_record(c, 1, st);
         if ((e = launch_dwt_forward(d_coefs, c->tmp.as<uint16_t>(), nb * chan, w, h, p->stages, p->filter, c->ovf.as<int>(), st, c->ls))) return e;
@@ -258,6 +274,17 @@ int icer_b200_compress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, co
         c->phase_ms[1] = ms_dwt; c->phase_ms[2] = ms_enc; c->phase_ms[3] = ms_asm;
     }
     return ICER_RESULT_OK;
+}
+
+int icer_b200_compress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, const uint16_t *frames, size_t n, uint8_t *out,
+                                 size_t out_stride, uint8_t *out_prio, uint16_t *coefs_out, uint64_t *size_used, int32_t *rc,
+                                 int mem, void *stream) {
+    return compress_batch_any(c, p, frames, ICER_B200_PIX_U16, n, out, out_stride, out_prio, coefs_out, size_used, rc, mem, stream);
+}
+
+int icer_b200_compress_batch_pix(icer_b200_ctx *c, const icer_b200_params *p, const void *frames, int pixfmt, size_t n, uint8_t *out,
+                                 size_t out_stride, uint64_t *size_used, int32_t *rc, int mem, void *stream) {
+    return compress_batch_any(c, p, frames, pixfmt, n, out, out_stride, nullptr, nullptr, size_used, rc, mem, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -341,9 +368,12 @@ void parse_stream(const uint8_t *s, size_t len, uint32_t chan, Parsed &out) {
 // ---------------------------------------------------------------------------------------------------------
 // batch decode
 // ---------------------------------------------------------------------------------------------------------
-int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, const uint8_t *streams, size_t stream_stride,
-                                   const uint64_t *stream_len, size_t n, uint16_t *frames, uint32_t *dims, int32_t *rc, int mem,
-                                   void *stream) {
+static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const uint8_t *streams, size_t stream_stride,
+                                const uint64_t *stream_len, size_t n, void *frames_any, int pixfmt, uint32_t *dims, int32_t *rc, int mem,
+                                void *stream) {
+    uint16_t *frames = (uint16_t *) frames_any;
+    if (pixfmt != ICER_B200_PIX_U16 && pixfmt != ICER_B200_PIX_U8 && pixfmt != ICER_B200_PIX_RGB888) return ICER_INVALID_INPUT;
+    if (pixfmt == ICER_B200_PIX_RGB888 && p && p->channels != 3) return ICER_INVALID_INPUT;
     if (!c || !p || !streams || !stream_len || !frames || !rc) return ICER_INVALID_INPUT;
     if (p->channels != 1 && p->channels != 3) return ICER_INVALID_INPUT;
     if (n == 0) return ICER_RESULT_OK;
@@ -414,10 +444,11 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, 
         if (cap_px < (size_t) info[i].w * info[i].h) { hrc[i] = ICER_BYTE_QUOTA_EXCEEDED; continue; }   // icer_compress.c:461-463
         groups[{info[i].w, info[i].h}].push_back(i);
     }
-    if (host && (e = c->coefs.ensure(n * chan * cap_px * 2))) return e;
+    const bool own16 = host || pixfmt != ICER_B200_PIX_U16;     // decode into our own uint16 planes, convert / copy afterwards
+    if (own16 && (e = c->coefs.ensure(n * chan * cap_px * 2))) return e;
     if ((e = c->mean.ensure(n * chan * 2))) return e;
     if ((e = c->misc.ensure(64))) return e;
-    uint16_t *d_frames = host ? c->coefs.as<uint16_t>() : frames;
+    uint16_t *d_frames = own16 ? c->coefs.as<uint16_t>() : frames;
     float ms_dec = 0, ms_dwt = 0;
     uint32_t dbg_flags = 0;
     { const char *dbg = getenv("ICER_B200_DEBUG"); dbg_flags = dbg ? (uint32_t) atoi(dbg) : 0u; }
@@ -508,11 +539,33 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, 
             cudaEventElapsedTime(&t, c->ev[3], c->ev[4]); ms_dwt += t;
         }
     }
-    // 5. results back
+    // 5. results back (8-bit clamp / Y,Cb,Cr -> RGB on the device when asked for)
+    const size_t out_bytes_per_frame = pixfmt == ICER_B200_PIX_U16 ? chan * cap_px * 2 : chan * cap_px;
+    uint8_t *d_out8 = nullptr;
+    if (pixfmt != ICER_B200_PIX_U16) {
+        d_out8 = (uint8_t *) frames_any;
+        if (host) { if ((e = c->pix.ensure(n * out_bytes_per_frame))) return e; d_out8 = c->pix.as<uint8_t>(); }
+        for (auto &g : groups) {
+            const size_t px = (size_t) g.first.first * g.first.second;
+            for (size_t i : g.second) {
+                if (hrc[i] != ICER_RESULT_OK) continue;
+                if (pixfmt == ICER_B200_PIX_U8) {
+                    for (uint32_t ch = 0; ch < chan; ch++)
+                        if ((e = launch_u16_to_u8(d_frames + (i * chan + ch) * cap_px, d_out8 + (i * chan + ch) * cap_px, px, st, c->ls))) return e;
+                } else {
+                    if ((e = launch_yuv_to_rgb(d_frames + i * 3 * cap_px, d_out8 + i * 3 * cap_px, 1, px, cap_px, st, c->ls))) return e;
+                }
+            }
+        }
+    }
     if (host) {
         for (size_t i = 0; i < n; i++)
-            if (hrc[i] == ICER_RESULT_OK)
-                CUDA_TRY(cudaMemcpyAsync(frames + i * chan * cap_px, d_frames + i * chan * cap_px, chan * cap_px * 2, cudaMemcpyDeviceToHost, st));
+            if (hrc[i] == ICER_RESULT_OK) {
+                if (pixfmt == ICER_B200_PIX_U16)
+                    CUDA_TRY(cudaMemcpyAsync(frames + i * chan * cap_px, d_frames + i * chan * cap_px, chan * cap_px * 2, cudaMemcpyDeviceToHost, st));
+                else
+                    CUDA_TRY(cudaMemcpyAsync((uint8_t *) frames_any + i * out_bytes_per_frame, d_out8 + i * out_bytes_per_frame, out_bytes_per_frame, cudaMemcpyDeviceToHost, st));
+            }
         memcpy(rc, hrc.data(), n * 4);
         if (dims) memcpy(dims, hdims.data(), n * 8);
     } else {
@@ -529,6 +582,18 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, 
         c->phase_ms[1] = ms_dwt; c->phase_ms[2] = ms_dec; c->phase_ms[3] = t;
     }
     return ICER_RESULT_OK;
+}
+
+int icer_b200_decompress_batch_u16(icer_b200_ctx *c, const icer_b200_params *p, const uint8_t *streams, size_t stream_stride,
+                                   const uint64_t *stream_len, size_t n, uint16_t *frames, uint32_t *dims, int32_t *rc, int mem,
+                                   void *stream) {
+    return decompress_batch_any(c, p, streams, stream_stride, stream_len, n, frames, ICER_B200_PIX_U16, dims, rc, mem, stream);
+}
+
+int icer_b200_decompress_batch_pix(icer_b200_ctx *c, const icer_b200_params *p, const uint8_t *streams, size_t stream_stride,
+                                   const uint64_t *stream_len, size_t n, void *frames, int pixfmt, uint32_t *dims, int32_t *rc, int mem,
+                                   void *stream) {
+    return decompress_batch_any(c, p, streams, stream_stride, stream_len, n, frames, pixfmt, dims, rc, mem, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

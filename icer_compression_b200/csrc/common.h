@@ -169,3 +169,9 @@ struct TableArgs {
     const uint32_t *unit_lut;
 };
 int launch_table(const TableArgs &t, cudaStream_t st, LaunchStats &ls);
+
+// ---- pixel formats at the boundary (pixfmt.cu) ---------------------------------------------------------
+int launch_u8_to_u16(const uint8_t *src, uint16_t *dst, size_t count, cudaStream_t st, LaunchStats &ls);
+int launch_u16_to_u8(const uint16_t *src, uint8_t *dst, size_t count, cudaStream_t st, LaunchStats &ls);
+int launch_rgb_to_yuv(const uint8_t *rgb, uint16_t *yuv, size_t n, size_t px, cudaStream_t st, LaunchStats &ls);
+int launch_yuv_to_rgb(const uint16_t *yuv, uint8_t *rgb, size_t n, size_t px, size_t cap_px, cudaStream_t st, LaunchStats &ls);

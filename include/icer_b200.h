@@ -78,6 +78,20 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *ctx, const icer_b200_params *p
                                    size_t stream_stride, const uint64_t *stream_len, size_t n, uint16_t *frames,
                                    uint32_t *dims, int32_t *rc, int mem, void *stream);
 
+/* Pixel formats at the batch boundary.  lib_icer itself only sees uint16 planes; its tools widen 8-bit samples and
+ * convert packed RGB to planar Y,Cb,Cr on the host right before the call and back right after it
+ * (example/src/icer_util.c:69-121,163-168,322-325, example/inc/color_util.h:27-34).  The *_pix calls do those steps on the
+ * device, bit-identically, so 8-bit / RGB batches travel at 1-3 bytes per pixel:
+ *   ICER_B200_PIX_U16     frames are uint16 [n][channels][h][w]                 (same as the calls above)
+ *   ICER_B200_PIX_U8      frames are uint8  [n][channels][h][w]; decode clamps to 255 like the tools' display path
+ *   ICER_B200_PIX_RGB888  frames are uint8  [n][h][w][3] packed R,G,B; params.channels must be 3 */
+enum { ICER_B200_PIX_U16 = 0, ICER_B200_PIX_U8 = 1, ICER_B200_PIX_RGB888 = 2 };
+int icer_b200_compress_batch_pix(icer_b200_ctx *ctx, const icer_b200_params *p, const void *frames, int pixfmt, size_t n,
+                                 uint8_t *out, size_t out_stride, uint64_t *size_used, int32_t *rc, int mem, void *stream);
+int icer_b200_decompress_batch_pix(icer_b200_ctx *ctx, const icer_b200_params *p, const uint8_t *streams, size_t stream_stride,
+                                   const uint64_t *stream_len, size_t n, void *frames, int pixfmt, uint32_t *dims, int32_t *rc,
+                                   int mem, void *stream);
+
 /* Wavelet transform only (parity hook for icer_wavelet_transform_stages_uint16 :446 / inverse :468) over a
  * batch of [n][height][width] planes, in place.  rc[n] receives ICER_INTEGER_OVERFLOW per plane (forward). */
 int icer_b200_dwt_batch_u16(icer_b200_ctx *ctx, uint16_t *planes, size_t n, uint32_t width, uint32_t height,

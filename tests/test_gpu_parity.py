@@ -359,3 +359,36 @@ def test_mixed_dimensions_in_one_batch(ctx9, oracle9):
     ob = oracle9.decompress(sb, 1, 8000, 3, 0, 4)["images"][0].ravel()
     assert (dec["frames"][0, 0][:oa.size] == oa).all() and (dec["frames"][2, 0][:oa.size] == oa).all()
     assert (dec["frames"][1, 0][:ob.size] == ob).all() and (dec["frames"][4, 0][:ob.size] == ob).all()
+
+
+def test_pixel_formats_at_the_boundary(ctx9, oracle9):
+    """8-bit widening and RGB888 <-> Y,Cb,Cr on the device equal the tools' host-side steps
+    (example/src/icer_util.c:69-121,163-168,322-325) around the uint16 codec."""
+    import icer_compression_b200 as icer
+    rng = np.random.default_rng(5)
+    # packed RGB -> YUV -> stream, and back
+    rgb = harness.load_boatcolor_rgb()[100:100 + 96, 200:200 + 128].copy()
+    noise = rng.integers(0, 256, rgb.shape, dtype=np.uint8)
+    batch = np.stack([rgb, noise])
+    quota = 3 * 96 * 128
+    enc = ctx9.compress_batch_pix(batch, icer.PIX_RGB888, 128, 96, 3, 3, 0, 6, quota)
+    for i in range(2):
+        yuv = harness.rgb_to_yuv(batch[i])
+        o = oracle9.compress(yuv, 3, 0, 6, quota)
+        assert o["rc"] == int(enc["rc"][i]) and o["stream"] == enc["streams"][i], i
+    dec = ctx9.decompress_batch_pix(enc["streams"], icer.PIX_RGB888, 3, 128, 96, 3, 0, 6)
+    for i in range(2):
+        y, cb, cr = [p.astype(np.int64).ravel() for p in oracle9.decompress(enc["streams"][i], 3, 96 * 128, 3, 0, 6)["images"]]
+        clip = lambda v: np.clip(v, 0, 255)
+        want = np.stack([clip(y + ((91881 * cr) >> 16) - 179), clip(y - ((22544 * cb + 46793 * cr) >> 16) + 135),
+                         clip(y + ((116129 * cb) >> 16) - 226)], axis=1).astype(np.uint8)
+        assert int(dec["rc"][i]) == 0 and (dec["frames"][i] == want).all(), i
+    # 8-bit gray: widened on the device; decode clamps to 255
+    g8 = np.stack([harness.load_boat()[:96, :128].astype(np.uint8), rng.integers(0, 256, (96, 128), dtype=np.uint8)])[:, None]
+    enc = ctx9.compress_batch_pix(g8, icer.PIX_U8, 128, 96, 1, 3, 0, 6, 2 * 96 * 128)
+    dec = ctx9.decompress_batch_pix(enc["streams"], icer.PIX_U8, 1, 128, 96, 3, 0, 6)
+    for i in range(2):
+        o = oracle9.compress([g8[i, 0].astype(np.uint16)], 3, 0, 6, 2 * 96 * 128)
+        assert o["stream"] == enc["streams"][i]
+        od = oracle9.decompress(o["stream"], 1, 96 * 128, 3, 0, 6)["images"][0].ravel()
+        assert (dec["frames"][i, 0] == np.minimum(od, 255).astype(np.uint8)).all()
