@@ -35,7 +35,7 @@ struct icer_b200_ctx {
     std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int>, Plan *> plans;
     LaunchStats ls;
     DevBuf coefs, tmp, scratch, bits, crc, rings, out, out_prio, size_used, rc, keep, offp, offr, mean, ovf, misc,
-        streams, segoff, dims, frame_ok, cand, ncand, pinfo, list, pix;
+        streams, segoff, dims, frame_ok, cand, ncand, pinfo, list, pix, fin, tmp2;
     uint32_t ring_threads = 0;
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -107,7 +107,7 @@ void icer_b200_destroy(icer_b200_ctx *c) {
     for (auto &kv : c->plans) { free_plan_device(*kv.second); delete kv.second; }
     DevBuf *all[] = {&c->coefs, &c->tmp, &c->scratch, &c->bits, &c->crc, &c->rings, &c->out, &c->out_prio, &c->size_used, &c->rc,
                      &c->keep, &c->offp, &c->offr, &c->mean, &c->ovf, &c->misc, &c->streams, &c->segoff, &c->dims, &c->frame_ok,
-                     &c->cand, &c->ncand, &c->pinfo, &c->list, &c->pix};
+                     &c->cand, &c->ncand, &c->pinfo, &c->list, &c->pix, &c->fin, &c->tmp2};
     for (auto b : all) b->release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -194,8 +194,14 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
             d_used = c->size_used.as<uint64_t>(); d_rc = c->rc.as<int32_t>();
         }
         uint16_t *d_coefs = c->coefs.as<uint16_t>();
+        // the planes to transform: the caller's device frames as they are, or a staging buffer (host input / 8-bit / RGB)
+        const uint16_t *d_in = frames + done * frame_px;
         if (pixfmt == ICER_B200_PIX_U16) {
-            if ((e = copy_in(d_coefs, frames + done * frame_px, nb * frame_px * 2, mem, st))) return e;
+            if (host) {
+                if ((e = c->fin.ensure(nb * frame_px * 2))) return e;
+                CUDA_TRY(cudaMemcpyAsync(c->fin.p, frames + done * frame_px, nb * frame_px * 2, cudaMemcpyHostToDevice, st));
+                d_in = c->fin.as<uint16_t>();
+            }
         } else {
             // 8-bit samples / packed RGB: one byte per sample crosses PCIe, widening / colour conversion happen here
             const uint8_t *src8 = (const uint8_t *) frames_any + done * frame_px;
@@ -204,13 +210,24 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
                 CUDA_TRY(cudaMemcpyAsync(c->pix.p, src8, nb * frame_px, cudaMemcpyHostToDevice, st));
                 src8 = c->pix.as<uint8_t>();
             }
-            if (pixfmt == ICER_B200_PIX_U8) e = launch_u8_to_u16(src8, d_coefs, nb * frame_px, st, c->ls);
-            else e = launch_rgb_to_yuv(src8, d_coefs, nb, plane_px, st, c->ls);
+            if ((e = c->fin.ensure(nb * frame_px * 2))) return e;
+            if (pixfmt == ICER_B200_PIX_U8) e = launch_u8_to_u16(src8, c->fin.as<uint16_t>(), nb * frame_px, st, c->ls);
+            else e = launch_rgb_to_yuv(src8, c->fin.as<uint16_t>(), nb, plane_px, st, c->ls);
             if (e) return e;
+            d_in = c->fin.as<uint16_t>();
         }
         CUDA_TRY(cudaMemsetAsync(c->ovf.p, 0, nb * chan * 4, st));
         ev_record(c, 1, st);
-        if ((e = launch_dwt_forward(d_coefs, c->tmp.as<uint16_t>(), nb * chan, w, h, p->stages, p->filter, c->ovf.as<int>(), st, c->ls))) return e;
+        static const bool no_tma = getenv("ICER_B200_NO_TMA") != nullptr;
+        if (!no_tma && dwt_fused_applicable(d_in, w, h, plane_px)) {
+            // fused row+column stage, tiles staged by TMA; reads d_in, leaves it untouched
+            if ((e = c->tmp2.ensure(nb * frame_px * 2))) return e;
+            if ((e = launch_dwt_forward_fused(d_in, plane_px, d_coefs, c->tmp.as<uint16_t>(), c->tmp2.as<uint16_t>(), nb * chan, w, h,
+                                              p->stages, p->filter, c->ovf.as<int>(), st, c->ls))) return e;
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(d_coefs, d_in, nb * frame_px * 2, cudaMemcpyDeviceToDevice, st));
+            if ((e = launch_dwt_forward(d_coefs, c->tmp.as<uint16_t>(), nb * chan, w, h, p->stages, p->filter, c->ovf.as<int>(), st, c->ls))) return e;
+        }
         if ((e = launch_ll_mean_signmag(d_coefs, nb * chan, w, h, (uint32_t) dim_low(w, p->stages), (uint32_t) dim_low(h, p->stages),
                                         c->mean.as<uint16_t>(), c->ovf.as<int>(), st, c->ls))) return e;
         if (coefs_out) if ((e = copy_out(coefs_out + done * frame_px, d_coefs, nb * frame_px * 2, mem, st))) return e;
@@ -619,12 +636,21 @@ int icer_b200_dwt_batch_u16(icer_b200_ctx *c, uint16_t *planes, size_t n, uint32
     if ((e = c->ovf.ensure(n * 4))) return e;
     uint16_t *d = planes;
     if (host) {
-        if ((e = c->coefs.ensure(n * ps * 2))) return e;
-        d = c->coefs.as<uint16_t>();
+        if ((e = c->fin.ensure(n * ps * 2))) return e;
+        d = c->fin.as<uint16_t>();
         CUDA_TRY(cudaMemcpyAsync(d, planes, n * ps * 2, cudaMemcpyHostToDevice, st));
     }
     CUDA_TRY(cudaMemsetAsync(c->ovf.p, 0, n * 4, st));
-    if (inverse) e = launch_dwt_inverse(d, c->tmp.as<uint16_t>(), n, width, height, stages, filter, false, st, c->ls);
+    static const bool no_tma = getenv("ICER_B200_NO_TMA") != nullptr;
+    if (!inverse && !no_tma && dwt_fused_applicable(d, width, height, ps)) {
+        // same fused TMA path as the encoder; the result replaces the input planes
+        if ((e = c->coefs.ensure(n * ps * 2))) return e;
+        if ((e = c->tmp2.ensure(n * ps * 2))) return e;
+        if ((e = launch_dwt_forward_fused(d, ps, c->coefs.as<uint16_t>(), c->tmp.as<uint16_t>(), c->tmp2.as<uint16_t>(), n, width, height, stages,
+                                          filter, c->ovf.as<int>(), st, c->ls))) return e;
+        CUDA_TRY(cudaMemcpyAsync(d, c->coefs.p, n * ps * 2, cudaMemcpyDeviceToDevice, st));
+        e = ICER_RESULT_OK;
+    } else if (inverse) e = launch_dwt_inverse(d, c->tmp.as<uint16_t>(), n, width, height, stages, filter, false, st, c->ls);
     else e = launch_dwt_forward(d, c->tmp.as<uint16_t>(), n, width, height, stages, filter, c->ovf.as<int>(), st, c->ls);
     if (e) return e;
     std::vector<int> ovf(n, 0);

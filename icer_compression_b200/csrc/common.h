@@ -175,3 +175,8 @@ int launch_u8_to_u16(const uint8_t *src, uint16_t *dst, size_t count, cudaStream
 int launch_u16_to_u8(const uint16_t *src, uint8_t *dst, size_t count, cudaStream_t st, LaunchStats &ls);
 int launch_rgb_to_yuv(const uint8_t *rgb, uint16_t *yuv, size_t n, size_t px, cudaStream_t st, LaunchStats &ls);
 int launch_yuv_to_rgb(const uint16_t *yuv, uint8_t *rgb, size_t n, size_t px, size_t cap_px, cudaStream_t st, LaunchStats &ls);
+
+// ---- fused forward DWT stage with TMA-staged tiles (wavelet_tma.cu) -------------------------------------
+bool dwt_fused_applicable(const void *src, uint32_t w, uint32_t h, size_t src_plane_stride);
+int launch_dwt_forward_fused(const uint16_t *src, size_t src_plane_stride, uint16_t *dst, uint16_t *pp0, uint16_t *pp1, size_t nplanes,
+                             uint32_t w, uint32_t h, uint32_t stages, uint32_t filt, int *d_ovf, cudaStream_t st, LaunchStats &ls);
