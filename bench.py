@@ -308,20 +308,34 @@ def run_ours(args, wl, rank, world, local_rank):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (K4 entropy coder) ------------------------------------------------
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------
+    # The step is dominated by the two coder kernels; whichever took longer is reported as THE roofline object, the
+    # other one under roofline_other.  Algorithmic bytes: K4 = coefficients read once + streams written
+    # once; K7 = streams read once + coefficients written once (the same number).
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = n * chan * w * h * 2 + stream_bytes            # K4: coefficients read once + streams written once
+    alg_bytes = n * chan * w * h * 2 + stream_bytes
     k4_ms = float(np.mean(kern_enc_ms))
     k7_ms = float(np.mean(kern_dec_ms))
-    ach = alg_bytes / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
     step_bytes = 2 * (n * chan * w * h * 2 + stream_bytes)       # encode: in + stream ; decode: stream + out
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "k_encode_traffic.json")
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp))
         except Exception:
-            traffic = None
+            traffic = {}
+
+    def roof(name, desc, ms):
+        ach = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"bound": "hbm", "kernel": desc, "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
+                "traffic": traffic.get(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(ms, 3)}
+
+    r_enc = roof("k_encode", "k_encode (bit-plane context model + interleaved entropy coder)", k4_ms)
+    r_dec = roof("k_decode", "k_decode (bit-plane context model + interleaved entropy decoder)", k7_ms)
+    roofline, roofline_other = (r_dec, r_enc) if k7_ms >= k4_ms else (r_enc, r_dec)
+    roofline["encode_dwt_ms"] = round(float(np.mean(enc_dwt_ms)), 3)
+    roofline["step_frac"] = round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 5)
+    roofline["note"] = "instruction-issue bound integer kernels: the HBM fraction is reported as the contract asks, it is not the limiter"
     line = {
         "metric": "encode+decode Mpixels/s", "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
@@ -333,11 +347,7 @@ def run_ours(args, wl, rank, world, local_rank):
         "encode_ms": round(enc_ms, 3), "decode_ms": round(dec_ms, 3),
         "compressed_bytes_per_step": stream_bytes, "frames_ok": ok_frames, "decode_rc_ok": int((drc_h == 0).sum()),
         "roundtrip_lossless": roundtrip,
-        "roofline": {"bound": "hbm", "kernel": "k_encode (bit-plane context model + interleaved entropy coder)",
-                     "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5), "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(k4_ms, 3),
-                     "decode_kernel_ms": round(k7_ms, 3), "encode_dwt_ms": round(float(np.mean(enc_dwt_ms)), 3),
-                     "step_frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 5)},
+        "roofline": roofline, "roofline_other": roofline_other,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     # ---- CPU baseline on a bounded sample of the same workload + bit-exactness of that sample -------------------
