@@ -41,6 +41,11 @@ struct icer_b200_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float phase_ms[4] = {0, 0, 0, 0};
     size_t workspace_budget = (size_t) 64 << 30;
+    // host-buffer pipeline: chunks of `pipe_chunk` frames, H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i
+    size_t pipe_chunk = 0;        // 0 = off (default): on B200 the per-chunk kernel tails cost more than the overlap saves; ICER_B200_PIPE_CHUNK=n enables it
+    cudaStream_t cs_in = nullptr, cs_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    DevBuf p_in[2], p_out[2], p_used[2], p_rc[2], p_dims[2];
 };
 
 namespace {
@@ -95,6 +100,7 @@ int icer_b200_create(icer_b200_ctx **out, int device) {
     CUDA_TRY(cudaSetDevice(device));
     icer_b200_ctx *c = new icer_b200_ctx();
     c->device = device;
+    { const char *pc = getenv("ICER_B200_PIPE_CHUNK"); if (pc) c->pipe_chunk = (size_t) atol(pc); }
     const char *gb = getenv("ICER_B200_WORKSPACE_GB");
     if (gb && atof(gb) > 0) c->workspace_budget = (size_t) (atof(gb) * (double) ((size_t) 1 << 30));
     *out = c;
@@ -109,6 +115,13 @@ void icer_b200_destroy(icer_b200_ctx *c) {
                      &c->keep, &c->offp, &c->offr, &c->mean, &c->ovf, &c->misc, &c->streams, &c->segoff, &c->dims, &c->frame_ok,
                      &c->cand, &c->ncand, &c->pinfo, &c->list, &c->pix, &c->fin, &c->tmp2};
     for (auto b : all) b->release();
+    for (int k = 0; k < 2; k++) {
+        c->p_in[k].release(); c->p_out[k].release(); c->p_used[k].release(); c->p_rc[k].release(); c->p_dims[k].release();
+        if (c->ev_in[k]) cudaEventDestroy(c->ev_in[k]);
+        if (c->ev_out[k]) cudaEventDestroy(c->ev_out[k]);
+    }
+    if (c->cs_in) cudaStreamDestroy(c->cs_in);
+    if (c->cs_out) cudaStreamDestroy(c->cs_out);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
 }
@@ -136,6 +149,112 @@ void icer_b200_enable_timing(icer_b200_ctx *c, int on) { if (c) c->timing = on !
 // ---------------------------------------------------------------------------------------------------------
 static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const void *frames_any, int pixfmt, size_t n, uint8_t *out,
                               size_t out_stride, uint8_t *out_prio, uint16_t *coefs_out, uint64_t *size_used, int32_t *rc,
+                              int mem, void *stream);
+static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const uint8_t *streams, size_t stream_stride,
+                                const uint64_t *stream_len, size_t n, void *frames_any, int pixfmt, uint32_t *dims, int32_t *rc, int mem,
+                                void *stream);
+
+static int pipe_setup(icer_b200_ctx *c) {
+    if (c->cs_in) return ICER_RESULT_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->cs_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->cs_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming));
+    }
+    return ICER_RESULT_OK;
+}
+
+// Host buffers, large batch: chunks of pipe_chunk frames run through the DEVICE-pointer path; the upload of chunk i+1
+// (copy stream cs_in) and the download of chunk i-1 (cs_out) overlap the kernels of chunk i (caller's stream).
+static int compress_host_pipelined(icer_b200_ctx *c, const icer_b200_params *p, const void *frames_any, int pixfmt, size_t n, uint8_t *out,
+                                   size_t out_stride, uint64_t *size_used, int32_t *rc, cudaStream_t st) {
+    int e = pipe_setup(c);
+    if (e) return e;
+    const size_t CH = c->pipe_chunk;
+    const size_t frame_bytes = (size_t) p->width * p->height * p->channels * (pixfmt == ICER_B200_PIX_U16 ? 2 : 1);
+    const size_t nchunks = (n + CH - 1) / CH;
+    for (int k = 0; k < 2; k++) {
+        if ((e = c->p_in[k].ensure(CH * frame_bytes))) return e;
+        if ((e = c->p_out[k].ensure(CH * out_stride))) return e;
+        if ((e = c->p_used[k].ensure(CH * 8))) return e;
+        if ((e = c->p_rc[k].ensure(CH * 4))) return e;
+    }
+    const uint8_t *src = (const uint8_t *) frames_any;
+    CUDA_TRY(cudaMemcpyAsync(c->p_in[0].p, src, std::min(CH, n) * frame_bytes, cudaMemcpyHostToDevice, c->cs_in));
+    CUDA_TRY(cudaEventRecord(c->ev_in[0], c->cs_in));
+    for (size_t i = 0; i < nchunks; i++) {
+        const int b = (int) (i & 1);
+        const size_t f0 = i * CH, nb = std::min(CH, n - f0);
+        if (i + 1 < nchunks) {      // p_in[b^1] was consumed by chunk i-1, whose call has returned: upload the next chunk now
+            const size_t f1 = (i + 1) * CH, nb1 = std::min(CH, n - f1);
+            CUDA_TRY(cudaMemcpyAsync(c->p_in[b ^ 1].p, src + f1 * frame_bytes, nb1 * frame_bytes, cudaMemcpyHostToDevice, c->cs_in));
+            CUDA_TRY(cudaEventRecord(c->ev_in[b ^ 1], c->cs_in));
+        }
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[b], 0));
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_out[b], 0));       // p_out[b] still being downloaded (chunk i-2)
+        e = compress_batch_any(c, p, c->p_in[b].p, pixfmt, nb, c->p_out[b].as<uint8_t>(), out_stride, nullptr, nullptr,
+                               c->p_used[b].as<uint64_t>(), c->p_rc[b].as<int32_t>(), ICER_B200_MEM_DEVICE, st);
+        if (e) return e;
+        CUDA_TRY(cudaMemcpyAsync(size_used + f0, c->p_used[b].p, nb * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(rc + f0, c->p_rc[b].p, nb * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        size_t maxlen = 0;
+        for (size_t k = 0; k < nb; k++) maxlen = std::max<size_t>(maxlen, (size_t) size_used[f0 + k]);
+        if (maxlen) CUDA_TRY(cudaMemcpy2DAsync(out + f0 * out_stride, out_stride, c->p_out[b].p, out_stride, maxlen, nb, cudaMemcpyDeviceToHost, c->cs_out));
+        CUDA_TRY(cudaEventRecord(c->ev_out[b], c->cs_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->cs_out));
+    return ICER_RESULT_OK;
+}
+
+static int decompress_host_pipelined(icer_b200_ctx *c, const icer_b200_params *p, const uint8_t *streams, size_t stream_stride,
+                                     const uint64_t *stream_len, size_t n, void *frames_any, int pixfmt, uint32_t *dims, int32_t *rc,
+                                     cudaStream_t st) {
+    int e = pipe_setup(c);
+    if (e) return e;
+    const size_t CH = c->pipe_chunk;
+    const size_t cap_px = (size_t) p->width * p->height;
+    const size_t frame_bytes = cap_px * p->channels * (pixfmt == ICER_B200_PIX_U16 ? 2 : 1);
+    const size_t nchunks = (n + CH - 1) / CH;
+    for (int k = 0; k < 2; k++) {
+        if ((e = c->p_in[k].ensure(CH * stream_stride + 16))) return e;
+        if ((e = c->p_out[k].ensure(CH * frame_bytes))) return e;
+        if ((e = c->p_used[k].ensure(CH * 8))) return e;
+        if ((e = c->p_rc[k].ensure(CH * 4))) return e;
+        if ((e = c->p_dims[k].ensure(CH * 8))) return e;
+    }
+    auto upload = [&](size_t i, int b) -> int {
+        const size_t f0 = i * CH, nb = std::min(CH, n - f0);
+        size_t maxlen = 0;
+        for (size_t k = 0; k < nb; k++) maxlen = std::max<size_t>(maxlen, (size_t) std::min<uint64_t>(stream_len[f0 + k], stream_stride));
+        if (maxlen) CUDA_TRY(cudaMemcpy2DAsync(c->p_in[b].p, stream_stride, streams + f0 * stream_stride, stream_stride, maxlen, nb, cudaMemcpyHostToDevice, c->cs_in));
+        CUDA_TRY(cudaMemcpyAsync(c->p_used[b].p, stream_len + f0, nb * 8, cudaMemcpyHostToDevice, c->cs_in));
+        CUDA_TRY(cudaEventRecord(c->ev_in[b], c->cs_in));
+        return ICER_RESULT_OK;
+    };
+    if ((e = upload(0, 0))) return e;
+    for (size_t i = 0; i < nchunks; i++) {
+        const int b = (int) (i & 1);
+        const size_t f0 = i * CH, nb = std::min(CH, n - f0);
+        if (i + 1 < nchunks && (e = upload(i + 1, b ^ 1))) return e;
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[b], 0));
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_out[b], 0));
+        e = decompress_batch_any(c, p, c->p_in[b].as<uint8_t>(), stream_stride, c->p_used[b].as<uint64_t>(), nb, c->p_out[b].p, pixfmt,
+                                 c->p_dims[b].as<uint32_t>(), c->p_rc[b].as<int32_t>(), ICER_B200_MEM_DEVICE, st);
+        if (e) return e;
+        CUDA_TRY(cudaMemcpyAsync(rc + f0, c->p_rc[b].p, nb * 4, cudaMemcpyDeviceToHost, st));
+        if (dims) CUDA_TRY(cudaMemcpyAsync(dims + 2 * f0, c->p_dims[b].p, nb * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpyAsync((uint8_t *) frames_any + f0 * frame_bytes, c->p_out[b].p, nb * frame_bytes, cudaMemcpyDeviceToHost, c->cs_out));
+        CUDA_TRY(cudaEventRecord(c->ev_out[b], c->cs_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->cs_out));
+    return ICER_RESULT_OK;
+}
+
+static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const void *frames_any, int pixfmt, size_t n, uint8_t *out,
+                              size_t out_stride, uint8_t *out_prio, uint16_t *coefs_out, uint64_t *size_used, int32_t *rc,
                               int mem, void *stream) {
     const uint16_t *frames = (const uint16_t *) frames_any;
     if (pixfmt != ICER_B200_PIX_U16 && pixfmt != ICER_B200_PIX_U8 && pixfmt != ICER_B200_PIX_RGB888) return ICER_INVALID_INPUT;
@@ -150,6 +269,8 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
     Plan *pl = get_plan(c, w, h, chan, p->stages, p->segments);
     if (pl->status == ICER_FATAL_ERROR) return ICER_FATAL_ERROR;
     const bool host = mem == ICER_B200_MEM_HOST;
+    if (host && c->pipe_chunk && n > c->pipe_chunk && pl->status == ICER_RESULT_OK && !out_prio && !coefs_out)
+        return compress_host_pipelined(c, p, frames_any, pixfmt, n, out, out_stride, size_used, rc, st);
     if (pl->status != ICER_RESULT_OK) {   // every frame of this shape fails the same way, nothing is written
         std::vector<uint64_t> z(n, 0);
         std::vector<int32_t> r(n, pl->status);
@@ -397,6 +518,8 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t) stream;
     const bool host = mem == ICER_B200_MEM_HOST;
+    if (host && c->pipe_chunk && n > c->pipe_chunk)
+        return decompress_host_pipelined(c, p, streams, stream_stride, stream_len, n, frames_any, pixfmt, dims, rc, st);
     const uint32_t chan = p->channels;
     const size_t cap_px = (size_t) p->width * p->height;
     ev_record(c, 0, st);

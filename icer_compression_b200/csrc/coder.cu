@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
         if (lane == 0) wid = atomicAdd(a.work_counter, 1ull);
         wid = __shfl_sync(0xffffffffu, wid, 0);
         if (wid >= total) break;
-        const uint32_t g = (uint32_t) (wid / nstreams), s = (uint32_t) (wid % nstreams);
+        // stream-major order: the largest streams of ALL groups first, so the tail of the kernel consists of small streams
+        const uint32_t g = (uint32_t) (wid % a.ngroups), s = (uint32_t) (wid / a.ngroups);
         const Unit u = a.units[s / a.planes];
         const int lsb = (int) (s % a.planes);
         const uint32_t frame = g * 32 + lane;
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(DEC_BT, 3) k_decode(DecodeArgs a) {
         __threadfence_block();
         const unsigned long long wid = sl.wid;
         if (wid >= total) break;                         // no more chains: every later task is void as well
-        const uint32_t g = (uint32_t) (wid / a.nunits), ui = (uint32_t) (wid % a.nunits);
+        const uint32_t g = (uint32_t) (wid % a.ngroups), ui = (uint32_t) (wid / a.ngroups);      // largest chains of all groups first
         const Unit u = a.units[ui];
         const int32_t frame = a.frame_of[g * 32 + lane];
         bool alive = false;

@@ -392,3 +392,25 @@ def test_pixel_formats_at_the_boundary(ctx9, oracle9):
         assert o["stream"] == enc["streams"][i]
         od = oracle9.decompress(o["stream"], 1, 96 * 128, 3, 0, 6)["images"][0].ravel()
         assert (dec["frames"][i, 0] == np.minimum(od, 255).astype(np.uint8)).all()
+
+
+def test_host_pipeline_chunks(oracle9):
+    """Host-buffer batches larger than the pipeline chunk go through overlapped upload / compute / download; results must
+    not depend on the chunking."""
+    import icer_compression_b200 as icer
+    os.environ["ICER_B200_PIPE_CHUNK"] = "5"
+    try:
+        c = icer.IcerB200(device=0)
+    finally:
+        del os.environ["ICER_B200_PIPE_CHUNK"]
+    n = 13
+    frames = np.stack([oracle9.synth(96, 64, f, 11, f % 2) for f in range(n)])[:, None]
+    enc = c.compress_batch(frames, 3, 0, 5, 96 * 64)
+    for i in range(n):
+        o = oracle9.compress([frames[i, 0]], 3, 0, 5, 96 * 64)
+        assert o["rc"] == int(enc["rc"][i]) and o["stream"] == enc["streams"][i], i
+    dec = c.decompress_batch(enc["streams"], 1, 96, 64, 3, 0, 5)
+    for i in range(n):
+        o = oracle9.decompress(enc["streams"][i], 1, 96 * 64, 3, 0, 5)
+        assert int(dec["rc"][i]) == 0 and (dec["frames"][i, 0] == o["images"][0].ravel()).all(), i
+    c.close()
