@@ -618,7 +618,7 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         if ((e = c->segoff.ensure(n * (size_t) pl->nstreams * 4))) return e;
         if ((e = c->frame_ok.ensure(frame_of.size() * 4))) return e;
         if ((e = c->list.ensure(list.size() * 4 + 4))) return e;
-        CUDA_TRY(cudaMemsetAsync(c->segoff.p, 0xFF, n * (size_t) pl->nstreams * 4, st));       // 0xFFFFFFFF = absent
+        CUDA_TRY(cudaMemsetAsync(c->segoff.p, 0, n * (size_t) pl->nstreams * 4, st));          // entries are offset + 1, 0 = absent
         CUDA_TRY(cudaMemcpyAsync(c->list.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
         TableArgs ta;
         ta.list = c->list.as<uint32_t>(); ta.nlist = (uint32_t) list.size(); ta.cand = c->cand.as<uint2>(); ta.cap = cap;
@@ -629,14 +629,14 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         for (size_t i : g.second) {     // host-scanned frames (overflow fallback): their table rows come from the host
             auto hp = host_parsed.find(i);
             if (hp == host_parsed.end()) continue;
-            std::vector<uint32_t> rowv(pl->nstreams, 0xFFFFFFFFu);
+            std::vector<uint32_t> rowv(pl->nstreams, 0u);
             for (auto &r : hp->second.segs) {
                 const int ch = chan == 1 ? 0 : (r.lsb_chan >> 4);
                 const int lsb = r.lsb_chan & 0x0F;
                 if (lsb >= (int) pl->planes) continue;
                 auto it = pl->unit_of.find(std::make_tuple(ch, (int) r.level, (int) r.subband, (int) r.seg));
                 if (it == pl->unit_of.end()) continue;
-                rowv[it->second * pl->planes + lsb] = r.off;
+                rowv[it->second * pl->planes + lsb] = r.off + 1;
             }
             CUDA_TRY(cudaMemcpyAsync(c->segoff.as<uint32_t>() + i * pl->nstreams, rowv.data(), rowv.size() * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));

@@ -676,11 +676,11 @@ __global__ void __launch_bounds__(DEC_BT, 3) k_decode(DecodeArgs a) {
             // a plane is decoded only if it and every plane above it are present (icer_partition.c:431)
             const uint32_t *row = a.seg_off + (size_t) frame * nstreams + ui * a.planes;
             alive = true;
-            for (int q = P - 1; q > lsb; q--) alive = alive && row[q] != 0xFFFFFFFFu;
-            const uint32_t off = row[lsb];
-            if (off == 0xFFFFFFFFu) alive = false;
+            for (int q = P - 1; q > lsb; q--) alive = alive && row[q] != 0u;      // table entries are offset + 1, 0 = absent
+            const uint32_t off1 = row[lsb];
+            if (off1 == 0u) alive = false;
             if (alive) {
-                const uint8_t *hd = a.streams + (size_t) frame * a.stream_stride + off;
+                const uint8_t *hd = a.streams + (size_t) frame * a.stream_stride + (off1 - 1);
                 dc.start(hd + ICER_HDR_BYTES, buf_end, hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24));
             }
         }
@@ -891,11 +891,22 @@ __global__ void __launch_bounds__(128) k_payload_crc(AssembleArgs a) {
     a.crc[id] = ~c;
 }
 
-// One thread per frame walks the streams in priority order with lib_icer's quota rule (SURVEY A.14;
-// icer_encoding.c:211-214, :133-135; icer_partition.c:323-326).  Then a second walk in rearranged order assigns
-// the offsets of the final stream.
-__global__ void k_quota_scan(AssembleArgs a) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per frame walks the streams in priority order with lib_icer's quota rule (SURVEY A.14;
+// icer_encoding.c:211-214, :133-135; icer_partition.c:323-326): 32 streams per step, a warp prefix sum gives the
+// bytes used before each stream, the first lane whose stream does not fit ends the walk.  A second walk in
+// rearranged order assigns the offsets of the final stream.
+__device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_quota_scan(AssembleArgs a) {
+    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (f >= a.nframes) return;
     int rc = a.plan_status;
     for (uint32_t c = 0; c < a.chan && rc == ICER_RESULT_OK; c++)
@@ -904,30 +915,58 @@ __global__ void k_quota_scan(AssembleArgs a) {
     uint64_t *offp = a.off_prio + (size_t) f * a.nstreams;     // indexed by STREAM ID; ~0 = dropped
     uint64_t used = 0;
     uint32_t kept = 0;
-    if (rc == ICER_RESULT_OK) {
-        for (uint32_t i = 0; i < a.nstreams; i++) {
-            const uint32_t s = a.prio[i];
-            const uint32_t nb = bits[s];
-            const uint64_t room = a.quota - used;
-            if (room < ICER_HDR_BYTES) { rc = ICER_BYTE_QUOTA_EXCEEDED; break; }
-            if (nb > 0 && (uint64_t) (nb >> 3) >= room - ICER_HDR_BYTES) { rc = ICER_BYTE_QUOTA_EXCEEDED; break; }
-            offp[s] = used;
-            used += ICER_HDR_BYTES + ((nb + 7) >> 3);
-            kept++;
+    bool stop = rc != ICER_RESULT_OK;
+    for (uint32_t base = 0; base < a.nstreams; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < a.nstreams;
+        const uint32_t s = valid ? a.prio[i] : 0;
+        const uint32_t nb = valid ? bits[s] : 0;
+        const uint64_t sz = valid ? ICER_HDR_BYTES + ((nb + 7) >> 3) : 0;
+        const uint64_t inc = warp_incl_scan(sz, lane);
+        const uint64_t before = used + inc - sz;
+        uint32_t nkeep = 0;
+        if (!stop) {
+            bool fail = false;
+            if (valid) {
+                if (before > a.quota) fail = true;
+                else {
+                    const uint64_t room = a.quota - before;
+                    fail = room < ICER_HDR_BYTES || (nb > 0 && (uint64_t) (nb >> 3) >= room - ICER_HDR_BYTES);
+                }
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, fail);
+            if (m) {
+                const int first = __ffs(m) - 1;
+                nkeep = first;
+                used = __shfl_sync(0xFFFFFFFFu, before, first);
+                stop = true;
+                rc = ICER_BYTE_QUOTA_EXCEEDED;
+            } else {
+                nkeep = a.nstreams - base < 32 ? a.nstreams - base : 32;
+                used += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
+            kept += nkeep;
         }
+        if (valid) offp[s] = (uint32_t) lane < nkeep ? before : ~0ull;
     }
-    for (uint32_t i = kept; i < a.nstreams; i++) offp[a.prio[i]] = ~0ull;
+    __syncwarp();
     uint64_t *offr = a.off_rearr + (size_t) f * a.nstreams;
     uint64_t ro = 0;
-    for (uint32_t i = 0; i < a.nstreams; i++) {
-        const uint32_t s = a.rearr[i];
-        if (offp[s] == ~0ull) { offr[s] = ~0ull; continue; }
-        offr[s] = ro;
-        ro += ICER_HDR_BYTES + ((bits[s] + 7) >> 3);
+    for (uint32_t base = 0; base < a.nstreams; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < a.nstreams;
+        const uint32_t s = valid ? a.rearr[i] : 0;
+        const bool keep = valid && offp[s] != ~0ull;
+        const uint64_t sz = keep ? ICER_HDR_BYTES + ((bits[s] + 7) >> 3) : 0;
+        const uint64_t inc = warp_incl_scan(sz, lane);
+        if (valid) offr[s] = keep ? ro + inc - sz : ~0ull;
+        ro += __shfl_sync(0xFFFFFFFFu, inc, 31);
     }
-    a.size_used[f] = (rc == ICER_RESULT_OK || rc == ICER_BYTE_QUOTA_EXCEEDED) ? used : 0;
-    a.rc[f] = rc;
-    a.keep[f] = kept;
+    if (lane == 0) {
+        a.size_used[f] = (rc == ICER_RESULT_OK || rc == ICER_BYTE_QUOTA_EXCEEDED) ? used : 0;
+        a.rc[f] = rc;
+        a.keep[f] = kept;
+    }
 }
 
 __device__ __forceinline__ uint32_t crc_bytes(const uint8_t *p, int n) {
@@ -1038,7 +1077,7 @@ int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls) {
     if (rc) return rc;
     const unsigned long long nst = (unsigned long long) a.nframes * a.nstreams;
     if (nst) k_payload_crc<<<(unsigned) ((nst + 127) / 128), 128, 0, st>>>(a);
-    k_quota_scan<<<(a.nframes + 63) / 64, 64, 0, st>>>(a);
+    k_quota_scan<<<(a.nframes + 3) / 4, 128, 0, st>>>(a);
     const unsigned long long warps = (unsigned long long) a.nframes * a.nstreams;
     const unsigned long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0x7FFFFFFFull) return ICER_FATAL_ERROR;

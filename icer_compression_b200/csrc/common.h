@@ -132,7 +132,7 @@ struct DecodeArgs {
     uint32_t plan_w, plan_h;
     const int32_t *frame_of;       // [ngroups*32] batch index of each lane's frame, -1 = padding
     const uint8_t *streams; uint64_t stream_stride; uint64_t total_bytes;
-    const uint32_t *seg_off;       // [batch frames][nstreams] byte offset of the segment header inside the frame's stream, 0xFFFFFFFF = absent
+    const uint32_t *seg_off;       // [batch frames][nstreams] 1 + byte offset of the segment header inside the frame's stream, 0 = absent
     unsigned long long *work_counter;
     uint32_t debug_flags;          // bit0: no quiet fast path, bit1: planes strictly one after the other
 };

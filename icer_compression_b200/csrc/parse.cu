@@ -125,46 +125,60 @@ __global__ void __launch_bounds__(256) k_walk(ParseArgs a) {
             }
             __syncthreads();
         }
+    // the sequential part touches shared memory only: compact the accepted candidates to the front, in stream order
+    __shared__ uint32_t s_nacc;
+    __shared__ unsigned long long s_mean[3];
+    if (threadIdx.x < 3) s_mean[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
-        const uint8_t *s = a.streams + (size_t) frame * a.stride;
         uint64_t cur = 0;
         uint32_t nacc = 0;
         for (uint32_t i = 0; i < cnt; i++) {
-            if (vals[i] == 0xFFFFFFFFu) continue;        // failed the payload CRC
-            const uint32_t off = keys[i];
+            const uint32_t v = vals[i], off = keys[i];
+            if (v == 0xFFFFFFFFu) continue;               // failed the payload CRC
             if (off < cur) continue;                      // inside a segment that was accepted before it
-            const uint8_t *h = s + off;
-            info.w = ld32(h + 8); info.h = ld32(h + 12);  // the LAST accepted header wins (icer_compress.c:454-456)
-            const uint32_t ch = a.chan == 1 ? 0 : (h[7] >> 4);
-            if (ch < 3) info.mean[ch] = (uint16_t) (h[2] | (h[3] << 8));
-            info.any = 1;
-            cand[nacc++] = make_uint2(off, vals[i]);      // accepted segments, in stream order
-            cur = (uint64_t) off + ICER_HDR_BYTES + vals[i];
+            keys[nacc] = off; vals[nacc] = v; nacc++;     // nacc <= i: in place
+            cur = (uint64_t) off + ICER_HDR_BYTES + v;
         }
+        s_nacc = nacc;
+    }
+    __syncthreads();
+    const uint32_t nacc = s_nacc;
+    const uint8_t *s = a.streams + (size_t) frame * a.stride;
+    for (uint32_t j = threadIdx.x; j < nacc; j += 256) {
+        const uint32_t off = keys[j];
+        cand[j] = make_uint2(off, vals[j]);
+        const uint8_t *h = s + off;
+        const uint32_t ch = a.chan == 1 ? 0 : (h[7] >> 4);
+        // per channel the mean of the LAST accepted header wins (icer_compress.c:454-456)
+        if (ch < 3) atomicMax(&s_mean[ch], ((unsigned long long) (j + 1) << 16) | (uint32_t) (h[2] | (h[3] << 8)));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (nacc) {
+            const uint8_t *h = s + keys[nacc - 1];
+            info.w = ld32(h + 8); info.h = ld32(h + 12);
+            info.any = 1;
+        }
+        for (int c = 0; c < 3; c++) info.mean[c] = (uint16_t) (s_mean[c] & 0xFFFF);
         info.naccepted = nacc;
         a.info[frame] = info;
     }
 }
 
-// accepted segments of the frames of one dimension group -> segment table.  One thread per frame, in stream order so
-// that a later duplicate overwrites an earlier one exactly like lib_icer's table assignment (icer_compress.c:453).
-__global__ void k_table(TableArgs t) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= t.nlist) return;
-    const uint32_t frame = t.list[k];
-    const uint2 *acc = t.cand + (size_t) frame * t.cap;
-    const uint8_t *s = t.streams + (size_t) frame * t.stride;
-    uint32_t *row = t.seg_off + (size_t) frame * t.nstreams;
-    const uint32_t n = t.info[frame].naccepted;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t off = acc[i].x;
-        const uint8_t *h = s + off;
-        const uint32_t level = h[4], sb = h[5], seg = h[6], lsb = h[7] & 0x0F, ch = t.chan == 1 ? 0 : (h[7] >> 4);
-        if (lsb >= t.planes || ch >= t.chan || level > t.max_level || sb > 3 || seg > ICER_MAX_SEGMENTS) continue;
-        const uint32_t unit = t.unit_lut[((ch * (t.max_level + 1) + level) * 4 + sb) * (ICER_MAX_SEGMENTS + 1) + seg];
-        if (unit == 0xFFFFFFFFu) continue;
-        row[unit * t.planes + lsb] = off;
-    }
+// accepted segments of the frames of one dimension group -> segment table (entries hold offset + 1, 0 = absent).  One
+// thread per accepted segment; for duplicates lib_icer's table assignment lets the LAST one in stream order win
+// (icer_compress.c:453) -- offsets grow in stream order, so that is an atomicMax.
+__global__ void __launch_bounds__(128) k_table(TableArgs t) {
+    const uint32_t frame = t.list[blockIdx.y];
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= t.info[frame].naccepted) return;
+    const uint32_t off = t.cand[(size_t) frame * t.cap + i].x;
+    const uint8_t *h = t.streams + (size_t) frame * t.stride + off;
+    const uint32_t level = h[4], sb = h[5], seg = h[6], lsb = h[7] & 0x0F, ch = t.chan == 1 ? 0 : (h[7] >> 4);
+    if (lsb >= t.planes || ch >= t.chan || level > t.max_level || sb > 3 || seg > ICER_MAX_SEGMENTS) return;
+    const uint32_t unit = t.unit_lut[((ch * (t.max_level + 1) + level) * 4 + sb) * (ICER_MAX_SEGMENTS + 1) + seg];
+    if (unit == 0xFFFFFFFFu) return;
+    atomicMax(&t.seg_off[(size_t) frame * t.nstreams + unit * t.planes + lsb], off + 1);
 }
 
 }  // namespace
@@ -193,7 +207,11 @@ int launch_parse(const ParseArgs &a, cudaStream_t st, LaunchStats &ls) {
 
 int launch_table(const TableArgs &t, cudaStream_t st, LaunchStats &ls) {
     if (t.nlist == 0) return ICER_RESULT_OK;
-    k_table<<<(t.nlist + 63) / 64, 64, 0, st>>>(t);
+    for (uint32_t l0 = 0; l0 < t.nlist; l0 += 32768) {
+        TableArgs b = t;
+        b.list += l0; b.nlist = t.nlist - l0 < 32768 ? t.nlist - l0 : 32768;
+        k_table<<<dim3((t.cap + 127) / 128, b.nlist), 128, 0, st>>>(b);
+    }
     ls.launches++;
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;
