@@ -13,7 +13,7 @@ ICER_BYTE_QUOTA_EXCEEDED = -5
 ICER_FATAL_ERROR = -10
 FILTERS = dict(A=0, B=1, C=2, D=3, E=4, F=5, Q=6)
 MEM_HOST, MEM_DEVICE = 0, 1
-PIX_U16, PIX_U8, PIX_RGB888 = 0, 1, 2
+PIX_U16, PIX_U8, PIX_RGB888, PIX_NATIVE_U8 = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -59,6 +59,15 @@ def load_library():
     L.icer_decompress_image_yuv_uint16.argtypes = [u16p] * 3 + [szp, szp, C.c_size_t, u8p, C.c_size_t, C.c_uint8, C.c_int, C.c_uint8]
     L.icer_wavelet_transform_stages_uint16.argtypes = [u16p, C.c_size_t, C.c_size_t, C.c_uint8, C.c_int]
     L.icer_inverse_wavelet_transform_stages_uint16.argtypes = [u16p, C.c_size_t, C.c_size_t, C.c_uint8, C.c_int]
+    L.icer_compress_image_uint8.argtypes = [u8p, C.c_size_t, C.c_size_t, C.c_uint8, C.c_int, C.c_uint8, C.POINTER(_OutBuf)]
+    L.icer_compress_image_yuv_uint8.argtypes = [u8p] * 3 + [C.c_size_t, C.c_size_t, C.c_uint8, C.c_int, C.c_uint8, C.POINTER(_OutBuf)]
+    L.icer_decompress_image_uint8.argtypes = [u8p, szp, szp, C.c_size_t, u8p, C.c_size_t, C.c_uint8, C.c_int, C.c_uint8]
+    L.icer_decompress_image_yuv_uint8.argtypes = [u8p] * 3 + [szp, szp, C.c_size_t, u8p, C.c_size_t, C.c_uint8, C.c_int, C.c_uint8]
+    L.icer_wavelet_transform_stages_uint8.argtypes = [u8p, C.c_size_t, C.c_size_t, C.c_uint8, C.c_int]
+    L.icer_inverse_wavelet_transform_stages_uint8.argtypes = [u8p, C.c_size_t, C.c_size_t, C.c_uint8, C.c_int]
+    L.icer_b200_set_limits_u8.argtypes = [vp, C.c_int, C.c_int]
+    L.icer_b200_dwt_batch_u8.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_int, vp]
+    L.icer_b200_u8_interleave_map.argtypes = [C.c_uint32, vp]
     L.icer_b200_create.argtypes = [C.POINTER(vp), C.c_int]
     L.icer_b200_destroy.argtypes = [vp]
     L.icer_b200_destroy.restype = None
@@ -215,14 +224,21 @@ class IcerB200:
         if e != 0:
             raise IcerError("icer_b200_synth_frames_u16 -> %d" % e)
 
-    def dwt_batch(self, planes, stages, filt, inverse=False):
-        a = np.ascontiguousarray(planes, dtype=np.uint16).copy()
+    def dwt_batch(self, planes, stages, filt, inverse=False, dtype=np.uint16):
+        """dtype uint16: icer_b200_dwt_batch_u16; uint8: the native uint8 transform (icer_b200_dwt_batch_u8)."""
+        a = np.ascontiguousarray(planes, dtype=dtype).copy()
         n, h, w = a.shape
         rc = np.zeros(n, dtype=np.int32)
-        e = self.lib.icer_b200_dwt_batch_u16(self.h, _ptr(a), n, w, h, stages, filt, 1 if inverse else 0, _ptr(rc), MEM_HOST, None)
+        f = self.lib.icer_b200_dwt_batch_u8 if dtype == np.uint8 else self.lib.icer_b200_dwt_batch_u16
+        e = f(self.h, _ptr(a), n, w, h, stages, filt, 1 if inverse else 0, _ptr(rc), MEM_HOST, None)
         if e != 0:
-            raise IcerError("icer_b200_dwt_batch_u16 -> %d" % e)
+            raise IcerError("icer_b200_dwt_batch -> %d" % e)
         return rc, a
+
+    def set_limits_u8(self, planes=0, max_packets=0):
+        rc = self.lib.icer_b200_set_limits_u8(self.h, planes, max_packets)
+        if rc != 0:
+            raise IcerError("icer_b200_set_limits_u8 -> %d" % rc)
 
 
 class LegacyAPI:
@@ -236,28 +252,39 @@ class LegacyAPI:
         if rc != 0:
             raise IcerError("icer_init() -> %d: no usable CUDA device; there is no CPU fallback" % rc)
 
-    def compress(self, planes_in, stages, filt, segments, quota):
-        imgs = [np.ascontiguousarray(p, dtype=np.uint16).copy() for p in planes_in]
+    def compress(self, planes_in, stages, filt, segments, quota, dtype=np.uint16):
+        imgs = [np.ascontiguousarray(p, dtype=dtype).copy() for p in planes_in]
         h, w = imgs[0].shape
         buf = np.zeros(2 * quota + 64, dtype=np.uint8)
         ob = _OutBuf()
         u8 = buf.ctypes.data_as(C.POINTER(C.c_uint8))
         assert self.lib.icer_init_output_struct(C.byref(ob), u8, 2 * quota, quota) == 0
-        pp = [im.ctypes.data_as(C.POINTER(C.c_uint16)) for im in imgs]
-        if len(imgs) == 1:
+        pp = [im.ctypes.data_as(C.POINTER(C.c_uint8 if dtype == np.uint8 else C.c_uint16)) for im in imgs]
+        if dtype == np.uint8:
+            if len(imgs) == 1:
+                rc = self.lib.icer_compress_image_uint8(pp[0], w, h, stages, filt, segments, C.byref(ob))
+            else:
+                rc = self.lib.icer_compress_image_yuv_uint8(pp[0], pp[1], pp[2], w, h, stages, filt, segments, C.byref(ob))
+        elif len(imgs) == 1:
             rc = self.lib.icer_compress_image_uint16(pp[0], w, h, stages, filt, segments, C.byref(ob))
         else:
             rc = self.lib.icer_compress_image_yuv_uint16(pp[0], pp[1], pp[2], w, h, stages, filt, segments, C.byref(ob))
         n = ob.size_used
         return dict(rc=rc, size_used=n, stream=bytes(buf[quota:quota + n]), prio=bytes(buf[:n]), coefs=imgs)
 
-    def decompress(self, stream, chan, bufsize_px, stages, filt, segments):
+    def decompress(self, stream, chan, bufsize_px, stages, filt, segments, dtype=np.uint16):
         data = np.frombuffer(bytes(stream) + b"\0" * 64, dtype=np.uint8).copy()
-        imgs = [np.zeros(max(bufsize_px, 1), dtype=np.uint16) for _ in range(chan)]
+        imgs = [np.zeros(max(bufsize_px, 1), dtype=dtype) for _ in range(chan)]
         w, h = C.c_size_t(0), C.c_size_t(0)
-        pp = [im.ctypes.data_as(C.POINTER(C.c_uint16)) for im in imgs]
+        pp = [im.ctypes.data_as(C.POINTER(C.c_uint8 if dtype == np.uint8 else C.c_uint16)) for im in imgs]
         u8 = data.ctypes.data_as(C.POINTER(C.c_uint8))
-        if chan == 1:
+        if dtype == np.uint8:
+            if chan == 1:
+                rc = self.lib.icer_decompress_image_uint8(pp[0], C.byref(w), C.byref(h), bufsize_px, u8, len(stream), stages, filt, segments)
+            else:
+                rc = self.lib.icer_decompress_image_yuv_uint8(pp[0], pp[1], pp[2], C.byref(w), C.byref(h), bufsize_px, u8,
+                                                              len(stream), stages, filt, segments)
+        elif chan == 1:
             rc = self.lib.icer_decompress_image_uint16(pp[0], C.byref(w), C.byref(h), bufsize_px, u8, len(stream), stages, filt, segments)
         else:
             rc = self.lib.icer_decompress_image_yuv_uint16(pp[0], pp[1], pp[2], C.byref(w), C.byref(h), bufsize_px, u8,
@@ -265,6 +292,12 @@ class LegacyAPI:
         W, H = w.value, h.value
         out = [im[:W * H].reshape(H, W) for im in imgs] if rc == 0 and W * H <= bufsize_px else None
         return dict(rc=rc, w=W, h=H, images=out)
+
+    def dwt8(self, img, stages, filt, inverse=False):
+        a = np.ascontiguousarray(img, dtype=np.uint8).copy()
+        f = self.lib.icer_inverse_wavelet_transform_stages_uint8 if inverse else self.lib.icer_wavelet_transform_stages_uint8
+        rc = f(a.ctypes.data_as(C.POINTER(C.c_uint8)), a.shape[1], a.shape[0], stages, filt)
+        return rc, a
 
     def dwt_forward(self, img, stages, filt):
         a = np.ascontiguousarray(img, dtype=np.uint16).copy()
@@ -275,3 +308,12 @@ class LegacyAPI:
         a = np.ascontiguousarray(img, dtype=np.uint16).copy()
         rc = self.lib.icer_inverse_wavelet_transform_stages_uint16(a.ctypes.data_as(C.POINTER(C.c_uint16)), a.shape[1], a.shape[0], stages, filt)
         return rc, a
+
+
+def u8_interleave_map(n):
+    """Host-only planning helper of the library: where lib_icer's icer_interleave_uint8 puts element i (length n)."""
+    dst = np.zeros(n, dtype=np.uint32)
+    rc = load_library().icer_b200_u8_interleave_map(n, dst.ctypes.data)
+    if rc != 0:
+        raise IcerError("icer_b200_u8_interleave_map -> %d" % rc)
+    return dst

@@ -31,8 +31,10 @@ struct DevBuf {
 struct icer_b200_ctx {
     int device = 0;
     int planes = ICER_BITPLANES_TO_COMPRESS_16, max_stages = ICER_MAX_DECOMP_STAGES, max_packets = ICER_MAX_PACKETS_16;
+    int planes8 = ICER_BITPLANES_TO_COMPRESS_8, max_packets8 = ICER_MAX_PACKETS;      // native uint8 codec (icer.h:35-43)
+    std::map<uint32_t, const uint32_t *> perms8;                                       // device tables, see u8_interleave_dst
     int scratch_bits = 3;
-    std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int>, Plan *> plans;
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int, int>, Plan *> plans;
     LaunchStats ls;
     DevBuf coefs, tmp, scratch, bits, crc, rings, out, out_prio, size_used, rc, keep, offp, offr, mean, ovf, misc,
         streams, segoff, dims, frame_ok, cand, ncand, pinfo, list, pix, fin, tmp2;
@@ -50,8 +52,9 @@ struct icer_b200_ctx {
 
 namespace {
 
-Plan *get_plan(icer_b200_ctx *c, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages, uint32_t segments) {
-    auto key = std::make_tuple(w, h, chan, stages, segments, (uint32_t) c->planes, c->scratch_bits);
+Plan *get_plan(icer_b200_ctx *c, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages, uint32_t segments, bool native8 = false) {
+    const uint32_t planes = (uint32_t) (native8 ? c->planes8 : c->planes);
+    auto key = std::make_tuple(w, h, chan, stages, segments, planes, c->scratch_bits, native8 ? 1 : 0);
     auto it = c->plans.find(key);
     if (it != c->plans.end()) return it->second;
     if (c->plans.size() > 64) {   // keep the cache bounded
@@ -59,11 +62,26 @@ Plan *get_plan(icer_b200_ctx *c, uint32_t w, uint32_t h, uint32_t chan, uint32_t
         c->plans.clear();
     }
     Plan *pl = new Plan();
-    build_plan(*pl, w, h, chan, stages, segments, (uint32_t) c->planes, (uint32_t) c->max_stages, (uint32_t) c->max_packets,
-               c->scratch_bits);
+    build_plan(*pl, w, h, chan, stages, segments, planes, (uint32_t) c->max_stages,
+               (uint32_t) (native8 ? c->max_packets8 : c->max_packets), c->scratch_bits, native8);
     if (upload_plan(*pl) != ICER_RESULT_OK) pl->status = ICER_FATAL_ERROR;
     c->plans[key] = pl;
     return pl;
+}
+
+// device copies of icer_interleave_uint8's placement for the odd line lengths of a w x h, `stages`-stage inverse transform
+int ensure_perms8(icer_b200_ctx *c, uint32_t w, uint32_t h, uint32_t stages) {
+    for (uint32_t s = 0; s < stages; s++)
+        for (uint32_t n : {(uint32_t) dim_low(w, s), (uint32_t) dim_low(h, s)}) {
+            if (!(n & 1) || c->perms8.count(n)) continue;
+            std::vector<uint32_t> dst;
+            u8_interleave_dst(n, dst);
+            uint32_t *d = nullptr;
+            CUDA_TRY(cudaMalloc(&d, (size_t) n * 4));
+            CUDA_TRY(cudaMemcpy(d, dst.data(), (size_t) n * 4, cudaMemcpyHostToDevice));
+            c->perms8[n] = d;
+        }
+    return ICER_RESULT_OK;
 }
 
 void ev_record(icer_b200_ctx *c, int i, cudaStream_t st) {
@@ -111,6 +129,7 @@ void icer_b200_destroy(icer_b200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto &kv : c->plans) { free_plan_device(*kv.second); delete kv.second; }
+    for (auto &kv : c->perms8) cudaFree((void *) kv.second);
     DevBuf *all[] = {&c->coefs, &c->tmp, &c->scratch, &c->bits, &c->crc, &c->rings, &c->out, &c->out_prio, &c->size_used, &c->rc,
                      &c->keep, &c->offp, &c->offr, &c->mean, &c->ovf, &c->misc, &c->streams, &c->segoff, &c->dims, &c->frame_ok,
                      &c->cand, &c->ncand, &c->pinfo, &c->list, &c->pix, &c->fin, &c->tmp2};
@@ -126,11 +145,33 @@ void icer_b200_destroy(icer_b200_ctx *c) {
     delete c;
 }
 
+static void drop_plans(icer_b200_ctx *c) {
+    for (auto &kv : c->plans) { free_plan_device(*kv.second); delete kv.second; }
+    c->plans.clear();
+}
+
 int icer_b200_set_limits(icer_b200_ctx *c, int planes, int max_stages, int max_packets) {
     if (!c) return ICER_INVALID_INPUT;
+    drop_plans(c);
     if (planes) { if (planes < 1 || planes > 15) return ICER_BITPLANE_OUT_OF_RANGE; c->planes = planes; }
     if (max_stages) { if (max_stages < 1 || max_stages > 15) return ICER_TOO_MANY_STAGES; c->max_stages = max_stages; }
     if (max_packets) c->max_packets = max_packets;
+    return ICER_RESULT_OK;
+}
+
+int icer_b200_set_limits_u8(icer_b200_ctx *c, int planes, int max_packets) {
+    if (!c) return ICER_INVALID_INPUT;
+    drop_plans(c);
+    if (planes) { if (planes < 1 || planes > 7) return ICER_BITPLANE_OUT_OF_RANGE; c->planes8 = planes; }   // icer_context_modeller.c:41-42
+    if (max_packets) c->max_packets8 = max_packets;
+    return ICER_RESULT_OK;
+}
+
+int icer_b200_u8_interleave_map(uint32_t len, uint32_t *dst) {
+    if (!dst || len < 2) return ICER_INVALID_INPUT;
+    std::vector<uint32_t> d;
+    u8_interleave_dst(len, d);
+    memcpy(dst, d.data(), (size_t) len * 4);
     return ICER_RESULT_OK;
 }
 
@@ -257,23 +298,27 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
                               size_t out_stride, uint8_t *out_prio, uint16_t *coefs_out, uint64_t *size_used, int32_t *rc,
                               int mem, void *stream) {
     const uint16_t *frames = (const uint16_t *) frames_any;
-    if (pixfmt != ICER_B200_PIX_U16 && pixfmt != ICER_B200_PIX_U8 && pixfmt != ICER_B200_PIX_RGB888) return ICER_INVALID_INPUT;
+    if (pixfmt != ICER_B200_PIX_U16 && pixfmt != ICER_B200_PIX_U8 && pixfmt != ICER_B200_PIX_RGB888 && pixfmt != ICER_B200_PIX_NATIVE_U8) return ICER_INVALID_INPUT;
     if (pixfmt == ICER_B200_PIX_RGB888 && p && p->channels != 3) return ICER_INVALID_INPUT;
     if (!c || !p || !frames || !out || !size_used || !rc) return ICER_INVALID_INPUT;
+    const bool native8 = pixfmt == ICER_B200_PIX_NATIVE_U8;
     if (p->channels != 1 && p->channels != 3) return ICER_INVALID_INPUT;
     if (out_stride < p->byte_quota) return ICER_OUTPUT_BUF_TOO_SMALL;
     if (n == 0) return ICER_RESULT_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t) stream;
     const uint32_t w = p->width, h = p->height, chan = p->channels;
-    Plan *pl = get_plan(c, w, h, chan, p->stages, p->segments);
+    Plan *pl = get_plan(c, w, h, chan, p->stages, p->segments, native8);
     if (pl->status == ICER_FATAL_ERROR) return ICER_FATAL_ERROR;
     const bool host = mem == ICER_B200_MEM_HOST;
-    if (host && c->pipe_chunk && n > c->pipe_chunk && pl->status == ICER_RESULT_OK && !out_prio && !coefs_out)
+    // a packet-count violation is found by lib_icer only AFTER the transform (icer_compress.c:327 vs :22): frames that also
+    // overflow report ICER_INTEGER_OVERFLOW, so that case runs the transform and skips only the coder
+    const int pstatus = pl->status;
+    if (host && c->pipe_chunk && n > c->pipe_chunk && pstatus == ICER_RESULT_OK && !out_prio && !coefs_out)
         return compress_host_pipelined(c, p, frames_any, pixfmt, n, out, out_stride, size_used, rc, st);
-    if (pl->status != ICER_RESULT_OK) {   // every frame of this shape fails the same way, nothing is written
+    if (pstatus != ICER_RESULT_OK) {   // every frame of this shape fails the same way, nothing is written
         std::vector<uint64_t> z(n, 0);
-        std::vector<int32_t> r(n, pl->status);
+        std::vector<int32_t> r(n, pstatus);
         CUDA_TRY(cudaMemcpyAsync(size_used, z.data(), n * 8, host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(rc, r.data(), n * 4, host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -333,6 +378,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
             }
             if ((e = c->fin.ensure(nb * frame_px * 2))) return e;
             if (pixfmt == ICER_B200_PIX_U8) e = launch_u8_to_u16(src8, c->fin.as<uint16_t>(), nb * frame_px, st, c->ls);
+            else if (native8) e = launch_s8_to_i16(src8, c->fin.as<uint16_t>(), nb * frame_px, st, c->ls);
             else e = launch_rgb_to_yuv(src8, c->fin.as<uint16_t>(), nb, plane_px, st, c->ls);
             if (e) return e;
             d_in = c->fin.as<uint16_t>();
@@ -340,24 +386,29 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
         CUDA_TRY(cudaMemsetAsync(c->ovf.p, 0, nb * chan * 4, st));
         ev_record(c, 1, st);
         static const bool no_tma = getenv("ICER_B200_NO_TMA") != nullptr;
-        if (!no_tma && dwt_fused_applicable(d_in, w, h, plane_px)) {
+        if (!native8 && !no_tma && dwt_fused_applicable(d_in, w, h, plane_px)) {
             // fused row+column stage, tiles staged by TMA; reads d_in, leaves it untouched
             if ((e = c->tmp2.ensure(nb * frame_px * 2))) return e;
             if ((e = launch_dwt_forward_fused(d_in, plane_px, d_coefs, c->tmp.as<uint16_t>(), c->tmp2.as<uint16_t>(), nb * chan, w, h,
                                               p->stages, p->filter, c->ovf.as<int>(), st, c->ls))) return e;
         } else {
             CUDA_TRY(cudaMemcpyAsync(d_coefs, d_in, nb * frame_px * 2, cudaMemcpyDeviceToDevice, st));
-            if ((e = launch_dwt_forward(d_coefs, c->tmp.as<uint16_t>(), nb * chan, w, h, p->stages, p->filter, c->ovf.as<int>(), st, c->ls))) return e;
+            if ((e = launch_dwt_forward(d_coefs, c->tmp.as<uint16_t>(), nb * chan, w, h, p->stages, p->filter, c->ovf.as<int>(), st, c->ls, native8))) return e;
         }
         if ((e = launch_ll_mean_signmag(d_coefs, nb * chan, w, h, (uint32_t) dim_low(w, p->stages), (uint32_t) dim_low(h, p->stages),
-                                        c->mean.as<uint16_t>(), c->ovf.as<int>(), st, c->ls))) return e;
-        if (coefs_out) if ((e = copy_out(coefs_out + done * frame_px, d_coefs, nb * frame_px * 2, mem, st))) return e;
+                                        c->mean.as<uint16_t>(), c->ovf.as<int>(), st, c->ls, native8))) return e;
+        if (coefs_out && !native8) if ((e = copy_out(coefs_out + done * frame_px, d_coefs, nb * frame_px * 2, mem, st))) return e;
+        if (coefs_out && native8) {     // the uint8 codec leaves 8-bit sign-magnitude coefficients behind
+            if ((e = c->pix.ensure(nb * frame_px))) return e;
+            if ((e = launch_sm16_to_sm8(d_coefs, c->pix.as<uint8_t>(), nb * frame_px, st, c->ls))) return e;
+            if ((e = copy_out((uint8_t *) coefs_out + done * frame_px, c->pix.p, nb * frame_px, mem, st))) return e;
+        }
         // frame-interleave the coefficients for the coder (lane = frame); the wavelet scratch is free again
         uint16_t *d_T = c->tmp.as<uint16_t>();
         if ((e = launch_frames_to_T(d_coefs, d_T, (uint32_t) nb, ngroups, chan, w, h, st, c->ls))) return e;
         ev_record(c, 2, st);
         // entropy coder, retried with a larger payload scratch in the (rare) case a stream outgrows its slot
-        for (;;) {
+        for (; pl->enc_status == ICER_RESULT_OK;) {
             if ((e = c->scratch.ensure(nb * pl->scratch_words * 4))) return e;
             CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 64, st));
             EncodeArgs ea;
@@ -373,7 +424,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
             if (!ovf) break;
             if (c->scratch_bits >= 24) { fprintf(stderr, "[icer_b200] payload scratch overflow at the worst-case bound\n"); return ICER_FATAL_ERROR; }
             c->scratch_bits = std::min(24, c->scratch_bits * 2);
-            pl = get_plan(c, w, h, chan, p->stages, p->segments);
+            pl = get_plan(c, w, h, chan, p->stages, p->segments, native8);
             if (pl->status != ICER_RESULT_OK) return ICER_FATAL_ERROR;
         }
         ev_record(c, 3, st);
@@ -381,7 +432,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
         aa.nframes = (uint32_t) nb; aa.nstreams = pl->nstreams; aa.planes = pl->planes; aa.chan = chan; aa.w = w; aa.h = h;
         aa.units = pl->d_units; aa.prio = pl->d_prio; aa.rearr = pl->d_rearr; aa.soff = pl->d_soff; aa.scratch_words = pl->scratch_words;
         aa.scratch = c->scratch.as<uint32_t>(); aa.bits = c->bits.as<uint32_t>(); aa.crc = c->crc.as<uint32_t>();
-        aa.mean = c->mean.as<uint16_t>(); aa.ovf = c->ovf.as<int>(); aa.plan_status = ICER_RESULT_OK; aa.quota = p->byte_quota;
+        aa.mean = c->mean.as<uint16_t>(); aa.ovf = c->ovf.as<int>(); aa.plan_status = pl->enc_status; aa.quota = p->byte_quota;
         aa.out = d_out; aa.out_stride = out_stride; aa.out_prio = d_prio; aa.size_used = d_used; aa.rc = d_rc;
         aa.keep = c->keep.as<uint32_t>(); aa.off_prio = c->offp.as<uint64_t>(); aa.off_rearr = c->offr.as<uint64_t>();
         if ((e = launch_assemble(aa, st, c->ls))) return e;
@@ -510,8 +561,9 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
                                 const uint64_t *stream_len, size_t n, void *frames_any, int pixfmt, uint32_t *dims, int32_t *rc, int mem,
                                 void *stream) {
     uint16_t *frames = (uint16_t *) frames_any;
-    if (pixfmt != ICER_B200_PIX_U16 && pixfmt != ICER_B200_PIX_U8 && pixfmt != ICER_B200_PIX_RGB888) return ICER_INVALID_INPUT;
+    if (pixfmt != ICER_B200_PIX_U16 && pixfmt != ICER_B200_PIX_U8 && pixfmt != ICER_B200_PIX_RGB888 && pixfmt != ICER_B200_PIX_NATIVE_U8) return ICER_INVALID_INPUT;
     if (pixfmt == ICER_B200_PIX_RGB888 && p && p->channels != 3) return ICER_INVALID_INPUT;
+    const bool native8 = pixfmt == ICER_B200_PIX_NATIVE_U8;
     if (!c || !p || !streams || !stream_len || !frames || !rc) return ICER_INVALID_INPUT;
     if (p->channels != 1 && p->channels != 3) return ICER_INVALID_INPUT;
     if (n == 0) return ICER_RESULT_OK;
@@ -594,7 +646,7 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
     { const char *dbg = getenv("ICER_B200_DEBUG"); dbg_flags = dbg ? (uint32_t) atoi(dbg) : 0u; }
     for (auto &g : groups) {
         const uint32_t w = g.first.first, h = g.first.second;
-        Plan *pl = get_plan(c, w, h, chan, p->stages, p->segments);
+        Plan *pl = get_plan(c, w, h, chan, p->stages, p->segments, native8);
         if (pl->status == ICER_FATAL_ERROR) return ICER_FATAL_ERROR;
         if (pl->status != ICER_RESULT_OK) {
             // lib_icer's decoder reports the partition / stage errors per image (icer_compress.c:480, icer_wavelet.c:92-94)
@@ -660,15 +712,16 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         // 4. back to planar frames (from sign-magnitude, + LL mean), inverse wavelet, clamp
         const uint32_t llw = (uint32_t) dim_low(w, p->stages), llh = (uint32_t) dim_low(h, p->stages);
         if ((e = launch_T_to_frames(d_T, d_frames, c->frame_ok.as<int32_t>(), c->mean.as<uint16_t>(), ngroups, chan, w, h, cap_px,
-                                    llw, llh, st, c->ls))) return e;
+                                    llw, llh, st, c->ls, native8))) return e;
+        if (native8 && (e = ensure_perms8(c, w, h, p->stages))) return e;
         const bool dense = plane_px == cap_px;
         if (dense && g.second.size() == n) {
-            if ((e = launch_dwt_inverse(d_frames, c->tmp.as<uint16_t>(), n * chan, w, h, p->stages, p->filter, true, st, c->ls))) return e;
+            if ((e = launch_dwt_inverse(d_frames, c->tmp.as<uint16_t>(), n * chan, w, h, p->stages, p->filter, true, st, c->ls, native8, &c->perms8))) return e;
         } else {
             for (size_t i : g.second)
                 for (uint32_t ch = 0; ch < chan; ch++) {
                     uint16_t *pp = d_frames + (i * chan + ch) * cap_px;
-                    if ((e = launch_dwt_inverse(pp, c->tmp.as<uint16_t>(), 1, w, h, p->stages, p->filter, true, st, c->ls))) return e;
+                    if ((e = launch_dwt_inverse(pp, c->tmp.as<uint16_t>(), 1, w, h, p->stages, p->filter, true, st, c->ls, native8, &c->perms8))) return e;
                 }
         }
         ev_record(c, 4, st);
@@ -689,7 +742,10 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
             const size_t px = (size_t) g.first.first * g.first.second;
             for (size_t i : g.second) {
                 if (hrc[i] != ICER_RESULT_OK) continue;
-                if (pixfmt == ICER_B200_PIX_U8) {
+                if (native8) {
+                    for (uint32_t ch = 0; ch < chan; ch++)
+                        if ((e = launch_i16_to_b8(d_frames + (i * chan + ch) * cap_px, d_out8 + (i * chan + ch) * cap_px, px, st, c->ls))) return e;
+                } else if (pixfmt == ICER_B200_PIX_U8) {
                     for (uint32_t ch = 0; ch < chan; ch++)
                         if ((e = launch_u16_to_u8(d_frames + (i * chan + ch) * cap_px, d_out8 + (i * chan + ch) * cap_px, px, st, c->ls))) return e;
                 } else {
@@ -788,6 +844,54 @@ int icer_b200_dwt_batch_u16(icer_b200_ctx *c, uint16_t *planes, size_t n, uint32
     return ICER_RESULT_OK;
 }
 
+// native uint8 transform (icer_wavelet_transform_stages_uint8 / inverse, icer_wavelet.c:8-28,32-53): int8 samples; the inverse
+// reproduces icer_interleave_uint8's placement for odd line lengths
+int icer_b200_dwt_batch_u8(icer_b200_ctx *c, uint8_t *planes, size_t n, uint32_t width, uint32_t height, uint32_t stages,
+                           uint32_t filter, int inverse, int32_t *rc, int mem, void *stream) {
+    if (!c || !planes || filter > ICER_FILTER_Q) return ICER_INVALID_INPUT;
+    if (n == 0) return ICER_RESULT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const bool host = mem == ICER_B200_MEM_HOST;
+    const size_t ps = (size_t) width * height;
+    if (dim_low(width, stages) < 3 || dim_low(height, stages) < 3) {
+        if (rc) {
+            std::vector<int32_t> r(n, ICER_TOO_MANY_STAGES);
+            CUDA_TRY(cudaMemcpy(rc, r.data(), n * 4, host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice));
+        }
+        return ICER_RESULT_OK;
+    }
+    int e;
+    if ((e = c->tmp.ensure(n * ps * 2))) return e;
+    if ((e = c->fin.ensure(n * ps * 2))) return e;
+    if ((e = c->ovf.ensure(n * 4))) return e;
+    uint8_t *d8 = planes;
+    if (host) {
+        if ((e = c->pix.ensure(n * ps))) return e;
+        d8 = c->pix.as<uint8_t>();
+        CUDA_TRY(cudaMemcpyAsync(d8, planes, n * ps, cudaMemcpyHostToDevice, st));
+    }
+    uint16_t *d = c->fin.as<uint16_t>();
+    if ((e = launch_s8_to_i16(d8, d, n * ps, st, c->ls))) return e;
+    CUDA_TRY(cudaMemsetAsync(c->ovf.p, 0, n * 4, st));
+    if (inverse) {
+        if ((e = ensure_perms8(c, width, height, stages))) return e;
+        e = launch_dwt_inverse(d, c->tmp.as<uint16_t>(), n, width, height, stages, filter, false, st, c->ls, true, &c->perms8);
+    } else e = launch_dwt_forward(d, c->tmp.as<uint16_t>(), n, width, height, stages, filter, c->ovf.as<int>(), st, c->ls, true);
+    if (e) return e;
+    if ((e = launch_i16_to_b8(d, d8, n * ps, st, c->ls))) return e;
+    std::vector<int> ovf(n, 0);
+    CUDA_TRY(cudaMemcpyAsync(ovf.data(), c->ovf.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if (host) CUDA_TRY(cudaMemcpyAsync(planes, d8, n * ps, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (rc) {
+        std::vector<int32_t> r(n);
+        for (size_t i = 0; i < n; i++) r[i] = ovf[i] ? ICER_INTEGER_OVERFLOW : ICER_RESULT_OK;
+        CUDA_TRY(cudaMemcpy(rc, r.data(), n * 4, host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice));
+    }
+    return ICER_RESULT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // lib_icer-compatible single-image API (include/icer.h)
 // ---------------------------------------------------------------------------------------------------------
@@ -828,7 +932,11 @@ int icer_generate_partition_parameters(partition_param_typdef *params, size_t ll
     return n < 0 ? n : ICER_RESULT_OK;
 }
 
-static int compress_common(uint16_t *const ch[3], uint32_t chan, size_t w, size_t h, uint8_t stages, int filt, uint8_t segments,
+}  // extern "C"
+
+// T = uint16_t: the *_uint16 entry points; T = uint8_t: the native *_uint8 codec (int8 arithmetic, 7 planes)
+template <typename T>
+static int compress_common(T *const ch[3], uint32_t chan, size_t w, size_t h, uint8_t stages, int filt, uint8_t segments,
                            icer_output_data_buf_typedef *od) {
     icer_b200_ctx *c = default_ctx();
     if (!c) return ICER_FATAL_ERROR;
@@ -837,41 +945,29 @@ static int compress_common(uint16_t *const ch[3], uint32_t chan, size_t w, size_
     p.width = (uint32_t) w; p.height = (uint32_t) h; p.channels = chan; p.stages = stages; p.filter = (uint32_t) filt;
     p.segments = segments; p.byte_quota = od->size_allocated;
     const size_t px = w * h;
-    std::vector<uint16_t> stage;
-    const uint16_t *src = ch[0];
+    std::vector<T> stage;
+    const T *src = ch[0];
     if (chan == 3) {
         stage.resize(px * 3);
-        for (int k = 0; k < 3; k++) memcpy(stage.data() + k * px, ch[k], px * 2);
+        for (int k = 0; k < 3; k++) memcpy(stage.data() + k * px, ch[k], px * sizeof(T));
         src = stage.data();
     }
-    std::vector<uint16_t> coefs(px * chan);
+    std::vector<T> coefs(px * chan);
     uint64_t used = 0;
     int32_t rc = ICER_FATAL_ERROR;
-    int e = icer_b200_compress_batch_u16(c, &p, src, 1, od->rearrange_start, od->size_allocated, od->data_start, coefs.data(), &used,
-                                         &rc, ICER_B200_MEM_HOST, nullptr);
+    int e = compress_batch_any(c, &p, src, sizeof(T) == 2 ? ICER_B200_PIX_U16 : ICER_B200_PIX_NATIVE_U8, 1, od->rearrange_start,
+                               od->size_allocated, od->data_start, (uint16_t *) coefs.data(), &used, &rc, ICER_B200_MEM_HOST, nullptr);
     if (e != ICER_RESULT_OK) return e;
     if (rc == ICER_RESULT_OK || rc == ICER_BYTE_QUOTA_EXCEEDED) {
         // lib_icer leaves the LL-mean-removed sign-magnitude coefficients in the caller's image buffer
-        for (uint32_t k = 0; k < chan; k++) memcpy(ch[k], coefs.data() + k * px, px * 2);
+        for (uint32_t k = 0; k < chan; k++) memcpy(ch[k], coefs.data() + k * px, px * sizeof(T));
         od->size_used = (size_t) used;
     }
     return rc;
 }
 
-int icer_compress_image_uint16(uint16_t *image, size_t image_w, size_t image_h, uint8_t stages, enum icer_filter_types filt,
-                               uint8_t segments, icer_output_data_buf_typedef *output_data) {
-    uint16_t *ch[3] = {image, nullptr, nullptr};
-    return compress_common(ch, 1, image_w, image_h, stages, filt, segments, output_data);
-}
-
-int icer_compress_image_yuv_uint16(uint16_t *y, uint16_t *u, uint16_t *v, size_t image_w, size_t image_h, uint8_t stages,
-                                   enum icer_filter_types filt, uint8_t segments, icer_output_data_buf_typedef *output_data) {
-    uint16_t *ch[3] = {y, u, v};
-    if (!u || !v) return ICER_INVALID_INPUT;
-    return compress_common(ch, 3, image_w, image_h, stages, filt, segments, output_data);
-}
-
-static int decompress_common(uint16_t *const ch[3], uint32_t chan, size_t *image_w, size_t *image_h, size_t bufsize,
+template <typename T>
+static int decompress_common(T *const ch[3], uint32_t chan, size_t *image_w, size_t *image_h, size_t bufsize,
                              const uint8_t *data, size_t len, uint8_t stages, int filt, uint8_t segments) {
     icer_b200_ctx *c = default_ctx();
     if (!c) return ICER_FATAL_ERROR;
@@ -886,22 +982,38 @@ static int decompress_common(uint16_t *const ch[3], uint32_t chan, size_t *image
     p.width = ps.w; p.height = ps.h; p.channels = chan; p.stages = stages; p.filter = (uint32_t) filt; p.segments = segments;
     p.byte_quota = 0;
     const size_t px = (size_t) ps.w * ps.h;
-    std::vector<uint16_t> outbuf(px * chan);
+    std::vector<T> outbuf(px * chan);
     uint64_t l = len;
     uint32_t dims[2];
     int32_t rc = ICER_FATAL_ERROR;
-    int e = icer_b200_decompress_batch_u16(c, &p, data, len, &l, 1, outbuf.data(), dims, &rc, ICER_B200_MEM_HOST, nullptr);
+    int e = decompress_batch_any(c, &p, data, len, &l, 1, outbuf.data(), sizeof(T) == 2 ? ICER_B200_PIX_U16 : ICER_B200_PIX_NATIVE_U8, dims,
+                                 &rc, ICER_B200_MEM_HOST, nullptr);
     if (e != ICER_RESULT_OK) return e;
     if (rc == ICER_RESULT_OK)
-        for (uint32_t k = 0; k < chan; k++) memcpy(ch[k], outbuf.data() + k * px, px * 2);
+        for (uint32_t k = 0; k < chan; k++) memcpy(ch[k], outbuf.data() + k * px, px * sizeof(T));
     return rc;
+}
+
+extern "C" {
+
+int icer_compress_image_uint16(uint16_t *image, size_t image_w, size_t image_h, uint8_t stages, enum icer_filter_types filt,
+                               uint8_t segments, icer_output_data_buf_typedef *output_data) {
+    uint16_t *ch[3] = {image, nullptr, nullptr};
+    return compress_common<uint16_t>(ch, 1, image_w, image_h, stages, filt, segments, output_data);
+}
+
+int icer_compress_image_yuv_uint16(uint16_t *y, uint16_t *u, uint16_t *v, size_t image_w, size_t image_h, uint8_t stages,
+                                   enum icer_filter_types filt, uint8_t segments, icer_output_data_buf_typedef *output_data) {
+    uint16_t *ch[3] = {y, u, v};
+    if (!u || !v) return ICER_INVALID_INPUT;
+    return compress_common<uint16_t>(ch, 3, image_w, image_h, stages, filt, segments, output_data);
 }
 
 int icer_decompress_image_uint16(uint16_t *image, size_t *image_w, size_t *image_h, size_t image_bufsize, const uint8_t *datastream,
                                  size_t data_length, uint8_t stages, enum icer_filter_types filt, uint8_t segments) {
     uint16_t *ch[3] = {image, nullptr, nullptr};
     if (!image) return ICER_INVALID_INPUT;
-    return decompress_common(ch, 1, image_w, image_h, image_bufsize, datastream, data_length, stages, filt, segments);
+    return decompress_common<uint16_t>(ch, 1, image_w, image_h, image_bufsize, datastream, data_length, stages, filt, segments);
 }
 
 int icer_decompress_image_yuv_uint16(uint16_t *y, uint16_t *u, uint16_t *v, size_t *image_w, size_t *image_h, size_t image_bufsize,
@@ -909,7 +1021,53 @@ int icer_decompress_image_yuv_uint16(uint16_t *y, uint16_t *u, uint16_t *v, size
                                      uint8_t segments) {
     uint16_t *ch[3] = {y, u, v};
     if (!y || !u || !v) return ICER_INVALID_INPUT;
-    return decompress_common(ch, 3, image_w, image_h, image_bufsize, datastream, data_length, stages, filt, segments);
+    return decompress_common<uint16_t>(ch, 3, image_w, image_h, image_bufsize, datastream, data_length, stages, filt, segments);
+}
+
+// ---- the native uint8 codec (lib_icer/inc/icer.h:386-390, :407-412): int8 wavelet arithmetic, 7 bit planes, 300 packets ----
+int icer_compress_image_uint8(uint8_t *image, size_t image_w, size_t image_h, uint8_t stages, enum icer_filter_types filt,
+                              uint8_t segments, icer_output_data_buf_typedef *output_data) {
+    uint8_t *ch[3] = {image, nullptr, nullptr};
+    return compress_common<uint8_t>(ch, 1, image_w, image_h, stages, filt, segments, output_data);
+}
+
+int icer_compress_image_yuv_uint8(uint8_t *y, uint8_t *u, uint8_t *v, size_t image_w, size_t image_h, uint8_t stages,
+                                  enum icer_filter_types filt, uint8_t segments, icer_output_data_buf_typedef *output_data) {
+    uint8_t *ch[3] = {y, u, v};
+    if (!u || !v) return ICER_INVALID_INPUT;
+    return compress_common<uint8_t>(ch, 3, image_w, image_h, stages, filt, segments, output_data);
+}
+
+int icer_decompress_image_uint8(uint8_t *image, size_t *image_w, size_t *image_h, size_t image_bufsize, const uint8_t *datastream,
+                                size_t data_length, uint8_t stages, enum icer_filter_types filt, uint8_t segments) {
+    uint8_t *ch[3] = {image, nullptr, nullptr};
+    if (!image) return ICER_INVALID_INPUT;
+    return decompress_common<uint8_t>(ch, 1, image_w, image_h, image_bufsize, datastream, data_length, stages, filt, segments);
+}
+
+int icer_decompress_image_yuv_uint8(uint8_t *y, uint8_t *u, uint8_t *v, size_t *image_w, size_t *image_h, size_t image_bufsize,
+                                    const uint8_t *datastream, size_t data_length, uint8_t stages, enum icer_filter_types filt,
+                                    uint8_t segments) {
+    uint8_t *ch[3] = {y, u, v};
+    if (!y || !u || !v) return ICER_INVALID_INPUT;
+    return decompress_common<uint8_t>(ch, 3, image_w, image_h, image_bufsize, datastream, data_length, stages, filt, segments);
+}
+
+int icer_wavelet_transform_stages_uint8(uint8_t *image, size_t image_w, size_t image_h, uint8_t stages, enum icer_filter_types filt) {
+    icer_b200_ctx *c = default_ctx();
+    if (!c) return ICER_FATAL_ERROR;
+    int32_t rc = ICER_FATAL_ERROR;
+    int e = icer_b200_dwt_batch_u8(c, image, 1, (uint32_t) image_w, (uint32_t) image_h, stages, (uint32_t) filt, 0, &rc, ICER_B200_MEM_HOST, nullptr);
+    return e != ICER_RESULT_OK ? e : rc;
+}
+
+int icer_inverse_wavelet_transform_stages_uint8(uint8_t *image, size_t image_w, size_t image_h, uint8_t stages,
+                                                enum icer_filter_types filt) {
+    icer_b200_ctx *c = default_ctx();
+    if (!c) return ICER_FATAL_ERROR;
+    int32_t rc = ICER_FATAL_ERROR;
+    int e = icer_b200_dwt_batch_u8(c, image, 1, (uint32_t) image_w, (uint32_t) image_h, stages, (uint32_t) filt, 1, &rc, ICER_B200_MEM_HOST, nullptr);
+    return e != ICER_RESULT_OK ? e : rc;
 }
 
 int icer_wavelet_transform_stages_uint16(uint16_t *image, size_t image_w, size_t image_h, uint8_t stages, enum icer_filter_types filt) {

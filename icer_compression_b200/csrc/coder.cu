@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(256) k_frames_to_T(const uint16_t *__restrict_
 
 __global__ void __launch_bounds__(256) k_T_to_frames(const uint16_t *__restrict__ T, uint16_t *__restrict__ dst,
                                                      const int32_t *__restrict__ frame_of, const uint16_t *__restrict__ mean,
-                                                     uint32_t chan, uint32_t plane_px, uint64_t cap_px, int W, int llw, int llh) {
+                                                     uint32_t chan, uint32_t plane_px, uint64_t cap_px, int W, int llw, int llh,
+                                                     int bits8) {
     __shared__ uint16_t tile[32][34];
     const uint32_t g = blockIdx.z, c = blockIdx.y;
     const size_t px0 = (size_t) blockIdx.x * 32;
@@ -190,7 +191,12 @@ __global__ void __launch_bounds__(256) k_T_to_frames(const uint16_t *__restrict_
         uint32_t v = tile[tx][f];
         v = (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;                      // icer_wavelet.c:880-886
         const int r = (int) (px / (size_t) W), cc = (int) (px % (size_t) W);
-        if (r < llh && cc < llw) v = (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + (int) (int16_t) mean[(size_t) frame * chan + c]);
+        if (r < llh && cc < llw) {
+            const int m = (int) mean[(size_t) frame * chan + c];
+            // uint16 API: int16 add (icer_compress.c:524-531); native uint8 API: int8 add of the header value's low byte (:258-265)
+            v = bits8 ? (uint32_t) (uint16_t) (int16_t) (int8_t) ((int) (int16_t) v + (int) (int8_t) m)
+                      : (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + (int) (int16_t) m);
+        }
         dst[((size_t) frame * chan + c) * cap_px + px] = (uint16_t) v;
     }
 }
@@ -908,9 +914,10 @@ __global__ void __launch_bounds__(128) k_quota_scan(AssembleArgs a) {
     const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (f >= a.nframes) return;
-    int rc = a.plan_status;
+    int rc = ICER_RESULT_OK;
     for (uint32_t c = 0; c < a.chan && rc == ICER_RESULT_OK; c++)
         if (a.ovf[(size_t) f * a.chan + c]) rc = ICER_INTEGER_OVERFLOW;
+    if (rc == ICER_RESULT_OK) rc = a.plan_status;      // ICER_PACKET_COUNT_EXCEEDED: found after the transform
     const uint32_t *bits = a.bits + (size_t) f * a.nstreams;
     uint64_t *offp = a.off_prio + (size_t) f * a.nstreams;     // indexed by STREAM ID; ~0 = dropped
     uint64_t used = 0;
@@ -1044,13 +1051,13 @@ int launch_frames_to_T(const uint16_t *frames, uint16_t *T, uint32_t nframes, ui
 
 int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame_of, const uint16_t *mean, uint32_t ngroups,
                        uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, uint32_t llw, uint32_t llh, cudaStream_t st,
-                       LaunchStats &ls) {
+                       LaunchStats &ls, bool bits8) {
     const size_t plane_px = (size_t) w * h;
     for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
         const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
         dim3 grid((unsigned) ((plane_px + 31) / 32), chan, cnt);
         k_T_to_frames<<<grid, 256, 0, st>>>(T + (size_t) g0 * chan * plane_px * 32, frames, frame_of + (size_t) g0 * 32, mean, chan,
-                                            (uint32_t) plane_px, cap_px, (int) w, (int) llw, (int) llh);
+                                            (uint32_t) plane_px, cap_px, (int) w, (int) llw, (int) llh, bits8 ? 1 : 0);
         ls.launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1076,12 +1083,13 @@ int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls) {
     int rc = upload_tables();
     if (rc) return rc;
     const unsigned long long nst = (unsigned long long) a.nframes * a.nstreams;
-    if (nst) k_payload_crc<<<(unsigned) ((nst + 127) / 128), 128, 0, st>>>(a);
+    const bool coded = a.plan_status == ICER_RESULT_OK;     // otherwise the coder did not run: only the per-frame status is produced
+    if (nst && coded) k_payload_crc<<<(unsigned) ((nst + 127) / 128), 128, 0, st>>>(a);
     k_quota_scan<<<(a.nframes + 3) / 4, 128, 0, st>>>(a);
     const unsigned long long warps = (unsigned long long) a.nframes * a.nstreams;
     const unsigned long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0x7FFFFFFFull) return ICER_FATAL_ERROR;
-    if (blocks) k_gather<<<(unsigned) blocks, 256, 0, st>>>(a);
+    if (blocks && coded) k_gather<<<(unsigned) blocks, 256, 0, st>>>(a);
     ls.launches += 3;
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;

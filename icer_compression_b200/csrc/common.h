@@ -48,6 +48,7 @@ struct Unit {
 struct Plan {
     uint32_t w, h, chan, stages, segments, planes, max_stages;
     int status;                          // ICER_RESULT_OK or the error every frame of this shape gets
+    int enc_status;                      // errors only the encoder reports (ICER_PACKET_COUNT_EXCEEDED)
     std::vector<Unit> units;
     uint32_t nstreams;                   // units.size() * planes
     std::vector<uint32_t> prio_order;    // stream ids in (priority packet, segment) order
@@ -66,7 +67,8 @@ struct Plan {
 };
 
 int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages, uint32_t segments, uint32_t planes,
-               uint32_t max_stages, uint32_t max_packets, int scratch_bits);
+               uint32_t max_stages, uint32_t max_packets, int scratch_bits, bool native_u8 = false);
+void u8_interleave_dst(uint32_t len, std::vector<uint32_t> &dst);
 void free_plan_device(Plan &pl);
 int upload_plan(Plan &pl);
 
@@ -80,12 +82,13 @@ struct LaunchStats { uint64_t launches = 0; };
 
 // forward / inverse multi-stage DWT over `nplanes` planes of w*h int16, in place (tmp has the same size)
 int launch_dwt_forward(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
-                       uint32_t filt, int *d_ovf /* per plane, pre-zeroed */, cudaStream_t st, LaunchStats &ls);
+                       uint32_t filt, int *d_ovf /* per plane, pre-zeroed */, cudaStream_t st, LaunchStats &ls, bool bits8 = false);
 int launch_dwt_inverse(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
-                       uint32_t filt, bool clamp_negative, cudaStream_t st, LaunchStats &ls);
+                       uint32_t filt, bool clamp_negative, cudaStream_t st, LaunchStats &ls, bool bits8 = false,
+                       const std::map<uint32_t, const uint32_t *> *perms = nullptr);
 // LL mean removal + sign-magnitude (encode), and the inverse (decode)
 int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
-                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls);
+                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8 = false);
 int launch_from_signmag_add_mean(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
                                  const uint16_t *d_mean, cudaStream_t st, LaunchStats &ls);
 
@@ -143,7 +146,7 @@ int launch_frames_to_T(const uint16_t *frames, uint16_t *T, uint32_t nframes, ui
 // also undoes sign-magnitude and adds the header LL mean; frame_of maps (group, lane) to the batch index (-1 = none)
 int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame_of, const uint16_t *mean, uint32_t ngroups,
                        uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, uint32_t llw, uint32_t llh, cudaStream_t st,
-                       LaunchStats &ls);
+                       LaunchStats &ls, bool bits8 = false);
 
 // ---- K6: device stream scanner (parse.cu) ------------------------------------------------------------
 struct ParseInfo {               // per frame, what lib_icer's scan loop leaves behind (icer_compress.c:443-459)
@@ -173,6 +176,10 @@ int launch_table(const TableArgs &t, cudaStream_t st, LaunchStats &ls);
 // ---- pixel formats at the boundary (pixfmt.cu) ---------------------------------------------------------
 int launch_u8_to_u16(const uint8_t *src, uint16_t *dst, size_t count, cudaStream_t st, LaunchStats &ls);
 int launch_u16_to_u8(const uint16_t *src, uint8_t *dst, size_t count, cudaStream_t st, LaunchStats &ls);
+// native uint8 codec: int8 samples sign-extended into the int16 containers and back (low byte); sign-magnitude 16 -> 8
+int launch_s8_to_i16(const uint8_t *src, uint16_t *dst, size_t count, cudaStream_t st, LaunchStats &ls);
+int launch_i16_to_b8(const uint16_t *src, uint8_t *dst, size_t count, cudaStream_t st, LaunchStats &ls);
+int launch_sm16_to_sm8(const uint16_t *src, uint8_t *dst, size_t count, cudaStream_t st, LaunchStats &ls);
 int launch_rgb_to_yuv(const uint8_t *rgb, uint16_t *yuv, size_t n, size_t px, cudaStream_t st, LaunchStats &ls);
 int launch_yuv_to_rgb(const uint16_t *yuv, uint8_t *rgb, size_t n, size_t px, size_t cap_px, cudaStream_t st, LaunchStats &ls);
 

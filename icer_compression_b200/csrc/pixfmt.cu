@@ -17,6 +17,21 @@ __global__ void __launch_bounds__(256) k_u16_to_u8(const uint16_t *__restrict__ 
         dst[i] = v > 255 ? 255 : (uint8_t) v;                                  // icer_util.c:322-325
     }
 }
+// native uint8 codec (icer_compress_image_uint8 & co): samples are int8; they travel sign-extended in the int16 containers
+__global__ void __launch_bounds__(256) k_s8_to_i16(const uint8_t *__restrict__ src, uint16_t *__restrict__ dst, size_t count) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x)
+        dst[i] = (uint16_t) (int16_t) (int8_t) src[i];
+}
+__global__ void __launch_bounds__(256) k_i16_to_b8(const uint16_t *__restrict__ src, uint8_t *__restrict__ dst, size_t count) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x) dst[i] = (uint8_t) src[i];
+}
+// sign bit 15 + 7-bit magnitude -> the uint8 codec's sign bit 7 + magnitude (what it leaves in the caller's image buffer)
+__global__ void __launch_bounds__(256) k_sm16_to_sm8(const uint16_t *__restrict__ src, uint8_t *__restrict__ dst, size_t count) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x) {
+        const uint16_t v = src[i];
+        dst[i] = (uint8_t) ((v & 0x7F) | ((v >> 8) & 0x80));
+    }
+}
 // rgb: [n][px][3] packed; yuv: [n][3][px]
 __global__ void __launch_bounds__(256) k_rgb_to_yuv(const uint8_t *__restrict__ rgb, uint16_t *__restrict__ yuv, size_t n, size_t px) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n * px; i += (size_t) gridDim.x * blockDim.x) {
@@ -56,6 +71,24 @@ int launch_u8_to_u16(const uint8_t *src, uint16_t *dst, size_t count, cudaStream
 }
 int launch_u16_to_u8(const uint16_t *src, uint8_t *dst, size_t count, cudaStream_t st, LaunchStats &ls) {
     k_u16_to_u8<<<grid_for(count), 256, 0, st>>>(src, dst, count);
+    ls.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+int launch_s8_to_i16(const uint8_t *src, uint16_t *dst, size_t count, cudaStream_t st, LaunchStats &ls) {
+    k_s8_to_i16<<<grid_for(count), 256, 0, st>>>(src, dst, count);
+    ls.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+int launch_i16_to_b8(const uint16_t *src, uint8_t *dst, size_t count, cudaStream_t st, LaunchStats &ls) {
+    k_i16_to_b8<<<grid_for(count), 256, 0, st>>>(src, dst, count);
+    ls.launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ICER_RESULT_OK;
+}
+int launch_sm16_to_sm8(const uint16_t *src, uint8_t *dst, size_t count, cudaStream_t st, LaunchStats &ls) {
+    k_sm16_to_sm8<<<grid_for(count), 256, 0, st>>>(src, dst, count);
     ls.launches++;
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;

@@ -144,10 +144,10 @@ struct Packet { int level, subband, lsb, chan; uint64_t prio; int order; };
 }
 
 int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages, uint32_t segments, uint32_t planes,
-               uint32_t max_stages, uint32_t max_packets, int scratch_bits) {
+               uint32_t max_stages, uint32_t max_packets, int scratch_bits, bool native_u8) {
     pl.w = w; pl.h = h; pl.chan = chan; pl.stages = stages; pl.segments = segments; pl.planes = planes;
     pl.max_stages = max_stages; pl.scratch_bits = scratch_bits;
-    pl.status = ICER_RESULT_OK;
+    pl.status = ICER_RESULT_OK; pl.enc_status = ICER_RESULT_OK;
     pl.units.clear(); pl.prio_order.clear(); pl.rearr_order.clear(); pl.unit_of.clear();
     pl.nstreams = 0; pl.scratch_words = 0;
     if (stages < 1 || stages > max_stages) { pl.status = ICER_TOO_MANY_STAGES; return pl.status; }
@@ -214,7 +214,8 @@ int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages,
             }
     }
     // lib_icer: `ind++; if (ind >= ICER_MAX_PACKETS_16) return ICER_PACKET_COUNT_EXCEEDED` (icer_compress.c:327)
-    if (pk.size() >= max_packets) { pl.status = ICER_PACKET_COUNT_EXCEEDED; return pl.status; }
+    // -- an ENCODER limit only: the decoder never builds the packet list, so the plan stays usable for decoding
+    pl.enc_status = pk.size() >= max_packets ? ICER_PACKET_COUNT_EXCEEDED : ICER_RESULT_OK;
     std::stable_sort(pk.begin(), pk.end(), [](const Packet &a, const Packet &b) {
         if (a.prio != b.prio) return a.prio > b.prio;
         return a.subband < b.subband;
@@ -225,12 +226,15 @@ int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages,
             if (it == pl.unit_of.end()) break;
             pl.prio_order.push_back(it->second * planes + (uint32_t) p.lsb);
         }
-    // rearranged order: segment asc, subband 3..0, level hi..lo, lsb hi..lo, channel asc
+    // rearranged order: segment asc, subband 3..0, level hi..lo, lsb hi..lo, channel asc -- except the native uint8
+    // COLOUR encoder, whose loops run subband, level and lsb ASCENDING (icer_color.c:184-203 vs :508-527)
+    const bool asc = native_u8 && chan == 3;
     for (int sg = 0; sg <= ICER_MAX_SEGMENTS; sg++)
-        for (int sb = 3; sb >= 0; sb--)
-            for (int lv = (int) max_stages; lv >= 0; lv--)
-                for (int lsb = (int) planes - 1; lsb >= 0; lsb--)
+        for (int a = 0; a <= 3; a++)
+            for (int b = 0; b <= (int) max_stages; b++)
+                for (int cidx = 0; cidx < (int) planes; cidx++)
                     for (int ch = 0; ch < (int) chan; ch++) {
+                        const int sb = asc ? a : 3 - a, lv = asc ? b : (int) max_stages - b, lsb = asc ? cidx : (int) planes - 1 - cidx;
                         auto it = pl.unit_of.find(std::make_tuple(ch, lv, sb, sg));
                         if (it != pl.unit_of.end()) pl.rearr_order.push_back(it->second * planes + (uint32_t) lsb);
                     }
@@ -247,6 +251,56 @@ int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages,
         }
     pl.scratch_words = off;
     return ICER_RESULT_OK;
+}
+
+// Where lib_icer's icer_interleave_uint8 (icer_wavelet.c:570-628) puts element i of a length-n lows|highs array.  For
+// even n this is the perfect in-shuffle (i -> 2i / 2(i - n/2) + 1); for odd n the function's `halfleft` is one too large
+// (:599) and the result is a different, fixed permutation, which the native uint8 decoder therefore applies
+// after every inverse 1-D pass over an odd-length line.  Derived by replaying the function's index operations (odd-tail
+// rotation, then per 3^k+1 slice: three reversals + cycle-leader walk, slice sizes from icer_find_k's binary search
+// :823-847, which is not always the largest fitting slice) on an identity array.
+void u8_interleave_dst(uint32_t len, std::vector<uint32_t> &dst) {
+    std::vector<uint32_t> a(len);
+    for (uint32_t i = 0; i < len; i++) a[i] = i;
+    size_t slice[12];
+    { size_t p3 = 1; for (int k = 0; k < 12; k++) { slice[k] = p3 + 1; p3 *= 3; } }
+    auto find_k = [&](size_t want) -> int {
+        int lo = 0, hi = 11, res = 0;
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (want > slice[mid]) { lo = mid + 1; res = mid; }
+            else if (want < slice[mid]) hi = mid - 1;
+            else break;
+        }
+        return res;
+    };
+    auto reverse = [&](size_t s, size_t e) { while (s < e) { std::swap(a[s], a[e]); s++; e--; } };
+    const bool odd = len & 1;
+    size_t n = odd ? len - 1 : len;
+    if (odd) {
+        const uint32_t keep = a[n / 2];
+        for (size_t i = n / 2; i < n; i++) a[i] = a[i + 1];
+        a[len - 1] = keep;
+    }
+    size_t done = 0;
+    while (done < n) {
+        const size_t seg = slice[find_k(n - done)], half = seg / 2, left = n - done;
+        const size_t halfleft = left / 2 - (odd ? 0 : 1);
+        reverse(done + half, done + halfleft + half);
+        reverse(done + half, done + seg - 1);
+        reverse(done + seg, done + halfleft + half);
+        for (size_t i = 1; i < seg; i *= 3) {
+            size_t j = i;
+            uint32_t carry = a[j + done];
+            do {
+                j = j < half ? 2 * j : (j - half) * 2 + 1;
+                std::swap(a[j + done], carry);
+            } while (j != i);
+        }
+        done += seg;
+    }
+    dst.assign(len, 0);
+    for (uint32_t pos = 0; pos < len; pos++) dst[a[pos]] = pos;
 }
 
 void free_plan_device(Plan &pl) {

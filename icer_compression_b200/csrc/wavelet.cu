@@ -14,6 +14,11 @@ __constant__ int c_filt[7][4] = {{0, 4, 4, 0}, {0, 4, 6, 4}, {-1, 4, 8, 6}, {0, 
 
 namespace {
 
+// Sample width of the stored values: the uint16 API wraps to int16 (icer_wavelet.c:412-415,460-461), the native uint8 API
+// (:216-381) wraps to int8 -- here with the int8 values sign-extended in the same int16 containers.
+template <bool B8> __device__ __forceinline__ int wrapv(int v) { return B8 ? (int) (int8_t) v : (int) (int16_t) v; }
+template <bool B8> __device__ __forceinline__ bool ovfv(int v) { return B8 ? (v > 127 || v < -128) : (v > 32767 || v < -32768); }
+
 // A line view: element i of line `line` of plane `p`.
 template <bool COL>
 struct LineView {
@@ -25,7 +30,7 @@ struct LineView {
 };
 
 // ---- forward pass: thread (line, k) produces l[k] and h[k] --------------------------------------------
-template <bool COL>
+template <bool COL, bool B8>
 __global__ void __launch_bounds__(256) k_fwd_pass(const int16_t *__restrict__ src, int16_t *__restrict__ dst, int n,
                                                   int nlines, int W, size_t plane_stride, int filt, int plane0,
                                                   int *__restrict__ ovf) {
@@ -40,16 +45,16 @@ __global__ void __launch_bounds__(256) k_fwd_pass(const int16_t *__restrict__ sr
     const size_t es = COL ? (size_t) W : 1;
 
     // stored (int16-wrapped) low / high of pair j
-    auto LO = [&](int j) -> int { return j < nh ? (int) (int16_t) ((X(2 * j) + X(2 * j + 1)) >> 1) : X(n - 1); };
-    auto HI = [&](int j) -> int { return (int) (int16_t) (X(2 * j) - X(2 * j + 1)); };
+    auto LO = [&](int j) -> int { return j < nh ? wrapv<B8>((X(2 * j) + X(2 * j + 1)) >> 1) : X(n - 1); };
+    auto HI = [&](int j) -> int { return wrapv<B8>(X(2 * j) - X(2 * j + 1)); };
     auto R = [&](int j) -> int { return (int) (int16_t) (LO(j - 1) - LO(j)); };   // get_r_int16 :206-208
 
     d[(size_t) k * es] = (int16_t) LO(k);
     if (k >= nh) return;
     const int a = X(2 * k), b = X(2 * k + 1);
     const int hi = a - b;
-    bool o = hi > 32767 || hi < -32768;
-    const int dk = (int) (int16_t) hi;
+    bool o = ovfv<B8>(hi);
+    const int dk = wrapv<B8>(hi);
     const int f0 = c_filt[filt][0], f1 = c_filt[filt][1], f2 = c_filt[filt][2], f3 = c_filt[filt][3];
     int sub;
     if (k == 0) {
@@ -65,15 +70,18 @@ __global__ void __launch_bounds__(256) k_fwd_pass(const int16_t *__restrict__ sr
         sub = (f0 * rm1 + f1 * R(k) + f2 * R(k + 1) - f3 * dn + 8) >> 4;
     }
     const int hv = dk - sub;
-    o |= hv > 32767 || hv < -32768;
-    d[(size_t) (nl + k) * es] = (int16_t) hv;
+    o |= ovfv<B8>(hv);
+    d[(size_t) (nl + k) * es] = (int16_t) wrapv<B8>(hv);
     if (o) atomicOr(&ovf[plane], 1);
 }
 
 // ---- inverse pass, data-parallel form (beta == 0 and alpha_-1 == 0: filter A) -----------------------------
-template <bool COL, bool CLAMP>
+// perm (native uint8 API, odd n only): where lib_icer's icer_interleave_uint8 really puts element i of the lows|highs
+// array (:570-628; it is NOT the perfect shuffle for odd n); nullptr = the true interleave.
+template <bool COL, bool CLAMP, bool B8>
 __global__ void __launch_bounds__(256) k_inv_pass_par(const int16_t *__restrict__ src, int16_t *__restrict__ dst, int n,
-                                                      int nlines, int W, size_t plane_stride, int filt, int plane0) {
+                                                      int nlines, int W, size_t plane_stride, int filt, int plane0,
+                                                      const uint32_t *__restrict__ perm) {
     const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y;
     const int line = COL ? tx : ty, k = COL ? ty : tx;
     const int nl = (n + 1) >> 1, nh = n >> 1;
@@ -87,7 +95,7 @@ __global__ void __launch_bounds__(256) k_inv_pass_par(const int16_t *__restrict_
     if (k >= nh) {   // odd tail: low + floor(1/2) = low (:537-545)
         int v = S(nl - 1);
         if (CLAMP && v < 0) v = 0;
-        d[(size_t) (n - 1) * es] = (int16_t) v;
+        d[(size_t) (perm ? (int) perm[nl - 1] : n - 1) * es] = (int16_t) v;
         return;
     }
     const int f1 = c_filt[filt][1], f2 = c_filt[filt][2];
@@ -95,18 +103,19 @@ __global__ void __launch_bounds__(256) k_inv_pass_par(const int16_t *__restrict_
     if (k == 0) add = R(1) >> 2;
     else if (!odd && k == nh - 1) add = R(k) >> 2;
     else add = (f1 * R(k) + f2 * R(k + 1) + 8) >> 4;
-    const int dk = (int) (int16_t) (S(nl + k) + add);
+    const int dk = wrapv<B8>(S(nl + k) + add);
     const int t = S(k) + ((dk + 1) >> 1);
-    int v0 = (int) (int16_t) t, v1 = (int) (int16_t) (t - dk);
+    int v0 = wrapv<B8>(t), v1 = wrapv<B8>(t - dk);
     if (CLAMP) { v0 = v0 < 0 ? 0 : v0; v1 = v1 < 0 ? 0 : v1; }
-    d[(size_t) (2 * k) * es] = (int16_t) v0;
-    d[(size_t) (2 * k + 1) * es] = (int16_t) v1;
+    d[(size_t) (perm ? (int) perm[k] : 2 * k) * es] = (int16_t) v0;
+    d[(size_t) (perm ? (int) perm[nl + k] : 2 * k + 1) * es] = (int16_t) v1;
 }
 
 // ---- inverse pass, serial along the line (beta != 0: d[k] needs the restored d[k+1]; :478-508) --------------
-template <bool COL, bool CLAMP>
+template <bool COL, bool CLAMP, bool B8>
 __global__ void __launch_bounds__(128) k_inv_pass_ser(const int16_t *__restrict__ src, int16_t *__restrict__ dst, int n,
-                                                      int nlines, int W, size_t plane_stride, int filt, int plane0) {
+                                                      int nlines, int W, size_t plane_stride, int filt, int plane0,
+                                                      const uint32_t *__restrict__ perm) {
     const int line = blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= nlines) return;
     const int plane = plane0 + blockIdx.z;
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(128) k_inv_pass_ser(const int16_t *__restrict_
     if (odd) {
         int v = S(nl - 1);
         if (CLAMP && v < 0) v = 0;
-        d[(size_t) (n - 1) * es] = (int16_t) v;
+        d[(size_t) (perm ? (int) perm[nl - 1] : n - 1) * es] = (int16_t) v;
     }
     int dnext = 0;
     for (int k = nh - 1; k >= 0; k--) {
@@ -137,17 +146,18 @@ __global__ void __launch_bounds__(128) k_inv_pass_ser(const int16_t *__restrict_
             const int dn = (odd && k + 1 == nl - 1) ? 0 : dnext;
             add = (f0 * rm1 + f1 * R(k) + f2 * R(k + 1) - f3 * dn + 8) >> 4;
         }
-        const int dk = (int) (int16_t) (S(nl + k) + add);
+        const int dk = wrapv<B8>(S(nl + k) + add);
         dnext = dk;
         const int t = S(k) + ((dk + 1) >> 1);
-        int v0 = (int) (int16_t) t, v1 = (int) (int16_t) (t - dk);
+        int v0 = wrapv<B8>(t), v1 = wrapv<B8>(t - dk);
         if (CLAMP) { v0 = v0 < 0 ? 0 : v0; v1 = v1 < 0 ? 0 : v1; }
-        d[(size_t) (2 * k) * es] = (int16_t) v0;
-        d[(size_t) (2 * k + 1) * es] = (int16_t) v1;
+        d[(size_t) (perm ? (int) perm[k] : 2 * k) * es] = (int16_t) v0;
+        d[(size_t) (perm ? (int) perm[nl + k] : 2 * k + 1) * es] = (int16_t) v1;
     }
 }
 
 // ---- K3: LL mean (unsigned sum, icer_compress.c:289-302), subtract on LL, then sign-magnitude everywhere ----
+template <bool B8>
 __global__ void __launch_bounds__(256) k_ll_mean(uint16_t *__restrict__ planes, size_t plane_stride, int W, int llw,
                                                  int llh, uint16_t *__restrict__ mean_out, int *__restrict__ ovf) {
     __shared__ unsigned long long red[256];
@@ -155,7 +165,8 @@ __global__ void __launch_bounds__(256) k_ll_mean(uint16_t *__restrict__ planes, 
     uint16_t *p = planes + (size_t) blockIdx.x * plane_stride;
     const int total = llw * llh;
     unsigned long long sum = 0;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) sum += p[(size_t) (i / llw) * W + (i % llw)];
+    // the sum runs over the UNSIGNED reinterpretation of the samples (uint16 / uint8: icer_compress.c:289-296, :28-36)
+    for (int i = threadIdx.x; i < total; i += blockDim.x) sum += p[(size_t) (i / llw) * W + (i % llw)] & (B8 ? 0xFFu : 0xFFFFu);
     red[threadIdx.x] = sum;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
@@ -163,27 +174,31 @@ __global__ void __launch_bounds__(256) k_ll_mean(uint16_t *__restrict__ planes, 
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        unsigned m = (unsigned) ((red[0] / (unsigned long long) total) & 0xFFFF);   // uint16_t ll_mean = sum / n
+        unsigned m = (unsigned) ((red[0] / (unsigned long long) total) & (B8 ? 0xFFu : 0xFFFFu));   // uintN_t ll_mean = sum / n
         s_mean = m;
         mean_out[blockIdx.x] = (uint16_t) m;
-        if (m > 32767) atomicOr(&ovf[blockIdx.x], 2);
+        if (m > (B8 ? 127u : 32767u)) atomicOr(&ovf[blockIdx.x], 2);
     }
     __syncthreads();
-    const int m = (int) (int16_t) s_mean;
+    const int m = wrapv<B8>((int) s_mean);
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         uint16_t *q = &p[(size_t) (i / llw) * W + (i % llw)];
-        *q = (uint16_t) (int16_t) ((int) (int16_t) *q - m);
+        *q = (uint16_t) (int16_t) wrapv<B8>((int) (int16_t) *q - m);
     }
 }
 
+// B8: the int8 value lives sign-extended in the container; its 7-bit magnitude goes to bits 0-6 and the sign to bit 15, so
+// that the coder sees the uint8 codec's samples (sign bit 7, icer_wavelet.c:851-857) in its own uint16 convention.
+template <bool B8>
 __device__ __forceinline__ uint32_t to_signmag(uint32_t v) {          // icer_wavelet.c:871-877
     const int s = (int) (int16_t) v;
-    return s < 0 ? (uint32_t) ((-s) & 0x7FFF) | 0x8000u : (uint32_t) s;
+    return s < 0 ? (uint32_t) ((-s) & (B8 ? 0x7F : 0x7FFF)) | 0x8000u : (uint32_t) s;
 }
 __device__ __forceinline__ uint32_t from_signmag(uint32_t v) {        // icer_wavelet.c:880-886
     return (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;
 }
 
+template <bool B8>
 __global__ void __launch_bounds__(256) k_to_signmag(uint16_t *__restrict__ data, size_t count) {
     // 8 samples (128 bits) per thread per iteration
     size_t nvec = count / 8;
@@ -192,11 +207,11 @@ __global__ void __launch_bounds__(256) k_to_signmag(uint16_t *__restrict__ data,
         uint4 q = v[i];
         uint32_t *w = reinterpret_cast<uint32_t *>(&q);
 #pragma unroll
-        for (int j = 0; j < 4; j++) w[j] = to_signmag(w[j] & 0xFFFF) | (to_signmag(w[j] >> 16) << 16);
+        for (int j = 0; j < 4; j++) w[j] = to_signmag<B8>(w[j] & 0xFFFF) | (to_signmag<B8>(w[j] >> 16) << 16);
         v[i] = q;
     }
     if (blockIdx.x == 0)
-        for (size_t i = nvec * 8 + threadIdx.x; i < count; i += blockDim.x) data[i] = (uint16_t) to_signmag(data[i]);
+        for (size_t i = nvec * 8 + threadIdx.x; i < count; i += blockDim.x) data[i] = (uint16_t) to_signmag<B8>(data[i]);
 }
 
 // decode side: from sign-magnitude everywhere, then add the header's LL mean on the LL region
@@ -224,7 +239,7 @@ int for_plane_chunks(size_t nplanes, F f) {
 }  // namespace
 
 int launch_dwt_forward(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
-                       uint32_t filt, int *d_ovf, cudaStream_t st, LaunchStats &ls) {
+                       uint32_t filt, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8) {
     uint32_t lw = w, lh = h;
     const size_t ps = (size_t) w * h;
     int16_t *A = reinterpret_cast<int16_t *>(planes), *B = reinterpret_cast<int16_t *>(tmp);
@@ -232,9 +247,14 @@ int launch_dwt_forward(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t
         for_plane_chunks(nplanes, [&](int p0, unsigned cnt) {
             dim3 blk(64, 4);
             dim3 g1(((lw + 1) / 2 + 63) / 64, (lh + 3) / 4, cnt);
-            k_fwd_pass<false><<<g1, blk, 0, st>>>(A, B, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, d_ovf);
             dim3 g2((lw + 63) / 64, ((lh + 1) / 2 + 3) / 4, cnt);
-            k_fwd_pass<true><<<g2, blk, 0, st>>>(B, A, (int) lh, (int) lw, (int) w, ps, (int) filt, p0, d_ovf);
+            if (bits8) {
+                k_fwd_pass<false, true><<<g1, blk, 0, st>>>(A, B, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, d_ovf);
+                k_fwd_pass<true, true><<<g2, blk, 0, st>>>(B, A, (int) lh, (int) lw, (int) w, ps, (int) filt, p0, d_ovf);
+            } else {
+                k_fwd_pass<false, false><<<g1, blk, 0, st>>>(A, B, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, d_ovf);
+                k_fwd_pass<true, false><<<g2, blk, 0, st>>>(B, A, (int) lh, (int) lw, (int) w, ps, (int) filt, p0, d_ovf);
+            }
             ls.launches += 2;
         });
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
@@ -243,29 +263,45 @@ int launch_dwt_forward(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t
     return ICER_RESULT_OK;
 }
 
+namespace {
+template <bool B8>
+void inverse_stage(int16_t *A, int16_t *B, int p0, unsigned cnt, uint32_t lw, uint32_t lh, uint32_t w, size_t ps, uint32_t filt,
+                   bool parallel, bool clamp, const uint32_t *perm_col, const uint32_t *perm_row, cudaStream_t st) {
+    if (parallel) {
+        dim3 blk(64, 4);
+        dim3 g1((lw + 63) / 64, ((lh + 1) / 2 + 3) / 4, cnt);
+        k_inv_pass_par<true, false, B8><<<g1, blk, 0, st>>>(A, B, (int) lh, (int) lw, (int) w, ps, (int) filt, p0, perm_col);
+        dim3 g2(((lw + 1) / 2 + 63) / 64, (lh + 3) / 4, cnt);
+        if (clamp) k_inv_pass_par<false, true, B8><<<g2, blk, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, perm_row);
+        else k_inv_pass_par<false, false, B8><<<g2, blk, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, perm_row);
+    } else {
+        dim3 g1((lw + 127) / 128, 1, cnt);
+        k_inv_pass_ser<true, false, B8><<<g1, 128, 0, st>>>(A, B, (int) lh, (int) lw, (int) w, ps, (int) filt, p0, perm_col);
+        dim3 g2((lh + 127) / 128, 1, cnt);
+        if (clamp) k_inv_pass_ser<false, true, B8><<<g2, 128, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, perm_row);
+        else k_inv_pass_ser<false, false, B8><<<g2, 128, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, perm_row);
+    }
+}
+}  // namespace
+
+// perms (bits8 only): device tables of icer_interleave_uint8's real placement for the ODD line lengths that occur
 int launch_dwt_inverse(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
-                       uint32_t filt, bool clamp_negative, cudaStream_t st, LaunchStats &ls) {
+                       uint32_t filt, bool clamp_negative, cudaStream_t st, LaunchStats &ls, bool bits8,
+                       const std::map<uint32_t, const uint32_t *> *perms) {
     const size_t ps = (size_t) w * h;
     int16_t *A = reinterpret_cast<int16_t *>(planes), *B = reinterpret_cast<int16_t *>(tmp);
     const bool parallel = (filt == ICER_FILTER_A);
+    auto perm_of = [&](uint32_t n) -> const uint32_t * {
+        if (!bits8 || !perms || !(n & 1)) return nullptr;
+        auto it = perms->find(n);
+        return it == perms->end() ? nullptr : it->second;
+    };
     for (int s = (int) stages - 1; s >= 0; s--) {
         const uint32_t lw = (uint32_t) dim_low(w, s), lh = (uint32_t) dim_low(h, s);
         const bool clamp = clamp_negative && s == 0;
         for_plane_chunks(nplanes, [&](int p0, unsigned cnt) {
-            if (parallel) {
-                dim3 blk(64, 4);
-                dim3 g1((lw + 63) / 64, ((lh + 1) / 2 + 3) / 4, cnt);
-                k_inv_pass_par<true, false><<<g1, blk, 0, st>>>(A, B, (int) lh, (int) lw, (int) w, ps, (int) filt, p0);
-                dim3 g2(((lw + 1) / 2 + 63) / 64, (lh + 3) / 4, cnt);
-                if (clamp) k_inv_pass_par<false, true><<<g2, blk, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0);
-                else k_inv_pass_par<false, false><<<g2, blk, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0);
-            } else {
-                dim3 g1((lw + 127) / 128, 1, cnt);
-                k_inv_pass_ser<true, false><<<g1, 128, 0, st>>>(A, B, (int) lh, (int) lw, (int) w, ps, (int) filt, p0);
-                dim3 g2((lh + 127) / 128, 1, cnt);
-                if (clamp) k_inv_pass_ser<false, true><<<g2, 128, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0);
-                else k_inv_pass_ser<false, false><<<g2, 128, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0);
-            }
+            if (bits8) inverse_stage<true>(A, B, p0, cnt, lw, lh, w, ps, filt, parallel, clamp, perm_of(lh), perm_of(lw), st);
+            else inverse_stage<false>(A, B, p0, cnt, lw, lh, w, ps, filt, parallel, clamp, nullptr, nullptr, st);
             ls.launches += 2;
         });
     }
@@ -274,14 +310,19 @@ int launch_dwt_inverse(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t
 }
 
 int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
-                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls) {
+                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8) {
     const size_t ps = (size_t) w * h;
-    k_ll_mean<<<(unsigned) nplanes, 256, 0, st>>>(planes, ps, (int) w, (int) llw, (int) llh, d_mean, d_ovf);
     const size_t count = ps * nplanes;
     unsigned blocks = (unsigned) ((count / 8 + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks == 0) blocks = 1;
-    k_to_signmag<<<blocks, 256, 0, st>>>(planes, count);
+    if (bits8) {
+        k_ll_mean<true><<<(unsigned) nplanes, 256, 0, st>>>(planes, ps, (int) w, (int) llw, (int) llh, d_mean, d_ovf);
+        k_to_signmag<true><<<blocks, 256, 0, st>>>(planes, count);
+    } else {
+        k_ll_mean<false><<<(unsigned) nplanes, 256, 0, st>>>(planes, ps, (int) w, (int) llw, (int) llh, d_mean, d_ovf);
+        k_to_signmag<false><<<blocks, 256, 0, st>>>(planes, count);
+    }
     ls.launches += 2;
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;

@@ -141,6 +141,26 @@ int icer_decompress_image_yuv_uint16(uint16_t *y_channel, uint16_t *u_channel, u
                                      size_t data_length, uint8_t stages, enum icer_filter_types filt,
                                      uint8_t segments);                                            /* icer.h:463-466 */
 
+/* ---- the native uint8 codec (int8 wavelet arithmetic, ICER_BITPLANES_TO_COMPRESS_8 planes, ICER_MAX_PACKETS packets) ---- */
+
+int icer_compress_image_uint8(uint8_t *image, size_t image_w, size_t image_h, uint8_t stages,
+                              enum icer_filter_types filt, uint8_t segments,
+                              icer_output_data_buf_typedef *output_data);                          /* icer.h:386-387 */
+int icer_compress_image_yuv_uint8(uint8_t *y_channel, uint8_t *u_channel, uint8_t *v_channel, size_t image_w,
+                                  size_t image_h, uint8_t stages, enum icer_filter_types filt, uint8_t segments,
+                                  icer_output_data_buf_typedef *output_data);                      /* icer.h:388-390 */
+int icer_decompress_image_uint8(uint8_t *image, size_t *image_w, size_t *image_h, size_t image_bufsize,
+                                const uint8_t *datastream, size_t data_length, uint8_t stages,
+                                enum icer_filter_types filt, uint8_t segments);                    /* icer.h:407-408 */
+int icer_decompress_image_yuv_uint8(uint8_t *y_channel, uint8_t *u_channel, uint8_t *v_channel, size_t *image_w,
+                                    size_t *image_h, size_t image_bufsize, const uint8_t *datastream,
+                                    size_t data_length, uint8_t stages, enum icer_filter_types filt,
+                                    uint8_t segments);                                             /* icer.h:409-412 */
+int icer_wavelet_transform_stages_uint8(uint8_t *image, size_t image_w, size_t image_h, uint8_t stages,
+                                        enum icer_filter_types filt);                              /* icer.h:392 */
+int icer_inverse_wavelet_transform_stages_uint8(uint8_t *image, size_t image_w, size_t image_h, uint8_t stages,
+                                                enum icer_filter_types filt);                      /* icer.h:414 */
+
 /* ---- public sub-APIs kept as kernel-level parity hooks -------------------------------------------- */
 
 int icer_wavelet_transform_stages_uint16(uint16_t *image, size_t image_w, size_t image_h, uint8_t stages,

@@ -46,6 +46,10 @@ void icer_b200_destroy(icer_b200_ctx *ctx);
  * max_stages default 6; max_packets default 800.  Pass 0 to keep a value. */
 int icer_b200_set_limits(icer_b200_ctx *ctx, int planes, int max_stages, int max_packets);
 
+/* The same for the native uint8 codec: planes 1..7 (default ICER_BITPLANES_TO_COMPRESS_8 = 7), max_packets (default
+ * ICER_MAX_PACKETS = 300).  Pass 0 to keep a value. */
+int icer_b200_set_limits_u8(icer_b200_ctx *ctx, int planes, int max_packets);
+
 /* Per-stream payload scratch budget in bits per pixel per plane (default 3).  If any stream needs more the
  * encoder transparently retries with a doubled budget; this knob exists so tests can exercise that path. */
 int icer_b200_set_scratch_bits(icer_b200_ctx *ctx, int bits_per_px_plane);
@@ -84,8 +88,12 @@ int icer_b200_decompress_batch_u16(icer_b200_ctx *ctx, const icer_b200_params *p
  * device, bit-identically, so 8-bit / RGB batches travel at 1-3 bytes per pixel:
  *   ICER_B200_PIX_U16     frames are uint16 [n][channels][h][w]                 (same as the calls above)
  *   ICER_B200_PIX_U8      frames are uint8  [n][channels][h][w]; decode clamps to 255 like the tools' display path
- *   ICER_B200_PIX_RGB888  frames are uint8  [n][h][w][3] packed R,G,B; params.channels must be 3 */
-enum { ICER_B200_PIX_U16 = 0, ICER_B200_PIX_U8 = 1, ICER_B200_PIX_RGB888 = 2 };
+ *   ICER_B200_PIX_RGB888  frames are uint8  [n][h][w][3] packed R,G,B; params.channels must be 3
+ *   ICER_B200_PIX_NATIVE_U8  frames are uint8 [n][channels][h][w] coded by lib_icer's NATIVE uint8 codec
+ *                         (icer_compress_image_uint8 / _yuv_uint8, icer.h:386-390): int8 wavelet arithmetic (only <= 7-bit
+ *                         data survives), ICER_BITPLANES_TO_COMPRESS_8 = 7 planes, ICER_MAX_PACKETS = 300, its own colour
+ *                         segment order and its odd-length interleave defect -- all reproduced bit for bit */
+enum { ICER_B200_PIX_U16 = 0, ICER_B200_PIX_U8 = 1, ICER_B200_PIX_RGB888 = 2, ICER_B200_PIX_NATIVE_U8 = 3 };
 int icer_b200_compress_batch_pix(icer_b200_ctx *ctx, const icer_b200_params *p, const void *frames, int pixfmt, size_t n,
                                  uint8_t *out, size_t out_stride, uint64_t *size_used, int32_t *rc, int mem, void *stream);
 int icer_b200_decompress_batch_pix(icer_b200_ctx *ctx, const icer_b200_params *p, const uint8_t *streams, size_t stream_stride,
@@ -96,6 +104,15 @@ int icer_b200_decompress_batch_pix(icer_b200_ctx *ctx, const icer_b200_params *p
  * batch of [n][height][width] planes, in place.  rc[n] receives ICER_INTEGER_OVERFLOW per plane (forward). */
 int icer_b200_dwt_batch_u16(icer_b200_ctx *ctx, uint16_t *planes, size_t n, uint32_t width, uint32_t height,
                             uint32_t stages, uint32_t filter, int inverse, int32_t *rc, int mem, void *stream);
+
+/* The native uint8 transform (icer_wavelet_transform_stages_uint8 :392 / inverse :414) over [n][height][width] uint8 planes. */
+int icer_b200_dwt_batch_u8(icer_b200_ctx *ctx, uint8_t *planes, size_t n, uint32_t width, uint32_t height, uint32_t stages,
+                           uint32_t filter, int inverse, int32_t *rc, int mem, void *stream);
+
+/* Planning helper (host only, no device needed): dst[i] = where lib_icer's icer_interleave_uint8 (icer_wavelet.c:570-628) puts
+ * element i of a length-len lows|highs array; for odd len this is NOT the perfect shuffle (the defect the native uint8 decoder
+ * has to reproduce). */
+int icer_b200_u8_interleave_map(uint32_t len, uint32_t *dst);
 
 /* Number of kernels launched by this context so far (bench.py's gpu_launches), and the elapsed device time of
  * the last batch call's named phase in milliseconds (measured with CUDA events on the call's stream):

@@ -61,17 +61,36 @@ class Ref:
         L.icer_wavelet_transform_1d_uint16.argtypes = [C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_int]
         L.icer_inverse_wavelet_transform_1d_uint16.argtypes = L.icer_wavelet_transform_1d_uint16.argtypes
         L.icer_compute_bin.argtypes = [C.c_uint32, C.c_uint32]
+        # the native uint8 codec (same shapes, uint8 samples)
+        u8 = C.POINTER(C.c_uint8)
+        L.icer_compress_image_uint8.argtypes = [u8, C.c_size_t, C.c_size_t, C.c_uint8, C.c_int, C.c_uint8, C.POINTER(_OutBuf)]
+        L.icer_compress_image_yuv_uint8.argtypes = [u8] * 3 + [C.c_size_t, C.c_size_t, C.c_uint8, C.c_int, C.c_uint8, C.POINTER(_OutBuf)]
+        L.icer_decompress_image_uint8.argtypes = [u8, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_size_t, u8, C.c_size_t,
+                                                  C.c_uint8, C.c_int, C.c_uint8]
+        L.icer_decompress_image_yuv_uint8.argtypes = [u8] * 3 + [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_size_t, u8,
+                                                                 C.c_size_t, C.c_uint8, C.c_int, C.c_uint8]
+        L.icer_wavelet_transform_stages_uint8.argtypes = [u8, C.c_size_t, C.c_size_t, C.c_uint8, C.c_int]
+        L.icer_inverse_wavelet_transform_stages_uint8.argtypes = L.icer_wavelet_transform_stages_uint8.argtypes
+        L.icer_interleave_uint8.argtypes = [u8, C.c_size_t, C.c_size_t]
+        L.icer_interleave_uint8.restype = None
 
     # ---- whole image -------------------------------------------------------------------------------
-    def compress(self, planes_in, stages, filt, segments, quota):
-        """planes_in: list of 1 or 3 uint16 arrays [h, w].  Returns dict(rc, size_used, stream, prio, coefs)."""
-        imgs = [np.ascontiguousarray(p, dtype=np.uint16).copy() for p in planes_in]
+    def compress(self, planes_in, stages, filt, segments, quota, dtype=np.uint16):
+        """planes_in: list of 1 or 3 arrays [h, w] (dtype uint16, or uint8 for the native uint8 codec).
+        Returns dict(rc, size_used, stream, prio, coefs)."""
+        imgs = [np.ascontiguousarray(p, dtype=dtype).copy() for p in planes_in]
         h, w = imgs[0].shape
         buf = np.zeros(2 * quota + 64, dtype=np.uint8)
         ob = _OutBuf()
         rc0 = self.lib.icer_init_output_struct(C.byref(ob), _u8p(buf), 2 * quota, quota)
         assert rc0 == 0
-        if len(imgs) == 1:
+        if dtype == np.uint8:
+            if len(imgs) == 1:
+                rc = self.lib.icer_compress_image_uint8(_u8p(imgs[0]), w, h, stages, filt, segments, C.byref(ob))
+            else:
+                rc = self.lib.icer_compress_image_yuv_uint8(_u8p(imgs[0]), _u8p(imgs[1]), _u8p(imgs[2]), w, h, stages, filt,
+                                                            segments, C.byref(ob))
+        elif len(imgs) == 1:
             rc = self.lib.icer_compress_image_uint16(_u16p(imgs[0]), w, h, stages, filt, segments, C.byref(ob))
         else:
             rc = self.lib.icer_compress_image_yuv_uint16(_u16p(imgs[0]), _u16p(imgs[1]), _u16p(imgs[2]), w, h, stages,
@@ -79,12 +98,20 @@ class Ref:
         n = ob.size_used
         return dict(rc=rc, size_used=n, stream=bytes(buf[quota:quota + n]), prio=bytes(buf[:n]), coefs=imgs)
 
-    def decompress(self, stream, chan, bufsize_px, stages, filt, segments):
+    def decompress(self, stream, chan, bufsize_px, stages, filt, segments, dtype=np.uint16):
         data = np.frombuffer(bytes(stream) + b"\0" * 64, dtype=np.uint8).copy()  # slack: the scanner over-reads
-        imgs = [np.zeros(max(bufsize_px, 1), dtype=np.uint16) for _ in range(chan)]
+        imgs = [np.zeros(max(bufsize_px, 1), dtype=dtype) for _ in range(chan)]
         w = C.c_size_t(0)
         h = C.c_size_t(0)
-        if chan == 1:
+        if dtype == np.uint8:
+            if chan == 1:
+                rc = self.lib.icer_decompress_image_uint8(_u8p(imgs[0]), C.byref(w), C.byref(h), bufsize_px, _u8p(data),
+                                                          len(stream), stages, filt, segments)
+            else:
+                rc = self.lib.icer_decompress_image_yuv_uint8(_u8p(imgs[0]), _u8p(imgs[1]), _u8p(imgs[2]), C.byref(w),
+                                                              C.byref(h), bufsize_px, _u8p(data), len(stream), stages, filt,
+                                                              segments)
+        elif chan == 1:
             rc = self.lib.icer_decompress_image_uint16(_u16p(imgs[0]), C.byref(w), C.byref(h), bufsize_px, _u8p(data),
                                                        len(stream), stages, filt, segments)
         else:
@@ -111,6 +138,25 @@ class Ref:
         f = self.lib.icer_inverse_wavelet_transform_1d_uint16 if inverse else self.lib.icer_wavelet_transform_1d_uint16
         rc = f(_u16p(a), a.size, 1, filt)
         return rc, a
+
+    def dwt8(self, img, stages, filt, inverse=False):
+        """The native uint8 transform (icer_wavelet_transform_stages_uint8 / inverse)."""
+        a = np.ascontiguousarray(img, dtype=np.uint8).copy()
+        f = self.lib.icer_inverse_wavelet_transform_stages_uint8 if inverse else self.lib.icer_wavelet_transform_stages_uint8
+        rc = f(_u8p(a), a.shape[1], a.shape[0], stages, filt)
+        return rc, a
+
+    def interleave8_map(self, n):
+        """dst[i] = where icer_interleave_uint8 puts element i of a length-n array (two passes: low / high index byte)."""
+        idx = np.arange(n)
+        lo = (idx & 0xFF).astype(np.uint8)
+        hi = (idx >> 8).astype(np.uint8)
+        self.lib.icer_interleave_uint8(_u8p(lo), n, 1)
+        self.lib.icer_interleave_uint8(_u8p(hi), n, 1)
+        at = lo.astype(np.int64) | (hi.astype(np.int64) << 8)      # at[pos] = original index now at pos
+        dst = np.zeros(n, dtype=np.int64)
+        dst[at] = idx
+        return dst
 
     def bin_of(self, zero, total):
         return self.lib.icer_compute_bin(zero, total)

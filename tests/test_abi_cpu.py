@@ -100,3 +100,18 @@ def test_host_scanner_matches_reference(lib, ref9):
             rc = L.icer_get_image_dimensions(p, len(v), C.byref(w), C.byref(h))
             res.append((offs, rc, (w.value, h.value) if rc == 0 else None))
         assert res[0] == res[1]
+
+
+def test_u8_interleave_map_matches_reference(ref9):
+    """The native uint8 decoder has to reproduce where lib_icer's icer_interleave_uint8 really puts every element (not the
+    perfect shuffle for odd lengths).  The library derives that placement on the host; check it against the
+    compiled reference for every length the transform can meet in small images and a sample of large ones."""
+    import numpy as np
+    from icer_compression_b200 import u8_interleave_map
+    for n in list(range(2, 1200)) + [2047, 2048, 2049, 4095, 4097, 8191]:
+        a = ref9.interleave8_map(n)
+        b = u8_interleave_map(n).astype(np.int64)
+        assert (a == b).all(), n
+        if n % 2 == 0:
+            half = n // 2
+            assert (b[:half] == 2 * np.arange(half)).all() and (b[half:] == 2 * np.arange(half) + 1).all()
