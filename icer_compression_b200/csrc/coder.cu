@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_T_to_frames(const uint16_t *__restrict_
 struct EncSmem {
     SmemTables T;
     uint32_t cnt[17][NT];      // zero << 16 | total, per context
-    uint32_t bseq[17][NT];     // sequence number of the codeword each bin is building
+    uint16_t bseq[17][NT];     // sequence number (low 16 bits; the window spans 2048) of the codeword each bin is building
     uint32_t bst[17][NT];      // Golomb: zeros counted; custom: input word (first bit = bit 0) | bits gathered << 16
 };
 
@@ -242,15 +242,15 @@ struct Enc {
         const uint32_t seq = S.bseq[bin][t];
         open_mask &= ~(1u << bin);
         ring[seq & (ICER_RING - 1)] = (uint16_t) ((nb << 11) | code);
-        if (seq != head) return;
-        uint32_t limit = tail;
+        if (seq != (head & 0xFFFFu)) return;
         const uint32_t h1 = head + 1;
+        uint32_t dist = tail - h1;                       // every other open codeword lies in [head + 1, tail)
         for (uint32_t m = open_mask; m; m &= m - 1) {
             const int b = __ffs(m) - 1;
-            const uint32_t sq = S.bseq[b][t];
-            if ((int32_t) (sq - h1) < (int32_t) (limit - h1)) { limit = sq; oldest = b; }
+            const uint32_t d = ((uint32_t) S.bseq[b][t] - h1) & 0xFFFFu;
+            if (d < dist) { dist = d; oldest = b; }
         }
-        head = limit;
+        head = h1 + dist;
     }
 
     // pack one ready codeword into the payload, LSB first (icer_encoding.c:114-139).  Called from ONE convergent site
@@ -292,7 +292,7 @@ struct Enc {
         if (open_mask & (1u << bin)) return;
         while (tail - emit_pos >= ICER_RING) pump();       // physical ring space (emission may lag behind `head`)
         if (open_mask == 0) oldest = bin;
-        S.bseq[bin][t] = tail++;
+        S.bseq[bin][t] = (uint16_t) tail++;
         S.bst[bin][t] = 0;
         open_mask |= 1u << bin;
     }
@@ -311,7 +311,7 @@ struct Enc {
 };
 
 // One warp per (frame group, stream); lane = frame of the group.
-__global__ void __launch_bounds__(NT, 4) k_encode(EncodeArgs a) {
+__global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
     const int t = threadIdx.x;
@@ -515,7 +515,7 @@ struct DecShared {
     uint32_t next_task;
     volatile uint32_t k_end;             // first chain ordinal that does not exist (work exhausted)
 };
-// followed in dynamic shared memory by: cnt[17][DEC_BT], depth[17][DEC_BT], stlow[17][DEC_BT]
+// followed in dynamic shared memory by: cnt[17][DEC_BT] u32, stlow[17][DEC_BT] u32, depth[17][DEC_BT] i16
 
 struct Dec {
     const SmemTables &T;
@@ -607,14 +607,14 @@ struct Dec {
     }
 };
 
-__global__ void __launch_bounds__(DEC_BT, 3) k_decode(DecodeArgs a) {
+__global__ void __launch_bounds__(DEC_BT, 4) k_decode(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecShared &S = *reinterpret_cast<DecShared *>(smem_raw);
     const int t = threadIdx.x;
     constexpr int BT = DEC_BT;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(DecShared) + 15) & ~(size_t) 15));
-    int32_t *depthA = reinterpret_cast<int32_t *>(cnt + 17 * BT);
-    uint32_t *stlow = reinterpret_cast<uint32_t *>(depthA + 17 * BT);
+    uint32_t *stlow = cnt + 17 * BT;
+    int16_t *depthA = reinterpret_cast<int16_t *>(stlow + 17 * BT);     // pending bits of a bin's stack: <= the largest Golomb m (512)
     {   // tables + pool state
         for (int i = t; i < 8 * 32; i += BT) (&S.T.v2v[0][0])[i] = (&c_tab.dlut[0][0])[i];
         for (int i = t; i < 45; i += BT) S.T.ctx_hv[i] = c_tab.ctx_hv[i];
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(DEC_BT, 3) k_decode(DecodeArgs a) {
                             if (zeros > 0) {
                                 const uint32_t n2 = zeros_in_same_bin(S.T, bin, z, tot);
                                 const uint32_t n3 = 500u - tot;
-                                depthA[bin * BT + t] = depth;
+                                depthA[bin * BT + t] = (int16_t) depth;
                                 stlow[bin * BT + t] = stamp | (low << 24);
                                 fz_left = min(zeros, min(n2, n3)) - 1;
                                 fz_run = 1;
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(DEC_BT, 3) k_decode(DecodeArgs a) {
                         const int top = depth - 1;
                         uint32_t b = 0;
                         if (top >= 0 && top < 8) { b = (low >> top) & 1u; low &= ~(1u << top); }
-                        depthA[bin * BT + t] = depth - 1;
+                        depthA[bin * BT + t] = (int16_t) (depth - 1);
                         stlow[bin * BT + t] = stamp | (low << 24);
                         const uint32_t bit = inv ? (b ^ 1u) : b;
                         if (ctx >= 0) {
@@ -1099,7 +1099,7 @@ int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls) {
     int rc = upload_tables();
     if (rc) return rc;
     if (a.planes < 1 || a.planes > 15) return ICER_BITPLANE_OUT_OF_RANGE;
-    const size_t smem = ((sizeof(DecShared) + 15) & ~(size_t) 15) + (size_t) 3 * 17 * DEC_BT * 4;
+    const size_t smem = ((sizeof(DecShared) + 15) & ~(size_t) 15) + (size_t) 17 * DEC_BT * 10;
     CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int dev = 0, sms = 148, bps = 1;
     cudaGetDevice(&dev);
