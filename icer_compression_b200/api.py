@@ -23,7 +23,8 @@ class IcerError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libicer_b200.so")
+    # ICER_B200_LIB: development hook to benchmark an alternative build of the same library (profiles/variants.sh)
+    return os.environ.get("ICER_B200_LIB") or os.path.join(_HERE, "lib", "libicer_b200.so")
 
 
 class _OutBuf(C.Structure):  # icer_output_data_buf_typedef (include/icer.h)

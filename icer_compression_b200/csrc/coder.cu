@@ -82,6 +82,7 @@ int upload_tables() {
 
 // tables every lane needs with divergent indices: staged in shared memory once per block
 struct SmemTables {
+    uint2 cutp[17];            // per bin: (cut-off below it, cut-off above it) with sentinels 0 / 65537 -- one 64-bit load validates a cached bin
     uint32_t cutoff[16];
     uint16_t v2v[8][32];
     uint16_t gol_m[17], gol_l[17], gol_i[17];
@@ -97,6 +98,7 @@ __device__ __forceinline__ void load_tables(SmemTables &T, bool decoder) {
     for (int i = t; i < 25; i += NT) { T.ctx_hh[i] = c_tab.ctx_hh[i]; T.ctx_sign[i] = c_tab.ctx_sign[i]; T.sign_pred[i] = c_tab.sign_pred[i]; }
     for (int i = t; i < 17; i += NT) { T.gol_m[i] = c_tab.gol_m[i]; T.gol_l[i] = c_tab.gol_l[i]; T.gol_i[i] = c_tab.gol_i[i]; }
     for (int i = t; i < 16; i += NT) T.cutoff[i] = c_tab.cutoff[i];
+    for (int i = t; i < 17; i += NT) T.cutp[i] = make_uint2(i ? c_tab.cutoff[i - 1] : 0u, i < 16 ? c_tab.cutoff[i] : 65537u);
 }
 
 // probability bin: number of cut-offs c with zz * 65536 >= tot * c (icer_util.c:48-56); cut-offs ascend
@@ -110,6 +112,20 @@ __device__ __forceinline__ int bin_of(const SmemTables &T, uint32_t zz, uint32_t
     if (bin == 15 && lhs >= tot * T.cutoff[15]) bin = 16;
     return bin;
 }
+
+// The bin of a context moves slowly, so each context remembers its last bin (bits 27..31 of its count word); the guess is
+// validated with two products (it holds iff cut[guess-1] * tot <= zz * 65536 < cut[guess] * tot) and the 5-step dependent
+// search only runs when the context has crossed into another bin.
+__device__ __forceinline__ int bin_cached(const SmemTables &T, uint32_t zz, uint32_t tot, int guess) {
+    const uint32_t lhs = zz << 16;
+    const uint2 c = T.cutp[guess];
+    if (lhs >= tot * c.x && lhs < tot * c.y) return guess;
+    return bin_of(T, zz, tot);
+}
+#define CNT_Z(zt) (((zt) >> 16) & 0x7FFu)
+#define CNT_TOT(zt) ((zt) & 0xFFFFu)
+#define CNT_BIN(zt) ((int) ((zt) >> 27))
+#define CNT_PACK(bin, z, tot) (((uint32_t) (bin) << 27) | ((z) << 16) | (tot))
 
 // number of consecutive all-zero decisions, starting at counts (z, tot), that stay in Golomb bin `bin`
 __device__ __forceinline__ uint32_t zeros_in_same_bin(const SmemTables &T, int bin, uint32_t z, uint32_t tot) {
@@ -383,9 +399,9 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
                         // apply `fz_run` (context 0, bit 0) decisions at once
                         bin = fz_bin;
                         const uint32_t zt = S.cnt[0][t];
-                        uint32_t z = (zt >> 16) + fz_run, tot = (zt & 0xFFFF) + fz_run;
+                        uint32_t z = CNT_Z(zt) + fz_run, tot = CNT_TOT(zt) + fz_run;
                         if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
-                        S.cnt[0][t] = (z << 16) | tot;
+                        S.cnt[0][t] = CNT_PACK(bin, z, tot);
                         const uint32_t k = S.bst[bin][t] + fz_run;
                         if (k >= S.T.gol_m[bin]) { done = true; code = 1; nb = 1; }
                         else S.bst[bin][t] = k;
@@ -409,11 +425,12 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
                                 bit = (S.T.sign_pred[si] ^ (v >> 15)) & 1;
                             }
                             const uint32_t zt = S.cnt[ctx][t];
-                            uint32_t z = zt >> 16, tot = zt & 0xFFFF;
+                            uint32_t z = CNT_Z(zt), tot = CNT_TOT(zt);
                             uint32_t zz = z;
                             const bool inv = zz < (tot >> 1);
                             if (inv) zz = tot - zz;
-                            bin = bin_of(S.T, zz, tot);
+                            bin = bin_cached(S.T, zz, tot, CNT_BIN(zt));
+                            const int cbin = bin;
                             if (cd.window_full_for(bin)) {
                                 // window full: force-complete the oldest codeword first, then redo this decision
                                 bin = cd.oldest; code = cd.forced_word(bin, nb); done = true; todo |= 1u << st;
@@ -433,7 +450,7 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
                             tot++;
                             z += bit ^ 1u;
                             if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }   // icer_context_modeller.c:396-402
-                            S.cnt[ctx][t] = (z << 16) | tot;
+                            S.cnt[ctx][t] = CNT_PACK(cbin, z, tot);
                             bit ^= inv ? 1u : 0u;
                         }
                         cd.open_bin(bin);
@@ -494,9 +511,20 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
 // smaller number has always been taken by some warp already, so waiting on it cannot deadlock; there is no block
 // barrier anywhere, so the quick (quiet) upper planes run ahead into the next chains while the dense lower planes are
 // still being decoded.  Chains in flight occupy one of DEC_SLOTS slots of progress / flag state in shared memory.
-constexpr int DEC_WARPS = 8;
+// Pool size (measured on config 2, k_decode ms): 8 warps x 4 blocks/SM 42.1, 16 x 2 38.0, 24 x 1 40.7, 32 x 1 (12 slots) 36.1 --
+// one SM-wide pool balances the very unequal planes of a chain best (profiles/README.md).
+#ifndef ICER_DEC_WARPS
+#define ICER_DEC_WARPS 32
+#endif
+#ifndef ICER_DEC_SLOTS
+#define ICER_DEC_SLOTS 12
+#endif
+#ifndef ICER_DEC_MINBLOCKS
+#define ICER_DEC_MINBLOCKS 1
+#endif
+constexpr int DEC_WARPS = ICER_DEC_WARPS;
 constexpr int DEC_BT = DEC_WARPS * 32;
-constexpr int DEC_SLOTS = 4;
+constexpr int DEC_SLOTS = ICER_DEC_SLOTS;
 
 struct DecSlot {
     volatile uint32_t chain;             // chain ordinal (within this block) that owns the slot; ~0 = never used
@@ -607,7 +635,7 @@ struct Dec {
     }
 };
 
-__global__ void __launch_bounds__(DEC_BT, 4) k_decode(DecodeArgs a) {
+__global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecShared &S = *reinterpret_cast<DecShared *>(smem_raw);
     const int t = threadIdx.x;
@@ -621,6 +649,7 @@ __global__ void __launch_bounds__(DEC_BT, 4) k_decode(DecodeArgs a) {
         for (int i = t; i < 25; i += BT) { S.T.ctx_hh[i] = c_tab.ctx_hh[i]; S.T.ctx_sign[i] = c_tab.ctx_sign[i]; S.T.sign_pred[i] = c_tab.sign_pred[i]; }
         for (int i = t; i < 17; i += BT) { S.T.gol_m[i] = c_tab.gol_m[i]; S.T.gol_l[i] = c_tab.gol_l[i]; S.T.gol_i[i] = c_tab.gol_i[i]; }
         for (int i = t; i < 16; i += BT) S.T.cutoff[i] = c_tab.cutoff[i];
+        for (int i = t; i < 17; i += BT) S.T.cutp[i] = make_uint2(i ? c_tab.cutoff[i - 1] : 0u, i < 16 ? c_tab.cutoff[i] : 65537u);
         if (t < DEC_SLOTS) { S.slot[t].chain = 0xFFFFFFFFu; S.slot[t].freed = 1; S.slot[t].done = 0; S.slot[t].anyerr = 0; }
         if (t == 0) { S.next_task = 0; S.k_end = 0xFFFFFFFFu; }
     }
@@ -751,9 +780,9 @@ __global__ void __launch_bounds__(DEC_BT, 4) k_decode(DecodeArgs a) {
                         if (st == 0) {
                             const int bin = fz_bin;
                             const uint32_t zt = cnt[t];
-                            uint32_t z = (zt >> 16) + fz_run, tot = (zt & 0xFFFF) + fz_run;
+                            uint32_t z = CNT_Z(zt) + fz_run, tot = CNT_TOT(zt) + fz_run;
                             if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
-                            cnt[t] = (z << 16) | tot;
+                            cnt[t] = CNT_PACK(bin, z, tot);
                             depthA[bin * BT + t] -= (int) fz_run;
                             fz_run = 0; fz_left = 0;
                             continue;
@@ -767,11 +796,11 @@ __global__ void __launch_bounds__(DEC_BT, 4) k_decode(DecodeArgs a) {
                             if (st == 1) ctx = mag_context(S.T, cat, lsb, sb, a0, a1, a2, b0, b2, c0, c1, c2);
                             else { si = sign_index(lsb, sb, a1, b0, b2, c1); ctx = S.T.ctx_sign[si]; }
                             const uint32_t zt = cnt[ctx * BT + t];
-                            z = zt >> 16; tot = zt & 0xFFFF;
+                            z = CNT_Z(zt); tot = CNT_TOT(zt);
                             uint32_t zz = z;
                             inv = zz < (tot >> 1);
                             if (inv) zz = tot - zz;
-                            bin = bin_of(S.T, zz, tot);
+                            bin = bin_cached(S.T, zz, tot, CNT_BIN(zt));
                         }
                         // next decoded bit of `bin` (icer_decoding.c:127, :186-192)
                         int depth = depthA[bin * BT + t];
@@ -808,7 +837,7 @@ __global__ void __launch_bounds__(DEC_BT, 4) k_decode(DecodeArgs a) {
                             tot++;
                             z += bit ^ 1u;
                             if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
-                            cnt[ctx * BT + t] = (z << 16) | tot;
+                            cnt[ctx * BT + t] = CNT_PACK(bin, z, tot);
                         }
                         if (st == 1) {
                             if (bit) { v |= 1u << lsb; changed = true; if (cat == 0) todo |= 4u; }
