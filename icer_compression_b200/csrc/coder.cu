@@ -541,6 +541,7 @@ struct DecShared {
     SmemTables T;
     DecSlot slot[DEC_SLOTS];
     uint32_t next_task;
+    volatile uint32_t fetch_turn;        // chain ordinal whose first task may fetch its global work id next
     volatile uint32_t k_end;             // first chain ordinal that does not exist (work exhausted)
 };
 // followed in dynamic shared memory by: cnt[17][DEC_BT] u32, stlow[17][DEC_BT] u32, depth[17][DEC_BT] i16
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
         for (int i = t; i < 16; i += BT) S.T.cutoff[i] = c_tab.cutoff[i];
         for (int i = t; i < 17; i += BT) S.T.cutp[i] = make_uint2(i ? c_tab.cutoff[i - 1] : 0u, i < 16 ? c_tab.cutoff[i] : 65537u);
         if (t < DEC_SLOTS) { S.slot[t].chain = 0xFFFFFFFFu; S.slot[t].freed = 1; S.slot[t].done = 0; S.slot[t].anyerr = 0; }
-        if (t == 0) { S.next_task = 0; S.k_end = 0xFFFFFFFFu; }
+        if (t == 0) { S.next_task = 0; S.fetch_turn = 0; S.k_end = 0xFFFFFFFFu; }
     }
     __syncthreads();
     const int lane = t & 31;
@@ -674,21 +675,31 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
         DecSlot &sl = S.slot[k % DEC_SLOTS];
         // ---- claim / find the slot of chain k ------------------------------------------------------------
         if (j == 0) {
-            // the first task of a chain recycles the slot of chain k - DEC_SLOTS and fetches the global work item
-            bool gone = false;
+            // The first task of a chain fetches the global work item and recycles the slot of chain k - DEC_SLOTS.
+            // The fetch happens in CHAIN ORDER (ticket S.fetch_turn): work ids then grow with k inside a block, so "chain k
+            // got no work" implies the same for every later chain -- the invariant k_end and the early exits rely on.
+            // (Fetching after the slot wait let a later chain overtake an earlier one; an earlier chain that then drew
+            // the end-of-work id made the warps of the later, valid chain give up: a stall seen with the 32-warp pool.)
+            unsigned long long wid = 0;
+            if (lane == 0) {
+                while (S.fetch_turn != k) __nanosleep(40);
+                wid = atomicAdd(a.work_counter, 1ull);
+                if (wid >= total && S.k_end > k) S.k_end = k;
+                __threadfence_block();
+                S.fetch_turn = k + 1;
+            }
+            wid = __shfl_sync(0xffffffffu, wid, 0);
+            if (wid >= total) break;
             if (lane == 0 && k >= (uint32_t) DEC_SLOTS)
-                while (!(sl.chain == k - DEC_SLOTS && sl.freed)) { if (S.k_end <= k) { gone = true; break; } __nanosleep(200); }
-            gone = __shfl_sync(0xffffffffu, gone ? 1 : 0, 0) != 0;
-            if (gone) break;
+                while (!(sl.chain == k - DEC_SLOTS && sl.freed)) __nanosleep(200);     // that chain is live: it will finish
+            __syncwarp();
             __threadfence_block();
             for (int q = 0; q < 15; q++) { sl.deadf[q][lane] = 0; sl.errf[q][lane] = 0; sl.posd[q][lane] = 0; }
             __threadfence_block();
             __syncwarp();
             if (lane == 0) {
-                const unsigned long long wid = atomicAdd(a.work_counter, 1ull);
                 for (int q = 0; q < 15; q++) sl.prog[q] = 0;
                 sl.done = 0; sl.anyerr = 0; sl.freed = 0; sl.wid = wid;
-                if (wid >= total && S.k_end > k) S.k_end = k;
                 __threadfence_block();
                 sl.chain = k;
             }

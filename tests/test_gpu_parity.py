@@ -414,3 +414,22 @@ def test_host_pipeline_chunks(oracle9):
         o = oracle9.decompress(enc["streams"][i], 1, 96 * 64, 3, 0, 5)
         assert int(dec["rc"][i]) == 0 and (dec["frames"][i, 0] == o["images"][0].ravel()).all(), i
     c.close()
+
+
+@pytest.mark.timeout(240)
+def test_decoder_pool_many_launches(ctx9, oracle9):
+    """Regression for a stall of the decoder's task pool: chains used to fetch their global work id after waiting for a
+    slot, so a later chain could overtake an earlier one and the end-of-work marker landed on the earlier chain while the
+    later one was still valid.  Many launches with many short chains per block (small frames, 32 segments) hit the window."""
+    import torch
+    w = h = 96
+    n = 96
+    frames = np.stack([oracle9.synth(128, 128, f, 77, 0)[:h, :w] for f in range(n)])[:, None]
+    enc = ctx9.compress_batch(frames, 3, 0, 32, w * h * 2)
+    assert (enc["rc"] == 0).all()
+    ref = ctx9.decompress_batch(enc["streams"], 1, w, h, 3, 0, 32)["frames"]
+    assert (ref.reshape(n, 1, h, w) == frames).all()
+    for _ in range(60):
+        out = ctx9.decompress_batch(enc["streams"], 1, w, h, 3, 0, 32)
+        assert (out["rc"] == 0).all()
+        assert (out["frames"] == ref).all()
