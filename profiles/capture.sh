@@ -5,10 +5,10 @@
 TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > $OUT/${TAG}_launches.log 2>&1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --watchdog 150 > $OUT/${TAG}_launches.log 2>&1
 for k in k_encode k_decode k_fwd_stage_tma; do
-    ncu --set full --clock-control none --import-source on -k regex:^$k -c 1 -f -o $OUT/${TAG}_$k \
-        python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e > $OUT/${TAG}_$k.log 2>&1
+    timeout 240 ncu --set full --clock-control none --import-source on -k regex:^$k -c 1 -f -o $OUT/${TAG}_$k \
+        python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e --watchdog 200 > $OUT/${TAG}_$k.log 2>&1
     ncu -i $OUT/${TAG}_$k.ncu-rep --page raw --csv > $OUT/${TAG}_${k}_raw.csv 2>/dev/null
 done

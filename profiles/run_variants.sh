@@ -1,6 +1,6 @@
-for v in w32b1s12 w32b1s8 w16b2s7 w16b2s5 w24b1s10; do
+for v in main base; do
   if [ $v = main ]; then unset ICER_B200_LIB; else export ICER_B200_LIB=$PWD/icer_compression_b200/lib/variants/libicer_b200_$v.so; fi
-  timeout 200 python bench.py --no-cpu --no-e2e --steps 4 --warmup 3 > gpurun_out/var_$v.json 2>gpurun_out/var_$v.err
+  timeout 100 python bench.py --no-cpu --no-e2e --steps 5 --warmup 3 --watchdog 80 > gpurun_out/var_$v.json 2>gpurun_out/var_$v.err
   python - <<PY
 import json
 try:
