@@ -172,7 +172,11 @@ static size_t dim_high(size_t d, int s) { return dim_low(d, s - 1) / 2; }       
  * temporary, then the lifting update on the highs.  r[k] = l[k-1]-l[k] is truncated to int16 (:206-208);
  * stores wrap to int16 and raise the overflow flag (:412-415,:460-461).
  */
-int orc_dwt_forward_1d_u16(uint16_t *data, size_t n, size_t stride, int filt) {
+/* b8 != 0: the native uint8 twin (src/icer_wavelet.c:216-305): identical steps, but stores wrap to int8 and the overflow
+ * flag is raised at the int8 range; the int8 samples live sign-extended in the int16 line */
+#define WRAP(v) (b8 ? (int16_t) (int8_t) (v) : (int16_t) (v))
+#define OVF(v) (b8 ? ((v) > 127 || (v) < -128) : ((v) > 32767 || (v) < -32768))
+static int fwd_1d(uint16_t *data, size_t n, size_t stride, int filt, int b8) {
     int16_t *line = (int16_t *) data;
     size_t nl = (n + 1) / 2, nh = n / 2;
     int odd = (int) (n & 1), ovf = 0;
@@ -180,9 +184,9 @@ int orc_dwt_forward_1d_u16(uint16_t *data, size_t n, size_t stride, int filt) {
     for (size_t k = 0; k < nh; k++) {
         int32_t a = AT(2 * k), b = AT(2 * k + 1);
         int32_t lo = fdiv(a + b, 2), hi = a - b;
-        if (lo > 32767 || lo < -32768 || hi > 32767 || hi < -32768) ovf = 1;
-        tmp[k] = (int16_t) lo;
-        tmp[nl + k] = (int16_t) hi;
+        if (OVF(lo) || OVF(hi)) ovf = 1;
+        tmp[k] = WRAP(lo);
+        tmp[nl + k] = WRAP(hi);
     }
     if (odd) tmp[nl - 1] = AT(n - 1);
     for (size_t k = 0; k < n; k++) AT(k) = tmp[k];
@@ -210,15 +214,67 @@ int orc_dwt_forward_1d_u16(uint16_t *data, size_t n, size_t stride, int filt) {
             sub = fdiv(f[0] * rm1 + f[1] * R(k) + f[2] * R(k + 1) - f[3] * dn + 8, 16);
         }
         int32_t h = (int32_t) AT(nl + k) - sub;
-        if (h > 32767 || h < -32768) ovf = 1;
-        AT(nl + k) = (int16_t) h;
+        if (OVF(h)) ovf = 1;
+        AT(nl + k) = WRAP(h);
     }
     return ovf ? ORC_INTEGER_OVERFLOW : ORC_OK;
 }
+int orc_dwt_forward_1d_u16(uint16_t *data, size_t n, size_t stride, int filt) { return fwd_1d(data, n, stride, filt, 0); }
+
+/*
+ * Where icer_interleave_uint8 (src/icer_wavelet.c:570-628) puts element i of a length-n lows|highs array.  Even n: the
+ * perfect in-shuffle.  Odd n: `halfleft = left / 2 - (is_odd ? 0 : 1)` (:599) is one too large and the three reversals
+ * (:601-605) therefore rotate the wrong span, so the result is a different (fixed) permutation -- SURVEY A.5.  The
+ * reference's uint8 decoder applies it after every inverse 1-D pass, so the oracle does too.  Derived by running the
+ * function's index operations on an identity array: odd-tail rotation (:586-592), then per slice of length 3^k + 1
+ * (k from icer_find_k's binary search :823-847 -- which returns the previous probe, not the match, on equality) the
+ * three reversals and the cycle-leader walk (:607-624).
+ */
+static void rev_span(uint32_t *a, size_t s, size_t e) { while (s < e) { uint32_t t = a[s]; a[s] = a[e]; a[e] = t; s++; e--; } }
+static void interleave8_dst(size_t len, uint32_t *dst) {
+    uint32_t *a = (uint32_t *) malloc(len * sizeof(uint32_t));
+    for (size_t i = 0; i < len; i++) a[i] = (uint32_t) i;
+    size_t slice[12], p3 = 1;
+    for (int k = 0; k < 12; k++) { slice[k] = p3 + 1; p3 *= 3; }
+    int odd = (int) (len & 1);
+    size_t n = odd ? len - 1 : len;
+    if (odd) {
+        uint32_t keep = a[n / 2];
+        for (size_t i = n / 2; i < n; i++) a[i] = a[i + 1];
+        a[len - 1] = keep;
+    }
+    size_t done = 0;
+    while (done < n) {
+        size_t want = n - done;
+        int lo = 0, hi = 11, k = 0;
+        while (lo < hi) {
+            int mid = (lo + hi) / 2;
+            if (want > slice[mid]) { lo = mid + 1; k = mid; }
+            else if (want < slice[mid]) hi = mid - 1;
+            else break;
+        }
+        size_t seg = slice[k], half = seg / 2, halfleft = want / 2 - (odd ? 0 : 1);
+        rev_span(a, done + half, done + halfleft + half);
+        rev_span(a, done + half, done + seg - 1);
+        rev_span(a, done + seg, done + halfleft + half);
+        for (size_t i = 1; i < seg; i *= 3) {
+            size_t j = i;
+            uint32_t carry = a[j + done];
+            do {
+                j = j < half ? 2 * j : (j - half) * 2 + 1;
+                uint32_t t = a[j + done]; a[j + done] = carry; carry = t;
+            } while (j != i);
+        }
+        done += seg;
+    }
+    for (size_t pos = 0; pos < len; pos++) dst[a[pos]] = (uint32_t) pos;
+    free(a);
+}
+void orc_interleave8_map(size_t len, uint32_t *dst) { interleave8_dst(len, dst); }
 
 /* src/icer_wavelet.c:467-550 : highs restored from the last one down (each uses the already restored
  * d[k+1] when beta != 0), then pairs rebuilt, then plain interleave (icer_interleave_uint16 :705-763) */
-int orc_dwt_inverse_1d_u16(uint16_t *data, size_t n, size_t stride, int filt) {
+static int inv_1d(uint16_t *data, size_t n, size_t stride, int filt, int b8) {
     int16_t *line = (int16_t *) data;
     size_t nl = (n + 1) / 2, nh = n / 2;
     int odd = (int) (n & 1), ovf = 0;
@@ -240,48 +296,76 @@ int orc_dwt_inverse_1d_u16(uint16_t *data, size_t n, size_t stride, int filt) {
             add = fdiv(f[0] * rm1 + f[1] * R(k) + f[2] * R(k + 1) - f[3] * dn + 8, 16);
         }
         int32_t d = (int32_t) AT(nl + k) + add;
-        if (d > 32767 || d < -32768) ovf = 1;
-        AT(nl + k) = (int16_t) d;
+        if (OVF(d)) ovf = 1;
+        AT(nl + k) = WRAP(d);
     }
 #undef R
     int16_t *tmp = (int16_t *) malloc(n * sizeof(int16_t));
+    /* uint16: plain interleave.  uint8 with odd n: the reference's icer_interleave_uint8 placement (see above) */
+    uint32_t *dst = NULL;
+    if (b8 && odd) { dst = (uint32_t *) malloc(n * sizeof(uint32_t)); interleave8_dst(n, dst); }
     for (size_t k = 0; k < nh; k++) {
         int32_t lo = AT(k), hi = AT(nl + k);
         int32_t t = lo + fdiv(hi + 1, 2);
-        if (t > 32767 || t < -32768 || t - hi > 32767 || t - hi < -32768) ovf = 1;
-        tmp[2 * k] = (int16_t) t;
-        tmp[2 * k + 1] = (int16_t) (t - hi);
+        if (OVF(t) || OVF(t - hi)) ovf = 1;
+        tmp[dst ? dst[k] : 2 * k] = WRAP(t);
+        tmp[dst ? dst[nl + k] : 2 * k + 1] = WRAP(t - hi);
     }
-    if (odd) tmp[n - 1] = AT(nl - 1); /* low + floor(1/2) = low (:537-545) */
+    if (odd) tmp[dst ? dst[nl - 1] : n - 1] = AT(nl - 1); /* low + floor(1/2) = low (:537-545) */
     for (size_t k = 0; k < n; k++) AT(k) = tmp[k];
     free(tmp);
+    free(dst);
     return ovf ? ORC_INTEGER_OVERFLOW : ORC_OK;
 }
+int orc_dwt_inverse_1d_u16(uint16_t *data, size_t n, size_t stride, int filt) { return inv_1d(data, n, stride, filt, 0); }
 #undef AT
 
 /* src/icer_wavelet.c:57-77 + :155-171 : rows then columns of the shrinking LL region */
-int orc_dwt_forward_u16(uint16_t *img, size_t w, size_t h, int stages, int filt) {
+static int dwt_forward(uint16_t *img, size_t w, size_t h, int stages, int filt, int b8) {
     if (dim_low(w, stages) < 3 || dim_low(h, stages) < 3) return ORC_TOO_MANY_STAGES;
     int ovf = 0;
     size_t lw = w, lh = h;
     for (int s = 0; s < stages; s++) {
-        for (size_t r = 0; r < lh; r++) ovf |= orc_dwt_forward_1d_u16(img + r * w, lw, 1, filt) != 0;
-        for (size_t c = 0; c < lw; c++) ovf |= orc_dwt_forward_1d_u16(img + c, lh, w, filt) != 0;
+        for (size_t r = 0; r < lh; r++) ovf |= fwd_1d(img + r * w, lw, 1, filt, b8) != 0;
+        for (size_t c = 0; c < lw; c++) ovf |= fwd_1d(img + c, lh, w, filt, b8) != 0;
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
     }
     return ovf ? ORC_INTEGER_OVERFLOW : ORC_OK;
 }
+int orc_dwt_forward_u16(uint16_t *img, size_t w, size_t h, int stages, int filt) { return dwt_forward(img, w, h, stages, filt, 0); }
 
 /* src/icer_wavelet.c:81-103 + :175-191 : columns then rows, coarse to fine */
-int orc_dwt_inverse_u16(uint16_t *img, size_t w, size_t h, int stages, int filt) {
+static int dwt_inverse(uint16_t *img, size_t w, size_t h, int stages, int filt, int b8) {
     if (dim_low(w, stages) < 3 || dim_low(h, stages) < 3) return ORC_TOO_MANY_STAGES;
     int ovf = 0;
     for (int s = stages - 1; s >= 0; s--) {
         size_t lw = dim_low(w, s), lh = dim_low(h, s);
-        for (size_t c = 0; c < lw; c++) ovf |= orc_dwt_inverse_1d_u16(img + c, lh, w, filt) != 0;
-        for (size_t r = 0; r < lh; r++) ovf |= orc_dwt_inverse_1d_u16(img + r * w, lw, 1, filt) != 0;
+        for (size_t c = 0; c < lw; c++) ovf |= inv_1d(img + c, lh, w, filt, b8) != 0;
+        for (size_t r = 0; r < lh; r++) ovf |= inv_1d(img + r * w, lw, 1, filt, b8) != 0;
     }
     return ovf ? ORC_INTEGER_OVERFLOW : ORC_OK;
+}
+int orc_dwt_inverse_u16(uint16_t *img, size_t w, size_t h, int stages, int filt) { return dwt_inverse(img, w, h, stages, filt, 0); }
+
+/* the native uint8 transform (src/icer_wavelet.c:8-53): samples widened to sign-extended int16, transformed with int8 wrap */
+static uint16_t *widen8(const uint8_t *img, size_t count) {
+    uint16_t *t = (uint16_t *) malloc(count * sizeof(uint16_t));
+    for (size_t k = 0; k < count; k++) t[k] = (uint16_t) (int16_t) (int8_t) img[k];
+    return t;
+}
+int orc_dwt_forward_u8(uint8_t *img, size_t w, size_t h, int stages, int filt) {
+    uint16_t *t = widen8(img, w * h);
+    int rc = dwt_forward(t, w, h, stages, filt, 1);
+    if (rc != ORC_TOO_MANY_STAGES) for (size_t k = 0; k < w * h; k++) img[k] = (uint8_t) t[k];
+    free(t);
+    return rc;
+}
+int orc_dwt_inverse_u8(uint8_t *img, size_t w, size_t h, int stages, int filt) {
+    uint16_t *t = widen8(img, w * h);
+    int rc = dwt_inverse(t, w, h, stages, filt, 1);
+    if (rc != ORC_TOO_MANY_STAGES) for (size_t k = 0; k < w * h; k++) img[k] = (uint8_t) t[k];
+    free(t);
+    return rc;
 }
 
 /* src/icer_wavelet.c:871-877 */
@@ -726,30 +810,39 @@ static void subband_geom(size_t w, size_t h, int level, int sb, size_t *x0, size
 }
 
 /* icer_compress.c:279-426 (gray) and icer_color.c:343-530 (3 planar channels) */
-int orc_compress_u16(uint16_t *const img[3], int chan, size_t w, size_t h, int stages, int filt, int segments,
-                     const orc_limits *lim, uint8_t *out, size_t quota, size_t *size_used) {
+/* native8: the uint8 twins icer_compress.c:18-159 / icer_color.c:19-206 -- int8 samples sign-extended in the containers,
+ * LL mean over the uint8 reinterpretation, 7-bit magnitudes (the sign sits in bit 15 here, bit 7 in the reference's bytes),
+ * and for colour the rearrangement loops run ASCENDING (icer_color.c:184-203) */
+static int compress_core(uint16_t *const img[3], int chan, size_t w, size_t h, int stages, int filt, int segments,
+                         const orc_limits *lim, uint8_t *out, size_t quota, size_t *size_used, int native8) {
     orc_init();
     const int planes = lim->planes;
     *size_used = 0;
     if (stages > lim->max_stages) return ORC_TOO_MANY_STAGES;   /* reference: out-of-bounds table index */
     for (int ch = 0; ch < chan; ch++) {
-        int rc = orc_dwt_forward_u16(img[ch], w, h, stages, filt);
+        int rc = dwt_forward(img[ch], w, h, stages, filt, native8);
         if (rc != ORC_OK) return rc;
     }
     size_t llw = dim_low(w, stages), llh = dim_low(h, stages);
     uint16_t mean[3] = {0, 0, 0};
-    for (int ch = 0; ch < chan; ch++) {                    /* icer_compress.c:289-302 : unsigned sum */
+    for (int ch = 0; ch < chan; ch++) {                    /* icer_compress.c:289-302 (:28-40 uint8) : unsigned sum */
         uint64_t sum = 0;
         for (size_t r = 0; r < llh; r++)
-            for (size_t c = 0; c < llw; c++) sum += img[ch][r * w + c];
-        mean[ch] = (uint16_t) (sum / (llw * llh));
-        if (mean[ch] > 32767) return ORC_INTEGER_OVERFLOW;
+            for (size_t c = 0; c < llw; c++) sum += native8 ? (img[ch][r * w + c] & 0xFF) : img[ch][r * w + c];
+        mean[ch] = native8 ? (uint16_t) (uint8_t) (sum / (llw * llh)) : (uint16_t) (sum / (llw * llh));
+        if (mean[ch] > (native8 ? 127 : 32767)) return ORC_INTEGER_OVERFLOW;
     }
     for (int ch = 0; ch < chan; ch++) {
         for (size_t r = 0; r < llh; r++)
-            for (size_t c = 0; c < llw; c++)
-                img[ch][r * w + c] = (uint16_t) (int16_t) ((int16_t) img[ch][r * w + c] - (int16_t) mean[ch]);
-        for (size_t k = 0; k < w * h; k++) img[ch][k] = to_signmag(img[ch][k]);
+            for (size_t c = 0; c < llw; c++) {
+                int32_t d = (int32_t) (int16_t) img[ch][r * w + c] - (native8 ? (int32_t) (int8_t) mean[ch] : (int32_t) (int16_t) mean[ch]);
+                img[ch][r * w + c] = (uint16_t) (native8 ? (int16_t) (int8_t) d : (int16_t) d);
+            }
+        for (size_t k = 0; k < w * h; k++) {
+            if (!native8) { img[ch][k] = to_signmag(img[ch][k]); continue; }
+            int32_t v = (int16_t) img[ch][k];           /* icer_wavelet.c:851-857: -128 becomes "-0" */
+            img[ch][k] = v < 0 ? (uint16_t) (0x8000u | ((uint32_t) (-v) & 0x7Fu)) : (uint16_t) v;
+        }
     }
 
     /* packet list: icer_compress.c:315-363 / icer_color.c:398-456 */
@@ -829,13 +922,15 @@ int orc_compress_u16(uint16_t *const img[3], int chan, size_t w, size_t h, int s
             used += HDR + nbytes;
         }
     }
-    /* rearrangement: icer_compress.c:409-423 / icer_color.c:508-527 */
+    /* rearrangement: icer_compress.c:409-423 / icer_color.c:508-527; the uint8 colour encoder loops ascending (:184-203) */
     size_t off = 0;
+    const int asc = native8 && chan == 3;
     for (int sg = 0; sg <= 32; sg++)
-        for (int sb = 3; sb >= 0; sb--)
-            for (int lv = lim->max_stages; lv >= 0; lv--)
-                for (int lsb = planes - 1; lsb >= 0; lsb--)
+        for (int i1 = 0; i1 <= 3; i1++)
+            for (int i2 = 0; i2 <= lim->max_stages; i2++)
+                for (int i3 = 0; i3 < planes; i3++)
                     for (int ch = 0; ch < chan; ch++) {
+                        const int sb = asc ? i1 : 3 - i1, lv = asc ? i2 : lim->max_stages - i2, lsb = asc ? i3 : planes - 1 - i3;
                         long at = WHERE(ch, lv, sb, lsb, sg);
                         if (at < 0) continue;
                         size_t len = HDR + (get32(out + at + 16) + 7) / 8;
@@ -846,6 +941,25 @@ int orc_compress_u16(uint16_t *const img[3], int chan, size_t w, size_t h, int s
     free(where);
     free(pk);
     *size_used = used;
+    return rc;
+}
+
+int orc_compress_u16(uint16_t *const img[3], int chan, size_t w, size_t h, int stages, int filt, int segments,
+                     const orc_limits *lim, uint8_t *out, size_t quota, size_t *size_used) {
+    return compress_core(img, chan, w, h, stages, filt, segments, lim, out, quota, size_used, 0);
+}
+
+int orc_compress_u8(uint8_t *const img[3], int chan, size_t w, size_t h, int stages, int filt, int segments,
+                    const orc_limits *lim, uint8_t *out, size_t quota, size_t *size_used) {
+    uint16_t *t[3] = {NULL, NULL, NULL};
+    for (int ch = 0; ch < chan; ch++) t[ch] = widen8(img[ch], w * h);
+    int rc = compress_core(t, chan, w, h, stages, filt, segments, lim, out, quota, size_used, 1);
+    for (int ch = 0; ch < chan; ch++) {
+        /* what the reference leaves in the caller's buffers: transform output (on ICER_INTEGER_OVERFLOW after the
+         * transform) or 8-bit sign-magnitude coefficients; the caller compares them only on success */
+        for (size_t k = 0; k < w * h; k++) img[ch][k] = (uint8_t) ((t[ch][k] & 0x7F) | ((t[ch][k] >> 8) & 0x80));
+        free(t[ch]);
+    }
     return rc;
 }
 
@@ -866,9 +980,9 @@ static int segment_at(const uint8_t *p, size_t left, size_t *len) {
 }
 
 /* icer_compress.c:430-536 / icer_color.c:534-663 */
-int orc_decompress_u16(uint16_t *const img[3], int chan, size_t *w_out, size_t *h_out, size_t bufsize_px,
-                       const uint8_t *stream, size_t len, int stages, int filt, int segments,
-                       const orc_limits *lim) {
+static int decompress_core(uint16_t *const img[3], int chan, size_t *w_out, size_t *h_out, size_t bufsize_px,
+                           const uint8_t *stream, size_t len, int stages, int filt, int segments,
+                           const orc_limits *lim, int native8) {
     orc_init();
     const int planes = lim->planes;
     size_t tab_n = (size_t) 3 * (size_t) (lim->max_stages + 1) * 4 * 33 * 15;
@@ -932,13 +1046,35 @@ int orc_decompress_u16(uint16_t *const img[3], int chan, size_t *w_out, size_t *
     for (int ch = 0; ch < chan; ch++) {
         for (size_t k = 0; k < w * h; k++) img[ch][k] = from_signmag(img[ch][k]);
         for (size_t r = 0; r < llh; r++)
-            for (size_t c = 0; c < llw; c++)
-                img[ch][r * w + c] = (uint16_t) (int16_t) ((int16_t) img[ch][r * w + c] + (int16_t) mean[ch]);
-        orc_dwt_inverse_u16(img[ch], w, h, stages, filt);   /* result ignored: icer_compress.c:533 */
+            for (size_t c = 0; c < llw; c++) {
+                /* uint8: `(int8_t)(*px + (int8_t) ll_mean)` with ll_mean the header's 16-bit field (icer_compress.c:258-265) */
+                int32_t d = (int32_t) (int16_t) img[ch][r * w + c] + (native8 ? (int32_t) (int8_t) mean[ch] : (int32_t) (int16_t) mean[ch]);
+                img[ch][r * w + c] = (uint16_t) (native8 ? (int16_t) (int8_t) d : (int16_t) d);
+            }
+        dwt_inverse(img[ch], w, h, stages, filt, native8);   /* result ignored: icer_compress.c:533 */
         for (size_t k = 0; k < w * h; k++)
             if ((int16_t) img[ch][k] < 0) img[ch][k] = 0;   /* icer_util.c:82-90 */
     }
     return ORC_OK;
+}
+
+int orc_decompress_u16(uint16_t *const img[3], int chan, size_t *w_out, size_t *h_out, size_t bufsize_px,
+                       const uint8_t *stream, size_t len, int stages, int filt, int segments,
+                       const orc_limits *lim) {
+    return decompress_core(img, chan, w_out, h_out, bufsize_px, stream, len, stages, filt, segments, lim, 0);
+}
+
+int orc_decompress_u8(uint8_t *const img[3], int chan, size_t *w_out, size_t *h_out, size_t bufsize_px,
+                      const uint8_t *stream, size_t len, int stages, int filt, int segments,
+                      const orc_limits *lim) {
+    uint16_t *t[3] = {NULL, NULL, NULL};
+    for (int ch = 0; ch < chan; ch++) t[ch] = (uint16_t *) calloc(bufsize_px ? bufsize_px : 1, sizeof(uint16_t));
+    int rc = decompress_core(t, chan, w_out, h_out, bufsize_px, stream, len, stages, filt, segments, lim, 1);
+    for (int ch = 0; ch < chan; ch++) {
+        if (rc == ORC_OK) for (size_t k = 0; k < *w_out * *h_out; k++) img[ch][k] = (uint8_t) t[ch][k];
+        free(t[ch]);
+    }
+    return rc;
 }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -9,7 +9,8 @@
  * Parity status: PINNED.  tests/test_oracle_vs_ref.py compares every entry point below byte-for-byte
  * with the unmodified reference compiled into oracle/_ref/libicer_ref{,15}.so (the reference ships no
  * golden vectors of its own), and tests/golden/ holds vectors generated from that
- * reference by tests/golden/make_golden.py.
+ * reference by tests/golden/make_golden.py.  The native uint8 entry points (orc_*_u8) are pinned by
+ * tests/test_oracle_u8_vs_ref.py and tests/golden/golden_u8.json (tests/golden/make_golden_u8.py).
  *
  * Differences from the reference that are deliberate:
  *   - bit planes / max stages / max packets are run-time parameters (reference: compile-time macros
@@ -51,6 +52,13 @@ int orc_dwt_inverse_u16(uint16_t *img, size_t w, size_t h, int stages, int filt)
 int orc_dwt_forward_1d_u16(uint16_t *data, size_t n, size_t stride, int filt);
 int orc_dwt_inverse_1d_u16(uint16_t *data, size_t n, size_t stride, int filt);
 
+/* the native uint8 transform (icer_wavelet.c:8-53, :216-381): int8 arithmetic; the inverse reproduces
+ * icer_interleave_uint8's placement for odd line lengths (:570-628) */
+int orc_dwt_forward_u8(uint8_t *img, size_t w, size_t h, int stages, int filt);
+int orc_dwt_inverse_u8(uint8_t *img, size_t w, size_t h, int stages, int filt);
+/* dst[i] = position icer_interleave_uint8 gives element i of a length-len array */
+void orc_interleave8_map(size_t len, uint32_t *dst);
+
 /* partition geometry (icer_partition.c:7-54 + the segment walk of :299-385); returns #rects or <0 */
 int orc_partition_rects(size_t w, size_t h, int segments, orc_rect *out /* >= 33 entries */);
 
@@ -72,6 +80,14 @@ int orc_compress_u16(uint16_t *const img[3], int chan, size_t w, size_t h, int s
 int orc_decompress_u16(uint16_t *const img[3], int chan, size_t *w, size_t *h, size_t bufsize_px,
                        const uint8_t *stream, size_t len, int stages, int filt, int segments,
                        const orc_limits *lim);
+
+/* the native uint8 codec (icer_compress.c:18-274, icer_color.c:19-338): call with lim = {7, 6, 300} for the reference's
+ * defaults (ICER_BITPLANES_TO_COMPRESS_8, ICER_MAX_PACKETS) */
+int orc_compress_u8(uint8_t *const img[3], int chan, size_t w, size_t h, int stages, int filt, int segments,
+                    const orc_limits *lim, uint8_t *out, size_t quota, size_t *size_used);
+int orc_decompress_u8(uint8_t *const img[3], int chan, size_t *w, size_t *h, size_t bufsize_px,
+                      const uint8_t *stream, size_t len, int stages, int filt, int segments,
+                      const orc_limits *lim);
 
 /* table access for cross-checks with the reference's globals */
 int orc_bin_of(uint32_t zero, uint32_t total);

@@ -201,24 +201,49 @@ class Oracle:
         L.orc_encode_segment_plane.argtypes = [C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                                C.c_int, C.POINTER(C.c_uint8), C.c_size_t]
         L.orc_encode_segment_plane.restype = C.c_long
+        # the native uint8 codec: limits = the reference's ICER_BITPLANES_TO_COMPRESS_8 / ICER_MAX_PACKETS (icer.h:35-43)
+        P3b = C.POINTER(C.c_uint8) * 3
+        self._P3b = P3b
+        self.lim8 = _Limits(7, max_stages, 300)
+        L.orc_compress_u8.argtypes = [P3b, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(_Limits), C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
+        L.orc_decompress_u8.argtypes = [P3b, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_size_t,
+                                        C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(_Limits)]
+        L.orc_dwt_forward_u8.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_int, C.c_int]
+        L.orc_dwt_inverse_u8.argtypes = L.orc_dwt_forward_u8.argtypes
+        L.orc_interleave8_map.argtypes = [C.c_size_t, C.POINTER(C.c_uint32)]
+        L.orc_interleave8_map.restype = None
 
-    def compress(self, planes_in, stages, filt, segments, quota):
-        imgs = [np.ascontiguousarray(p, dtype=np.uint16).copy() for p in planes_in]
+    def compress(self, planes_in, stages, filt, segments, quota, dtype=np.uint16):
+        imgs = [np.ascontiguousarray(p, dtype=dtype).copy() for p in planes_in]
         h, w = imgs[0].shape
         buf = np.zeros(2 * quota + 64, dtype=np.uint8)
-        ptrs = self._P3(*[_u16p(imgs[min(i, len(imgs) - 1)]) for i in range(3)])
         used = C.c_size_t(0)
+        if dtype == np.uint8:
+            ptrs = self._P3b(*[_u8p(imgs[min(i, len(imgs) - 1)]) for i in range(3)])
+            rc = self.lib.orc_compress_u8(ptrs, len(imgs), w, h, stages, filt, segments, C.byref(self.lim8), _u8p(buf),
+                                          quota, C.byref(used))
+            n = used.value
+            return dict(rc=rc, size_used=n, stream=bytes(buf[quota:quota + n]), prio=bytes(buf[:n]), coefs=imgs)
+        ptrs = self._P3(*[_u16p(imgs[min(i, len(imgs) - 1)]) for i in range(3)])
         rc = self.lib.orc_compress_u16(ptrs, len(imgs), w, h, stages, filt, segments, C.byref(self.lim), _u8p(buf),
                                        quota, C.byref(used))
         n = used.value
         return dict(rc=rc, size_used=n, stream=bytes(buf[quota:quota + n]), prio=bytes(buf[:n]), coefs=imgs)
 
-    def decompress(self, stream, chan, bufsize_px, stages, filt, segments):
+    def decompress(self, stream, chan, bufsize_px, stages, filt, segments, dtype=np.uint16):
         data = np.frombuffer(bytes(stream) + b"\0" * 64, dtype=np.uint8).copy()
-        imgs = [np.zeros(max(bufsize_px, 1), dtype=np.uint16) for _ in range(chan)]
-        ptrs = self._P3(*[_u16p(imgs[min(i, chan - 1)]) for i in range(3)])
+        imgs = [np.zeros(max(bufsize_px, 1), dtype=dtype) for _ in range(chan)]
         w = C.c_size_t(0)
         h = C.c_size_t(0)
+        if dtype == np.uint8:
+            ptrs = self._P3b(*[_u8p(imgs[min(i, chan - 1)]) for i in range(3)])
+            rc = self.lib.orc_decompress_u8(ptrs, chan, C.byref(w), C.byref(h), bufsize_px, _u8p(data), len(stream),
+                                            stages, filt, segments, C.byref(self.lim8))
+            W, H = w.value, h.value
+            out = [im[:W * H].reshape(H, W) for im in imgs] if rc == 0 and W * H <= bufsize_px else None
+            return dict(rc=rc, w=W, h=H, images=out)
+        ptrs = self._P3(*[_u16p(imgs[min(i, chan - 1)]) for i in range(3)])
         rc = self.lib.orc_decompress_u16(ptrs, chan, C.byref(w), C.byref(h), bufsize_px, _u8p(data), len(stream),
                                          stages, filt, segments, C.byref(self.lim))
         W, H = w.value, h.value
@@ -240,6 +265,17 @@ class Oracle:
         f = self.lib.orc_dwt_inverse_1d_u16 if inverse else self.lib.orc_dwt_forward_1d_u16
         rc = f(_u16p(a), a.size, 1, filt)
         return rc, a
+
+    def dwt8(self, img, stages, filt, inverse=False):
+        a = np.ascontiguousarray(img, dtype=np.uint8).copy()
+        f = self.lib.orc_dwt_inverse_u8 if inverse else self.lib.orc_dwt_forward_u8
+        rc = f(_u8p(a), a.shape[1], a.shape[0], stages, filt)
+        return rc, a
+
+    def interleave8_map(self, n):
+        d = np.zeros(n, dtype=np.uint32)
+        self.lib.orc_interleave8_map(n, d.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return d.astype(np.int64)
 
     def partition(self, w, h, segments):
         r = (_Rect * 40)()
