@@ -387,7 +387,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override frames per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--watchdog", type=float, default=900.0, help="dump every Python stack and exit if the run takes longer than this many seconds")
+    ap.add_argument("--watchdog", type=float, default=600.0, help="dump every Python stack and exit if the run takes longer than this many seconds")
     args = ap.parse_args()
     import faulthandler
     faulthandler.dump_traceback_later(args.watchdog, exit=True)     # a stalled run must not hold a GPU box until the outer limit

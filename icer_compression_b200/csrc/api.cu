@@ -2,7 +2,7 @@
 // the lib_icer-compatible single-image entry points (include/icer.h) implemented as batch-of-one wrappers.
 //
 // There is NO CPU codec path in this file: every compress/decompress call runs the CUDA kernels of wavelet.cu,
-// encode.cu and decode.cu; if no CUDA device is usable the calls fail with ICER_FATAL_ERROR.
+// wavelet_tma.cu, coder.cu, parse.cu and pixfmt.cu; if no CUDA device is usable the calls fail with ICER_FATAL_ERROR.
 // Host-side work is limited to planning (plan.cu), the byte-stream scanner that locates CRC-valid segments
 // (lib_icer does this on the host too: icer_compress.c:443-459,:569-588) and buffer management.
 #include "common.h"

@@ -77,7 +77,7 @@ static inline size_t dim_high(size_t d, unsigned s) { return dim_low(d, s - 1) /
 int partition_rects(size_t w, size_t h, int segments, int *xs, int *ys, int *ws, int *hs, partition_param_typdef *pp);
 uint32_t host_crc32(const uint8_t *buf, size_t len);
 
-// ---- kernel launchers (wavelet.cu / encode.cu / decode.cu) -------------------------------------------
+// ---- kernel launchers (wavelet.cu / wavelet_tma.cu / coder.cu) -------------------------------------------
 struct LaunchStats { uint64_t launches = 0; };
 
 // forward / inverse multi-stage DWT over `nplanes` planes of w*h int16, in place (tmp has the same size)
@@ -86,11 +86,9 @@ int launch_dwt_forward(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t
 int launch_dwt_inverse(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
                        uint32_t filt, bool clamp_negative, cudaStream_t st, LaunchStats &ls, bool bits8 = false,
                        const std::map<uint32_t, const uint32_t *> *perms = nullptr);
-// LL mean removal + sign-magnitude (encode), and the inverse (decode)
+// LL mean removal + sign-magnitude (encode); the decode-side inverse is fused into launch_T_to_frames
 int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
                            uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8 = false);
-int launch_from_signmag_add_mean(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
-                                 const uint16_t *d_mean, cudaStream_t st, LaunchStats &ls);
 
 struct EncodeArgs {
     const uint16_t *coefsT;    // [ngroups][chan][h][w][32] sign-magnitude, frame-interleaved (32 frames per group)

@@ -194,10 +194,6 @@ __device__ __forceinline__ uint32_t to_signmag(uint32_t v) {          // icer_wa
     const int s = (int) (int16_t) v;
     return s < 0 ? (uint32_t) ((-s) & (B8 ? 0x7F : 0x7FFF)) | 0x8000u : (uint32_t) s;
 }
-__device__ __forceinline__ uint32_t from_signmag(uint32_t v) {        // icer_wavelet.c:880-886
-    return (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;
-}
-
 template <bool B8>
 __global__ void __launch_bounds__(256) k_to_signmag(uint16_t *__restrict__ data, size_t count) {
     // 8 samples (128 bits) per thread per iteration
@@ -212,19 +208,6 @@ __global__ void __launch_bounds__(256) k_to_signmag(uint16_t *__restrict__ data,
     }
     if (blockIdx.x == 0)
         for (size_t i = nvec * 8 + threadIdx.x; i < count; i += blockDim.x) data[i] = (uint16_t) to_signmag<B8>(data[i]);
-}
-
-// decode side: from sign-magnitude everywhere, then add the header's LL mean on the LL region
-__global__ void __launch_bounds__(256) k_from_signmag(uint16_t *__restrict__ planes, size_t plane_stride, size_t count,
-                                                      int W, int llw, int llh, const uint16_t *__restrict__ mean) {
-    uint16_t *p = planes + (size_t) blockIdx.y * plane_stride;
-    const int m = (int) (int16_t) mean[blockIdx.y];
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x) {
-        uint32_t v = from_signmag(p[i]);
-        const int r = (int) (i / W), c = (int) (i % W);
-        if (r < llh && c < llw) v = (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + m);
-        p[i] = (uint16_t) v;
-    }
 }
 
 template <typename F>
@@ -324,20 +307,6 @@ int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_
         k_to_signmag<false><<<blocks, 256, 0, st>>>(planes, count);
     }
     ls.launches += 2;
-    CUDA_TRY(cudaGetLastError());
-    return ICER_RESULT_OK;
-}
-
-int launch_from_signmag_add_mean(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
-                                 const uint16_t *d_mean, cudaStream_t st, LaunchStats &ls) {
-    const size_t ps = (size_t) w * h;
-    for (size_t p0 = 0; p0 < nplanes; p0 += 32768) {
-        unsigned cnt = (unsigned) (nplanes - p0 < 32768 ? nplanes - p0 : 32768);
-        unsigned bx = (unsigned) ((ps + 255) / 256);
-        if (bx > 256) bx = 256;
-        k_from_signmag<<<dim3(bx, cnt), 256, 0, st>>>(planes + p0 * ps, ps, ps, (int) w, (int) llw, (int) llh, d_mean + p0);
-        ls.launches++;
-    }
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;
 }
