@@ -522,6 +522,12 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
 #ifndef ICER_DEC_MINBLOCKS
 #define ICER_DEC_MINBLOCKS 1
 #endif
+#ifndef ICER_DEC_RECHECK
+#define ICER_DEC_RECHECK 32          /* pixels a plane decodes between two looks at the progress of the plane above */
+#endif
+#ifndef ICER_DEC_BACKOFF_NS
+#define ICER_DEC_BACKOFF_NS 300      /* sleep when the plane above is not far enough ahead */
+#endif
 constexpr int DEC_WARPS = ICER_DEC_WARPS;
 constexpr int DEC_BT = DEC_WARPS * 32;
 constexpr int DEC_SLOTS = ICER_DEC_SLOTS;
@@ -756,8 +762,8 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
                 }
                 if (up < px) limit = (a.debug_flags & 2u) ? 0u : (up > lag ? up - lag : 0u);
             }
-            if (pos >= limit) { __nanosleep(300); continue; }   // the plane above is not far enough ahead yet
-            uint32_t stop = pos + 32 < limit ? pos + 32 : limit;      // re-check progress every 32 pixels
+            if (pos >= limit) { __nanosleep(ICER_DEC_BACKOFF_NS); continue; }   // the plane above is not far enough ahead yet
+            uint32_t stop = pos + ICER_DEC_RECHECK < limit ? pos + ICER_DEC_RECHECK : limit;      // re-check progress every ICER_DEC_RECHECK pixels
             for (; pos < stop; pos++) {
                 uint16_t *p = seg + (size_t) row * RS + (size_t) col * 32;
                 const bool up_ = row > 0, dn = row + 1 < sh, rt = col + 1 < sw;
