@@ -99,7 +99,12 @@ class Ref:
         return dict(rc=rc, size_used=n, stream=bytes(buf[quota:quota + n]), prio=bytes(buf[:n]), coefs=imgs)
 
     def decompress(self, stream, chan, bufsize_px, stages, filt, segments, dtype=np.uint16):
-        data = np.frombuffer(bytes(stream) + b"\0" * 64, dtype=np.uint8).copy()  # slack: the scanner over-reads
+        # Zero slack behind the stream.  lib_icer's scanner reads header fields past the end, and its bit reader never
+        # stops at a segment's bit count (decoded_bits_total is never advanced, icer_decoding.c:66,88): when encoder and
+        # decoder contexts disagree (coefficients with bits above the top coded plane, e.g. 12-bit data at 9 planes) the
+        # decoder keeps pulling bits far behind the buffer and its output depends on that memory.  Oracle and product
+        # define those bytes as zero, so the reference gets zeros there too.
+        data = np.frombuffer(bytes(stream) + b"\0" * (4096 + 4 * max(bufsize_px, 1) * chan), dtype=np.uint8).copy()
         imgs = [np.zeros(max(bufsize_px, 1), dtype=dtype) for _ in range(chan)]
         w = C.c_size_t(0)
         h = C.c_size_t(0)
