@@ -345,6 +345,8 @@ def run_ours(args, wl, rank, world, local_rank):
                    "timing": "CUDA events on the launching stream, max over ranks"},
         "encode_mpix_s": round(px_step / (enc_ms * 1e-3) / 1e6, 2), "decode_mpix_s": round(px_step / (dec_ms * 1e-3) / 1e6, 2),
         "encode_ms": round(enc_ms, 3), "decode_ms": round(dec_ms, 3),
+        # a planar Y,U,V frame counts w*h pixels but 3*w*h samples: both are reported
+        "samples_per_pixel": chan, "value_msamples_s": round(value * chan, 2),
         "compressed_bytes_per_step": stream_bytes, "frames_ok": ok_frames, "decode_rc_ok": int((drc_h == 0).sum()),
         "roundtrip_lossless": roundtrip,
         "roofline": roofline, "roofline_other": roofline_other,
