@@ -528,6 +528,12 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
 #ifndef ICER_DEC_BACKOFF_NS
 #define ICER_DEC_BACKOFF_NS 300      /* sleep when the plane above is not far enough ahead */
 #endif
+#ifndef ICER_DEC_SLOTWAIT_NS
+#define ICER_DEC_SLOTWAIT_NS 200     /* poll interval while a chain waits for a free slot (chains last milliseconds) */
+#endif
+#ifndef ICER_DEC_CHAINWAIT_NS
+#define ICER_DEC_CHAINWAIT_NS 100    /* poll interval while a plane waits for its chain's slot to be published */
+#endif
 constexpr int DEC_WARPS = ICER_DEC_WARPS;
 constexpr int DEC_BT = DEC_WARPS * 32;
 constexpr int DEC_SLOTS = ICER_DEC_SLOTS;
@@ -697,7 +703,7 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
             wid = __shfl_sync(0xffffffffu, wid, 0);
             if (wid >= total) break;
             if (lane == 0 && k >= (uint32_t) DEC_SLOTS)
-                while (!(sl.chain == k - DEC_SLOTS && sl.freed)) __nanosleep(200);     // that chain is live: it will finish
+                while (!(sl.chain == k - DEC_SLOTS && sl.freed)) __nanosleep(ICER_DEC_SLOTWAIT_NS);     // that chain is live: it will finish
             __syncwarp();
             __threadfence_block();
             for (int q = 0; q < 15; q++) { sl.deadf[q][lane] = 0; sl.errf[q][lane] = 0; sl.posd[q][lane] = 0; }
@@ -712,7 +718,7 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
             __syncwarp();
         } else {
             bool gone = false;
-            if (lane == 0) while (sl.chain != k) { if (S.k_end <= k) { gone = true; break; } __nanosleep(100); }
+            if (lane == 0) while (sl.chain != k) { if (S.k_end <= k) { gone = true; break; } __nanosleep(ICER_DEC_CHAINWAIT_NS); }
             gone = __shfl_sync(0xffffffffu, gone ? 1 : 0, 0) != 0;
             if (gone) break;
         }
