@@ -44,6 +44,7 @@ struct icer_b200_ctx {
     float phase_ms[4] = {0, 0, 0, 0};
     size_t workspace_budget = (size_t) 64 << 30;
     // host-buffer pipeline: chunks of `pipe_chunk` frames, H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i
+    bool bulk_copy = false;       // ICER_B200_BULK_COPY=1 (experimental, unmeasured): strided bulk copies instead of one copy per frame on the host paths
     size_t pipe_chunk = 0;        // 0 = off (default): on B200 the per-chunk kernel tails cost more than the overlap saves; ICER_B200_PIPE_CHUNK=n enables it
     cudaStream_t cs_in = nullptr, cs_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -119,6 +120,7 @@ int icer_b200_create(icer_b200_ctx **out, int device) {
     icer_b200_ctx *c = new icer_b200_ctx();
     c->device = device;
     { const char *pc = getenv("ICER_B200_PIPE_CHUNK"); if (pc) c->pipe_chunk = (size_t) atol(pc); }
+    { const char *bc = getenv("ICER_B200_BULK_COPY"); c->bulk_copy = bc && atoi(bc) != 0; }
     const char *gb = getenv("ICER_B200_WORKSPACE_GB");
     if (gb && atof(gb) > 0) c->workspace_budget = (size_t) (atof(gb) * (double) ((size_t) 1 << 30));
     *out = c;
@@ -442,6 +444,12 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
             CUDA_TRY(cudaMemcpyAsync(rc + done, d_rc, nb * 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             // only the used part of every slot travels back
+            size_t maxlen = 0;
+            for (size_t i = 0; i < nb; i++) maxlen = std::max<size_t>(maxlen, (size_t) size_used[done + i]);
+            if (c->bulk_copy && maxlen) {      // one strided copy: every slot up to the longest stream (bytes behind size_used are unspecified)
+                CUDA_TRY(cudaMemcpy2DAsync(out + done * out_stride, out_stride, d_out, out_stride, maxlen, nb, cudaMemcpyDeviceToHost, st));
+                if (out_prio) CUDA_TRY(cudaMemcpy2DAsync(out_prio + done * out_stride, out_stride, d_prio, out_stride, maxlen, nb, cudaMemcpyDeviceToHost, st));
+            } else
             for (size_t i = 0; i < nb; i++) {
                 const size_t len = (size_t) size_used[done + i];
                 if (len) CUDA_TRY(cudaMemcpyAsync(out + (done + i) * out_stride, d_out + i * out_stride, len, cudaMemcpyDeviceToHost, st));
@@ -584,6 +592,11 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
     if (host) {
         if ((e = c->streams.ensure(total_bytes + 16))) return e;
         if ((e = c->dims.ensure(n * 8))) return e;
+        size_t maxlen = 0;
+        for (size_t i = 0; i < n; i++) maxlen = std::max<size_t>(maxlen, (size_t) std::min<uint64_t>(stream_len[i], stream_stride));
+        if (c->bulk_copy && maxlen && maxlen < stream_stride)     // only the used part of the slots (bytes behind it keep whatever the buffer held)
+            CUDA_TRY(cudaMemcpy2DAsync(c->streams.p, stream_stride, streams, stream_stride, maxlen, n, cudaMemcpyHostToDevice, st));
+        else
         CUDA_TRY(cudaMemcpyAsync(c->streams.p, streams, total_bytes, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(c->dims.p, stream_len, n * 8, cudaMemcpyHostToDevice, st));
         d_streams = c->streams.as<uint8_t>();
@@ -755,6 +768,12 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         }
     }
     if (host) {
+        bool all_ok = c->bulk_copy;
+        for (size_t i = 0; i < n && all_ok; i++) all_ok = hrc[i] == ICER_RESULT_OK;
+        if (all_ok) {        // every frame decoded: one copy for the whole batch
+            if (pixfmt == ICER_B200_PIX_U16) CUDA_TRY(cudaMemcpyAsync(frames, d_frames, n * chan * cap_px * 2, cudaMemcpyDeviceToHost, st));
+            else CUDA_TRY(cudaMemcpyAsync(frames_any, d_out8, n * out_bytes_per_frame, cudaMemcpyDeviceToHost, st));
+        } else
         for (size_t i = 0; i < n; i++)
             if (hrc[i] == ICER_RESULT_OK) {
                 if (pixfmt == ICER_B200_PIX_U16)
