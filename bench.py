@@ -165,6 +165,8 @@ def run_reference_arm(args, wl, rank, world):
     if rank != 0:
         return
     fpc = frames_per_core_for(wl)
+    if os.environ.get("ICER_BENCH_FRAMES_PER_CORE"):       # test hook: a shorter sample (tests/test_bench_contract_cpu.py)
+        fpc = max(1, int(os.environ["ICER_BENCH_FRAMES_PER_CORE"]))
     vals = []
     for it in range(args.warmup + args.steps):
         r = cpu_reference_run(wl, fpc)

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.skipif(not harness.have_ref(), reason="oracle/_ref not built")
 def test_reference_arm_line():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=240, cwd=ROOT)
+                       capture_output=True, text=True, timeout=240, cwd=ROOT, env=dict(os.environ, ICER_BENCH_FRAMES_PER_CORE="3"))
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
     assert line["impl"] == "reference" and line["metric"] == "encode+decode Mpixels/s" and line["unit"] == "Mpixels/s"
