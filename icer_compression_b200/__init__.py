@@ -7,7 +7,7 @@ points under their own names plus the batch extension.  There is no Python or CP
 library is missing or no CUDA device is usable every call raises.
 """
 from .api import (  # noqa: F401
-    IcerB200, LegacyAPI, IcerError, lib_path, load_library, MEM_HOST, MEM_DEVICE, PIX_U16, PIX_U8, PIX_RGB888, PIX_NATIVE_U8, u8_interleave_map,
+    IcerB200, IcerMulti, LegacyAPI, IcerError, device_count, lib_path, load_library, MEM_HOST, MEM_DEVICE, PIX_U16, PIX_U8, PIX_RGB888, PIX_NATIVE_U8, u8_interleave_map,
     ICER_RESULT_OK, ICER_INTEGER_OVERFLOW, ICER_OUTPUT_BUF_TOO_SMALL, ICER_TOO_MANY_SEGMENTS, ICER_TOO_MANY_STAGES,
     ICER_BYTE_QUOTA_EXCEEDED, ICER_FATAL_ERROR, FILTERS,
 )

@@ -79,6 +79,9 @@ def load_library():
     L.icer_b200_compress_batch_pix.argtypes = [vp, C.POINTER(_Params), vp, C.c_int, C.c_size_t, vp, C.c_size_t, vp, vp, C.c_int, vp]
     L.icer_b200_decompress_batch_pix.argtypes = [vp, C.POINTER(_Params), vp, C.c_size_t, vp, C.c_size_t, vp, C.c_int, vp, vp, C.c_int, vp]
     L.icer_b200_dwt_batch_u16.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_int, vp]
+    L.icer_b200_compress_batch_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(_Params), vp, C.c_int, C.c_size_t, vp, C.c_size_t, vp, vp, C.c_int]
+    L.icer_b200_decompress_batch_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(_Params), vp, C.c_size_t, vp, C.c_size_t, vp, C.c_int, vp, vp, C.c_int]
+    L.icer_b200_device_count.restype = C.c_int
     L.icer_b200_launch_count.argtypes = [vp]
     L.icer_b200_launch_count.restype = C.c_uint64
     L.icer_b200_last_phase_ms.argtypes = [vp, C.c_int]
@@ -240,6 +243,65 @@ class IcerB200:
         rc = self.lib.icer_b200_set_limits_u8(self.h, planes, max_packets)
         if rc != 0:
             raise IcerError("icer_b200_set_limits_u8 -> %d" % rc)
+
+
+class IcerMulti:
+    """One batch over several contexts (icer_b200_compress_batch_multi / icer_b200_decompress_batch_multi): context g codes
+    the frames [g*n/G, (g+1)*n/G), one host thread per context inside the library.  devices: list of CUDA ordinals (a device
+    may appear more than once: every entry gets its own context)."""
+
+    def __init__(self, devices, planes=9, max_stages=6, max_packets=800):
+        self.ctxs = [IcerB200(device=d, planes=planes, max_stages=max_stages, max_packets=max_packets) for d in devices]
+        self.lib = self.ctxs[0].lib
+        self._arr = (C.c_void_p * len(self.ctxs))(*[c.h for c in self.ctxs])
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+
+    def launch_count(self):
+        return sum(c.launch_count() for c in self.ctxs)
+
+    def compress_batch_raw(self, params, frames, n, out, out_stride, size_used, rc, mem, pixfmt=PIX_U16):
+        p = _Params(*params)
+        e = self.lib.icer_b200_compress_batch_multi(self._arr, len(self.ctxs), C.byref(p), _ptr(frames), pixfmt, n, _ptr(out), out_stride,
+                                                    _ptr(size_used), _ptr(rc), mem)
+        if e != 0:
+            raise IcerError("icer_b200_compress_batch_multi -> %d" % e)
+
+    def decompress_batch_raw(self, params, streams, stream_stride, stream_len, n, frames, dims, rc, mem, pixfmt=PIX_U16):
+        p = _Params(*params)
+        e = self.lib.icer_b200_decompress_batch_multi(self._arr, len(self.ctxs), C.byref(p), _ptr(streams), stream_stride, _ptr(stream_len),
+                                                      n, _ptr(frames), pixfmt, _ptr(dims), _ptr(rc), mem)
+        if e != 0:
+            raise IcerError("icer_b200_decompress_batch_multi -> %d" % e)
+
+    def compress_batch(self, frames, stages, filt, segments, quota):
+        frames = np.ascontiguousarray(frames, dtype=np.uint16)
+        n, chan, h, w = frames.shape
+        out = np.zeros((n, quota), dtype=np.uint8)
+        used = np.zeros(n, dtype=np.uint64)
+        rc = np.zeros(n, dtype=np.int32)
+        self.compress_batch_raw((w, h, chan, stages, filt, segments, quota), frames, n, out, quota, used, rc, MEM_HOST)
+        return dict(rc=rc, size_used=used, streams=[bytes(out[i, :int(used[i])]) for i in range(n)])
+
+    def decompress_batch(self, streams, chan, w, h, stages, filt, segments):
+        n = len(streams)
+        stride = max(max((len(s) for s in streams), default=1), 1)
+        buf = np.zeros((n, stride), dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.uint64)
+        for i, s in enumerate(streams):
+            buf[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+            lens[i] = len(s)
+        frames = np.zeros((n, chan, h * w), dtype=np.uint16)
+        dims = np.zeros((n, 2), dtype=np.uint32)
+        rc = np.zeros(n, dtype=np.int32)
+        self.decompress_batch_raw((w, h, chan, stages, filt, segments, 0), buf, stride, lens, n, frames, dims, rc, MEM_HOST)
+        return dict(rc=rc, dims=dims, frames=frames)
+
+
+def device_count():
+    return int(load_library().icer_b200_device_count())
 
 
 class LegacyAPI:

@@ -17,10 +17,15 @@ struct DevBuf {
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return ICER_RESULT_OK;
-        if (p) cudaFree(p);
+        if (p) cudaFree(p);            // contents are never carried over; freeing first lets the allocator reuse the range
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
-        CUDA_TRY(cudaMalloc(&p, want));
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            (void) cudaGetLastError();
+            p = nullptr;
+            want = bytes;              // retry without the growth margin before giving up
+            CUDA_TRY(cudaMalloc(&p, want));
+        }
         cap = want;
         return ICER_RESULT_OK;
     }
@@ -44,9 +49,9 @@ struct icer_b200_ctx {
     float phase_ms[4] = {0, 0, 0, 0};
     size_t workspace_budget = (size_t) 64 << 30;
     // host-buffer pipeline: chunks of `pipe_chunk` frames, H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i
-    bool bulk_copy = false;       // ICER_B200_BULK_COPY=1 (experimental, unmeasured): strided bulk copies instead of one copy per frame on the host paths
+    bool bulk_copy = true;        // strided bulk copies (one cudaMemcpy2DAsync per direction) on the host paths; ICER_B200_BULK_COPY=0 falls back to one copy per frame
     size_t pipe_chunk = 0;        // 0 = off (default): on B200 the per-chunk kernel tails cost more than the overlap saves; ICER_B200_PIPE_CHUNK=n enables it
-    cudaStream_t cs_in = nullptr, cs_out = nullptr;
+    cudaStream_t cs_in = nullptr, cs_out = nullptr, cs_own = nullptr;    // cs_own: the stream of the *_multi calls
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     DevBuf p_in[2], p_out[2], p_used[2], p_rc[2], p_dims[2];
 };
@@ -120,7 +125,7 @@ int icer_b200_create(icer_b200_ctx **out, int device) {
     icer_b200_ctx *c = new icer_b200_ctx();
     c->device = device;
     { const char *pc = getenv("ICER_B200_PIPE_CHUNK"); if (pc) c->pipe_chunk = (size_t) atol(pc); }
-    { const char *bc = getenv("ICER_B200_BULK_COPY"); c->bulk_copy = bc && atoi(bc) != 0; }
+    { const char *bc = getenv("ICER_B200_BULK_COPY"); if (bc) c->bulk_copy = atoi(bc) != 0; }
     const char *gb = getenv("ICER_B200_WORKSPACE_GB");
     if (gb && atof(gb) > 0) c->workspace_budget = (size_t) (atof(gb) * (double) ((size_t) 1 << 30));
     *out = c;
@@ -143,6 +148,7 @@ void icer_b200_destroy(icer_b200_ctx *c) {
     }
     if (c->cs_in) cudaStreamDestroy(c->cs_in);
     if (c->cs_out) cudaStreamDestroy(c->cs_out);
+    if (c->cs_own) cudaStreamDestroy(c->cs_own);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
 }
@@ -305,6 +311,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
     if (!c || !p || !frames || !out || !size_used || !rc) return ICER_INVALID_INPUT;
     const bool native8 = pixfmt == ICER_B200_PIX_NATIVE_U8;
     if (p->channels != 1 && p->channels != 3) return ICER_INVALID_INPUT;
+    if (p->filter > ICER_FILTER_Q || p->width == 0 || p->height == 0) return ICER_INVALID_INPUT;
     if (out_stride < p->byte_quota) return ICER_OUTPUT_BUF_TOO_SMALL;
     if (n == 0) return ICER_RESULT_OK;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -333,18 +340,29 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
     float ms_dwt = 0, ms_enc = 0, ms_asm = 0;
     size_t done = 0;
     while (done < n) {
-        // chunk size under the workspace budget
-        const size_t per_frame = frame_px * 2 * 2 + frame_px / 8 + pl->scratch_words * 4 + (size_t) pl->nstreams * 24 + (host ? out_stride * (out_prio ? 2 : 1) : 0) + 64;
+        // chunk size under the workspace budget: every per-frame buffer counts (coefs, tmp rounded up to 32-frame groups, tmp2
+        // and fin at 2 B/sample each, the 8-bit staging, payload scratch, per-stream arrays, host staging of the output slots)
+        const size_t per_frame = frame_px * 2 * 4 + (pixfmt != ICER_B200_PIX_U16 ? frame_px : 0) + pl->scratch_words * 4 +
+                                 (size_t) pl->nstreams * 24 + (host ? out_stride * (out_prio ? 2 : 1) : 0) + 64;
         size_t nb = std::max<size_t>(1, c->workspace_budget / per_frame);
+        if (nb > 32) nb &= ~(size_t) 31;             // whole coder groups
         nb = std::min(nb, n - done);
         int e;
-        if ((e = c->coefs.ensure(nb * frame_px * 2))) return e;
-        const uint32_t ngroups = (uint32_t) ((nb + 31) / 32);
-        if ((e = c->tmp.ensure((size_t) ngroups * 32 * frame_px * 2))) return e;
-        if ((e = c->bits.ensure(nb * pl->nstreams * 4))) return e;
-        if ((e = c->crc.ensure(nb * pl->nstreams * 4))) return e;
-        if ((e = c->offp.ensure(nb * pl->nstreams * 8))) return e;
-        if ((e = c->offr.ensure(nb * pl->nstreams * 8))) return e;
+        uint32_t ngroups = 0;
+        for (;;) {      // a failed allocation halves the chunk instead of failing the call
+            ngroups = (uint32_t) ((nb + 31) / 32);
+            e = c->coefs.ensure(nb * frame_px * 2);
+            if (!e) e = c->tmp.ensure((size_t) ngroups * 32 * frame_px * 2);
+            if (!e) e = c->fin.ensure(host || pixfmt != ICER_B200_PIX_U16 ? nb * frame_px * 2 : 0);
+            if (!e) e = c->scratch.ensure(nb * pl->scratch_words * 4);
+            if (!e) e = c->bits.ensure(nb * pl->nstreams * 4);
+            if (!e) e = c->crc.ensure(nb * pl->nstreams * 4);
+            if (!e) e = c->offp.ensure(nb * pl->nstreams * 8);
+            if (!e) e = c->offr.ensure(nb * pl->nstreams * 8);
+            if (!e) break;
+            if (nb <= 1) return e;
+            nb = (nb + 1) / 2;
+        }
         if ((e = c->rings.ensure((size_t) c->ring_threads * ICER_RING * 2))) return e;
         if ((e = c->mean.ensure(nb * chan * 2))) return e;
         if ((e = c->ovf.ensure(nb * chan * 4))) return e;
@@ -574,6 +592,7 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
     const bool native8 = pixfmt == ICER_B200_PIX_NATIVE_U8;
     if (!c || !p || !streams || !stream_len || !frames || !rc) return ICER_INVALID_INPUT;
     if (p->channels != 1 && p->channels != 3) return ICER_INVALID_INPUT;
+    if (p->filter > ICER_FILTER_Q) return ICER_INVALID_INPUT;
     if (n == 0) return ICER_RESULT_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t) stream;
@@ -594,10 +613,11 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         if ((e = c->dims.ensure(n * 8))) return e;
         size_t maxlen = 0;
         for (size_t i = 0; i < n; i++) maxlen = std::max<size_t>(maxlen, (size_t) std::min<uint64_t>(stream_len[i], stream_stride));
-        if (c->bulk_copy && maxlen && maxlen < stream_stride)     // only the used part of the slots (bytes behind it keep whatever the buffer held)
+        // only the used part of every slot travels: the kernels never read a frame's slot behind its stream_len
+        if (c->bulk_copy && maxlen && maxlen < stream_stride)
             CUDA_TRY(cudaMemcpy2DAsync(c->streams.p, stream_stride, streams, stream_stride, maxlen, n, cudaMemcpyHostToDevice, st));
-        else
-        CUDA_TRY(cudaMemcpyAsync(c->streams.p, streams, total_bytes, cudaMemcpyHostToDevice, st));
+        else if (maxlen)
+            CUDA_TRY(cudaMemcpyAsync(c->streams.p, streams, (n - 1) * stream_stride + maxlen, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(c->dims.p, stream_len, n * 8, cudaMemcpyHostToDevice, st));
         d_streams = c->streams.as<uint8_t>();
         d_lens = c->dims.as<uint64_t>();
@@ -716,7 +736,7 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         da.coefsT = d_T; da.ngroups = ngroups; da.chan = chan; da.planes = pl->planes;
         da.units = pl->d_units; da.nunits = (uint32_t) pl->units.size(); da.plan_w = w; da.plan_h = h;
         da.frame_of = c->frame_ok.as<int32_t>();
-        da.streams = d_streams; da.stream_stride = stream_stride; da.total_bytes = total_bytes;
+        da.streams = d_streams; da.stream_stride = stream_stride; da.stream_len = d_lens;
         da.seg_off = c->segoff.as<uint32_t>();
         da.work_counter = c->misc.as<unsigned long long>();
         da.debug_flags = dbg_flags;
@@ -810,6 +830,146 @@ int icer_b200_decompress_batch_pix(icer_b200_ctx *c, const icer_b200_params *p, 
                                    void *stream) {
     return decompress_batch_any(c, p, streams, stream_stride, stream_len, n, frames, pixfmt, dims, rc, mem, stream);
 }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// one batch over several contexts (several GPUs of one box): frames are independent, so context g gets the
+// frames [g*n/G, (g+1)*n/G) and there is no exchange between the devices.  One host thread per context.
+//   mem = HOST   : every context moves its own slice over its own PCIe link
+//   mem = DEVICE : the buffers live on the device of ctxs[0]; the other devices fetch their slice and return their
+//                  results with peer copies (NVLink through the NVSwitch) -- the single scatter / gather of SURVEY 8(e)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct MultiSlice { size_t f0, nb; };
+MultiSlice slice_of(size_t n, int G, int g) {
+    const size_t a = n * (size_t) g / (size_t) G, b = n * (size_t) (g + 1) / (size_t) G;
+    return MultiSlice{a, b - a};
+}
+int own_stream(icer_b200_ctx *c, cudaStream_t *st) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->cs_own) CUDA_TRY(cudaStreamCreateWithFlags(&c->cs_own, cudaStreamNonBlocking));
+    *st = c->cs_own;
+    return ICER_RESULT_OK;
+}
+void enable_peer(int dev, int peer) {
+    if (dev == peer) return;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, dev, peer) == cudaSuccess && can) {
+        cudaSetDevice(dev);
+        if (cudaDeviceEnablePeerAccess(peer, 0) != cudaSuccess) (void) cudaGetLastError();    // already enabled is fine
+    }
+}
+template <typename F> int run_per_context(int nctx, F f) {
+    std::vector<int> res((size_t) nctx, ICER_RESULT_OK);
+    std::vector<std::thread> th;
+    for (int g = 1; g < nctx; g++) th.emplace_back([&, g]() { res[(size_t) g] = f(g); });
+    res[0] = f(0);
+    for (auto &t : th) t.join();
+    for (int r : res) if (r != ICER_RESULT_OK) return r;
+    return ICER_RESULT_OK;
+}
+bool multi_args_ok(icer_b200_ctx *const *ctxs, int nctx) {
+    if (!ctxs || nctx < 1 || nctx > 64) return false;
+    for (int g = 0; g < nctx; g++) {
+        if (!ctxs[g]) return false;
+        for (int k = 0; k < g; k++) if (ctxs[k] == ctxs[g]) return false;      // a context serves one host thread at a time
+    }
+    return true;
+}
+}  // namespace
+
+extern "C" int icer_b200_compress_batch_multi(icer_b200_ctx *const *ctxs, int nctx, const icer_b200_params *p, const void *frames,
+                                              int pixfmt, size_t n, uint8_t *out, size_t out_stride, uint64_t *size_used, int32_t *rc,
+                                              int mem) {
+    if (!multi_args_ok(ctxs, nctx) || !p || !frames || !out || !size_used || !rc) return ICER_INVALID_INPUT;
+    const size_t frame_bytes = (size_t) p->width * p->height * p->channels * (pixfmt == ICER_B200_PIX_U16 ? 2 : 1);
+    const int dev0 = ctxs[0]->device;
+    return run_per_context(nctx, [&](int g) -> int {
+        icer_b200_ctx *c = ctxs[g];
+        const MultiSlice sl = slice_of(n, nctx, g);
+        if (sl.nb == 0) return ICER_RESULT_OK;
+        cudaStream_t st;
+        int e = own_stream(c, &st);
+        if (e) return e;
+        const uint8_t *src = (const uint8_t *) frames + sl.f0 * frame_bytes;
+        uint8_t *dst = out + sl.f0 * out_stride;
+        if (mem == ICER_B200_MEM_HOST || c->device == dev0) {
+            e = compress_batch_any(c, p, src, pixfmt, sl.nb, dst, out_stride, nullptr, nullptr, size_used + sl.f0, rc + sl.f0, mem, st);
+            if (e) return e;
+            CUDA_TRY(cudaStreamSynchronize(st));
+            return ICER_RESULT_OK;
+        }
+        // device buffers on dev0, this context on another GPU: scatter the slice in, gather the results back (peer copies)
+        enable_peer(c->device, dev0);
+        CUDA_TRY(cudaSetDevice(c->device));
+        if ((e = c->p_in[0].ensure(sl.nb * frame_bytes))) return e;
+        if ((e = c->p_out[0].ensure(sl.nb * out_stride))) return e;
+        if ((e = c->p_used[0].ensure(sl.nb * 8))) return e;
+        if ((e = c->p_rc[0].ensure(sl.nb * 4))) return e;
+        CUDA_TRY(cudaMemcpyPeerAsync(c->p_in[0].p, c->device, src, dev0, sl.nb * frame_bytes, st));
+        e = compress_batch_any(c, p, c->p_in[0].p, pixfmt, sl.nb, c->p_out[0].as<uint8_t>(), out_stride, nullptr, nullptr,
+                               c->p_used[0].as<uint64_t>(), c->p_rc[0].as<int32_t>(), ICER_B200_MEM_DEVICE, st);
+        if (e) return e;
+        CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(cudaMemcpyPeerAsync(dst, dev0, c->p_out[0].p, c->device, sl.nb * out_stride, st));
+        CUDA_TRY(cudaMemcpyPeerAsync(size_used + sl.f0, dev0, c->p_used[0].p, c->device, sl.nb * 8, st));
+        CUDA_TRY(cudaMemcpyPeerAsync(rc + sl.f0, dev0, c->p_rc[0].p, c->device, sl.nb * 4, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return ICER_RESULT_OK;
+    });
+}
+
+extern "C" int icer_b200_decompress_batch_multi(icer_b200_ctx *const *ctxs, int nctx, const icer_b200_params *p, const uint8_t *streams,
+                                                size_t stream_stride, const uint64_t *stream_len, size_t n, void *frames, int pixfmt,
+                                                uint32_t *dims, int32_t *rc, int mem) {
+    if (!multi_args_ok(ctxs, nctx) || !p || !streams || !stream_len || !frames || !rc) return ICER_INVALID_INPUT;
+    const size_t frame_bytes = (size_t) p->width * p->height * p->channels * (pixfmt == ICER_B200_PIX_U16 ? 2 : 1);
+    const int dev0 = ctxs[0]->device;
+    return run_per_context(nctx, [&](int g) -> int {
+        icer_b200_ctx *c = ctxs[g];
+        const MultiSlice sl = slice_of(n, nctx, g);
+        if (sl.nb == 0) return ICER_RESULT_OK;
+        cudaStream_t st;
+        int e = own_stream(c, &st);
+        if (e) return e;
+        const uint8_t *src = streams + sl.f0 * stream_stride;
+        uint8_t *dst = (uint8_t *) frames + sl.f0 * frame_bytes;
+        uint32_t *dd = dims ? dims + 2 * sl.f0 : nullptr;
+        if (mem == ICER_B200_MEM_HOST || c->device == dev0) {
+            e = decompress_batch_any(c, p, src, stream_stride, stream_len + sl.f0, sl.nb, dst, pixfmt, dd, rc + sl.f0, mem, st);
+            if (e) return e;
+            CUDA_TRY(cudaStreamSynchronize(st));
+            return ICER_RESULT_OK;
+        }
+        enable_peer(c->device, dev0);
+        CUDA_TRY(cudaSetDevice(c->device));
+        if ((e = c->p_in[0].ensure(sl.nb * stream_stride + 16))) return e;
+        if ((e = c->p_out[0].ensure(sl.nb * frame_bytes))) return e;
+        if ((e = c->p_used[0].ensure(sl.nb * 8))) return e;
+        if ((e = c->p_rc[0].ensure(sl.nb * 4))) return e;
+        if ((e = c->p_dims[0].ensure(sl.nb * 8))) return e;
+        CUDA_TRY(cudaMemcpyPeerAsync(c->p_in[0].p, c->device, src, dev0, sl.nb * stream_stride, st));
+        CUDA_TRY(cudaMemcpyPeerAsync(c->p_used[0].p, c->device, stream_len + sl.f0, dev0, sl.nb * 8, st));
+        e = decompress_batch_any(c, p, c->p_in[0].as<uint8_t>(), stream_stride, c->p_used[0].as<uint64_t>(), sl.nb, c->p_out[0].p, pixfmt,
+                                 c->p_dims[0].as<uint32_t>(), c->p_rc[0].as<int32_t>(), ICER_B200_MEM_DEVICE, st);
+        if (e) return e;
+        CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(cudaMemcpyPeerAsync(dst, dev0, c->p_out[0].p, c->device, sl.nb * frame_bytes, st));
+        if (dd) CUDA_TRY(cudaMemcpyPeerAsync(dd, dev0, c->p_dims[0].p, c->device, sl.nb * 8, st));
+        CUDA_TRY(cudaMemcpyPeerAsync(rc + sl.f0, dev0, c->p_rc[0].p, c->device, sl.nb * 4, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return ICER_RESULT_OK;
+    });
+}
+
+extern "C" int icer_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void) cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" {
 
 // ---------------------------------------------------------------------------------------------------------
 // wavelet-only hook
@@ -916,6 +1076,9 @@ int icer_b200_dwt_batch_u8(icer_b200_ctx *c, uint8_t *planes, size_t n, uint32_t
 // ---------------------------------------------------------------------------------------------------------
 static icer_b200_ctx *g_ctx = nullptr;
 static std::mutex g_mu;
+// lib_icer is non-re-entrant (global work buffers); the compat entry points share ONE default context, so they are
+// serialised here instead of corrupting each other's workspace when called from several host threads
+static std::mutex g_call_mu;
 
 static icer_b200_ctx *default_ctx() {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -960,6 +1123,7 @@ static int compress_common(T *const ch[3], uint32_t chan, size_t w, size_t h, ui
     icer_b200_ctx *c = default_ctx();
     if (!c) return ICER_FATAL_ERROR;
     if (!od || !ch[0]) return ICER_INVALID_INPUT;
+    std::lock_guard<std::mutex> call_lock(g_call_mu);
     icer_b200_params p;
     p.width = (uint32_t) w; p.height = (uint32_t) h; p.channels = chan; p.stages = stages; p.filter = (uint32_t) filt;
     p.segments = segments; p.byte_quota = od->size_allocated;
@@ -991,6 +1155,7 @@ static int decompress_common(T *const ch[3], uint32_t chan, size_t *image_w, siz
     icer_b200_ctx *c = default_ctx();
     if (!c) return ICER_FATAL_ERROR;
     if (!data || !image_w || !image_h) return ICER_INVALID_INPUT;
+    std::lock_guard<std::mutex> call_lock(g_call_mu);
     // dimensions of the LAST valid header decide the geometry (icer_compress.c:454-455)
     Parsed ps;
     parse_stream(data, len, chan, ps);
@@ -1075,6 +1240,7 @@ int icer_decompress_image_yuv_uint8(uint8_t *y, uint8_t *u, uint8_t *v, size_t *
 int icer_wavelet_transform_stages_uint8(uint8_t *image, size_t image_w, size_t image_h, uint8_t stages, enum icer_filter_types filt) {
     icer_b200_ctx *c = default_ctx();
     if (!c) return ICER_FATAL_ERROR;
+    std::lock_guard<std::mutex> call_lock(g_call_mu);
     int32_t rc = ICER_FATAL_ERROR;
     int e = icer_b200_dwt_batch_u8(c, image, 1, (uint32_t) image_w, (uint32_t) image_h, stages, (uint32_t) filt, 0, &rc, ICER_B200_MEM_HOST, nullptr);
     return e != ICER_RESULT_OK ? e : rc;
@@ -1084,6 +1250,7 @@ int icer_inverse_wavelet_transform_stages_uint8(uint8_t *image, size_t image_w, 
                                                 enum icer_filter_types filt) {
     icer_b200_ctx *c = default_ctx();
     if (!c) return ICER_FATAL_ERROR;
+    std::lock_guard<std::mutex> call_lock(g_call_mu);
     int32_t rc = ICER_FATAL_ERROR;
     int e = icer_b200_dwt_batch_u8(c, image, 1, (uint32_t) image_w, (uint32_t) image_h, stages, (uint32_t) filt, 1, &rc, ICER_B200_MEM_HOST, nullptr);
     return e != ICER_RESULT_OK ? e : rc;
@@ -1092,6 +1259,7 @@ int icer_inverse_wavelet_transform_stages_uint8(uint8_t *image, size_t image_w, 
 int icer_wavelet_transform_stages_uint16(uint16_t *image, size_t image_w, size_t image_h, uint8_t stages, enum icer_filter_types filt) {
     icer_b200_ctx *c = default_ctx();
     if (!c) return ICER_FATAL_ERROR;
+    std::lock_guard<std::mutex> call_lock(g_call_mu);
     int32_t rc = ICER_FATAL_ERROR;
     int e = icer_b200_dwt_batch_u16(c, image, 1, (uint32_t) image_w, (uint32_t) image_h, stages, (uint32_t) filt, 0, &rc, ICER_B200_MEM_HOST, nullptr);
     return e != ICER_RESULT_OK ? e : rc;
@@ -1101,6 +1269,7 @@ int icer_inverse_wavelet_transform_stages_uint16(uint16_t *image, size_t image_w
                                                  enum icer_filter_types filt) {
     icer_b200_ctx *c = default_ctx();
     if (!c) return ICER_FATAL_ERROR;
+    std::lock_guard<std::mutex> call_lock(g_call_mu);
     int32_t rc = ICER_FATAL_ERROR;
     int e = icer_b200_dwt_batch_u16(c, image, 1, (uint32_t) image_w, (uint32_t) image_h, stages, (uint32_t) filt, 1, &rc, ICER_B200_MEM_HOST, nullptr);
     // lib_icer reports inverse overflow too (icer_wavelet.c:102) but no caller looks at it; we return OK / TOO_MANY_STAGES

@@ -22,6 +22,7 @@
 // variable-to-variable / uncoded bins, 2048-codeword interleave window with forced flush and its decoder mirror),
 // icer_util.c:48-56 (bin cut-offs), icer_partition.c:328-334 + icer_encoding.c:210-234 (segment header, quota).
 #include "common.h"
+#include <mutex>
 
 namespace {
 
@@ -38,7 +39,10 @@ struct DevTables {
     uint8_t ctx_hv[45], ctx_hh[25], ctx_sign[25], sign_pred[25];   // icer_config.c:26-67
 };
 __constant__ DevTables c_tab;
-bool g_tables_uploaded = false;
+// __constant__ memory has one instance PER DEVICE: the upload is tracked per device ordinal (a process may hold contexts on
+// several GPUs, e.g. icer_b200_*_batch_multi)
+std::mutex g_tab_mu;
+bool g_tables_uploaded[64] = {false};
 
 const uint8_t h_ctx_hv[45] = {0, 1, 2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 6, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7,
                               8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8};
@@ -47,7 +51,11 @@ const uint8_t h_ctx_sign[25] = {14, 14, 15, 16, 16, 14, 14, 15, 16, 16, 13, 13, 
 const uint8_t h_sign_pred[25] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 int upload_tables() {
-    if (g_tables_uploaded) return ICER_RESULT_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return ICER_FATAL_ERROR;
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    if (g_tables_uploaded[dev]) return ICER_RESULT_OK;
     const HostTables &h = icer_host_tables();
     static DevTables d;
     for (int b = 0; b < 8; b++)
@@ -75,8 +83,8 @@ int upload_tables() {
     }
     memcpy(d.ctx_hv, h_ctx_hv, 45); memcpy(d.ctx_hh, h_ctx_hh, 25);
     memcpy(d.ctx_sign, h_ctx_sign, 25); memcpy(d.sign_pred, h_sign_pred, 25);
-    CUDA_TRY(cudaMemcpyToSymbol(c_tab, &d, sizeof d));
-    g_tables_uploaded = true;
+    CUDA_TRY(cudaMemcpyToSymbol(c_tab, &d, sizeof d));      // synchronous: complete before any later launch on any stream
+    g_tables_uploaded[dev] = true;
     return ICER_RESULT_OK;
 }
 
@@ -561,7 +569,7 @@ struct DecShared {
 struct Dec {
     const SmemTables &T;
     const uint32_t *wp = nullptr;   // next aligned stream word to load
-    const uint8_t *end = nullptr;   // end of the whole stream buffer (bytes at or beyond it read as zero)
+    const uint8_t *end = nullptr;   // end of THIS FRAME's stream (bytes at or beyond it read as zero, like the oracle and the legacy calls)
     unsigned long long bb = 0;      // bit buffer, LSB = next stream bit
     int bbn = 0;                    // bits in bb that came from loads (zeros beyond)
     uint32_t total_bits = 0;
@@ -574,7 +582,10 @@ struct Dec {
         const ptrdiff_t left = end - reinterpret_cast<const uint8_t *>(wp);
         uint32_t w = 0;
         if (left >= 4) w = *wp;
-        else if (left > 0) w = *wp & ((1u << (8 * (int) left)) - 1u);
+        else if (left > 0) {           // tail: byte loads, nothing behind `end` is touched (the caller's buffer may stop there)
+            const uint8_t *bp = reinterpret_cast<const uint8_t *>(wp);
+            for (int i = 0; i < (int) left; i++) w |= (uint32_t) bp[i] << (8 * i);
+        }
         wp++;
         return w;
     }
@@ -671,7 +682,6 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
     const int P = (int) a.planes;
     const unsigned long long total = (unsigned long long) a.ngroups * a.nunits;
     const uint32_t nstreams = a.nunits * a.planes;
-    const uint8_t *buf_end = a.streams + a.total_bytes;
     const int W = (int) a.plan_w;
     const int RS = W * 32;
     const size_t plane_px = (size_t) a.plan_w * a.plan_h;
@@ -738,8 +748,12 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
             const uint32_t off1 = row[lsb];
             if (off1 == 0u) alive = false;
             if (alive) {
-                const uint8_t *hd = a.streams + (size_t) frame * a.stream_stride + (off1 - 1);
-                dc.start(hd + ICER_HDR_BYTES, buf_end, hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24));
+                // lib_icer's bit reader never stops at a segment's bit count (icer_decoding.c:59-105): a desynchronised stream
+                // keeps reading.  Those reads end at the frame's own stream length; behind it every bit is zero.
+                const uint8_t *fbase = a.streams + (size_t) frame * a.stream_stride;
+                const uint64_t flen = a.stream_len[frame] < a.stream_stride ? a.stream_len[frame] : a.stream_stride;
+                const uint8_t *hd = fbase + (off1 - 1);
+                dc.start(hd + ICER_HDR_BYTES, fbase + flen, hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24));
             }
         }
         uint16_t *seg = a.coefsT + (((size_t) g * a.chan + u.chan) * plane_px + (size_t) u.y * W + u.x) * 32 + lane;

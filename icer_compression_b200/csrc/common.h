@@ -132,7 +132,8 @@ struct DecodeArgs {
     const Unit *units; uint32_t nunits;
     uint32_t plan_w, plan_h;
     const int32_t *frame_of;       // [ngroups*32] batch index of each lane's frame, -1 = padding
-    const uint8_t *streams; uint64_t stream_stride; uint64_t total_bytes;
+    const uint8_t *streams; uint64_t stream_stride;
+    const uint64_t *stream_len;    // [batch frames] bytes of each frame's stream; the bit readers of a frame see zeros behind it
     const uint32_t *seg_off;       // [batch frames][nstreams] 1 + byte offset of the segment header inside the frame's stream, 0 = absent
     unsigned long long *work_counter;
     uint32_t debug_flags;          // bit0: no quiet fast path, bit1: planes strictly one after the other

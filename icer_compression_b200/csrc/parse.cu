@@ -16,14 +16,20 @@
 //             one; offsets that are not valid candidates only ever advance the reference's cursor by one byte
 //   k_table   per dimension group: accepted segments -> [frame][stream] offset table through the plan's unit LUT
 #include "common.h"
+#include <mutex>
 
 namespace {
 
 __constant__ uint32_t c_crc[256];
-bool g_crc_uploaded = false;
+std::mutex g_crc_mu;
+bool g_crc_uploaded[64] = {false};       // per device: __constant__ memory has one instance per GPU
 
 int upload_crc() {
-    if (g_crc_uploaded) return ICER_RESULT_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return ICER_FATAL_ERROR;
+    std::lock_guard<std::mutex> lk(g_crc_mu);
+    if (g_crc_uploaded[dev]) return ICER_RESULT_OK;
     uint32_t tab[256];
     for (uint32_t n = 0; n < 256; n++) {
         uint32_t c = n;
@@ -31,7 +37,7 @@ int upload_crc() {
         tab[n] = c;
     }
     CUDA_TRY(cudaMemcpyToSymbol(c_crc, tab, sizeof tab));
-    g_crc_uploaded = true;
+    g_crc_uploaded[dev] = true;
     return ICER_RESULT_OK;
 }
 

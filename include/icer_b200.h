@@ -100,6 +100,24 @@ int icer_b200_decompress_batch_pix(icer_b200_ctx *ctx, const icer_b200_params *p
                                    const uint64_t *stream_len, size_t n, void *frames, int pixfmt, uint32_t *dims, int32_t *rc,
                                    int mem, void *stream);
 
+/*
+ * One batch over several contexts -- normally one context per GPU of the box (frames are independent, the
+ * batch shards by frame index, context g codes frames [g*n/nctx, (g+1)*n/nctx), no exchange between devices).  The call
+ * runs one host thread per context and returns when all of them are done.  Contexts must be distinct.
+ *   mem = ICER_B200_MEM_HOST    every context moves its slice over its own PCIe link
+ *   mem = ICER_B200_MEM_DEVICE  all buffers live on the device of ctxs[0]; the other devices fetch their slice and return
+ *                               their results with peer copies over NVLink (one scatter in, one gather out)
+ * Arguments as in icer_b200_compress_batch_pix / icer_b200_decompress_batch_pix (pixfmt ICER_B200_PIX_U16 for uint16 frames).
+ * No reference counterpart (lib_icer is single-threaded, src/icer_util.c:16-32); this is the C entry point of BASELINE's
+ * "batch sharded across 8 GPUs" configuration. */
+int icer_b200_compress_batch_multi(icer_b200_ctx *const *ctxs, int nctx, const icer_b200_params *p, const void *frames, int pixfmt,
+                                   size_t n, uint8_t *out, size_t out_stride, uint64_t *size_used, int32_t *rc, int mem);
+int icer_b200_decompress_batch_multi(icer_b200_ctx *const *ctxs, int nctx, const icer_b200_params *p, const uint8_t *streams,
+                                     size_t stream_stride, const uint64_t *stream_len, size_t n, void *frames, int pixfmt,
+                                     uint32_t *dims, int32_t *rc, int mem);
+/* number of usable CUDA devices (0 if none) */
+int icer_b200_device_count(void);
+
 /* Wavelet transform only (parity hook for icer_wavelet_transform_stages_uint16 :446 / inverse :468) over a
  * batch of [n][height][width] planes, in place.  rc[n] receives ICER_INTEGER_OVERFLOW per plane (forward). */
 int icer_b200_dwt_batch_u16(icer_b200_ctx *ctx, uint16_t *planes, size_t n, uint32_t width, uint32_t height,
