@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- encode+decode throughput of the ICER hot path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2noise|c3|c4|c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2noise|c3|c4|c5|all]
 
 A "step" is one pass of the hot path over one batch of synthetic frames: batch ENCODE (forward DWT -> LL mean /
 sign-magnitude -> bit-plane context model + interleaved entropy coder -> segment assembly) followed by batch DECODE
@@ -9,10 +9,19 @@ of the streams just produced (scan -> entropy decoder -> inverse DWT).  The metr
     Mpixels/s = frames * W * H / (t_encode + t_decode) / 1e6     (whole job, all ranks).
 `value`  : inputs already resident in HBM, outputs left in HBM (device pointers through the C ABI).
 `e2e`    : the same step through the C ABI with HOST (pinned) buffers; H2D of the frames, D2H of the streams,
-           H2D of the streams and D2H of the decoded frames are all inside the timed region.
+           H2D of the streams and D2H of the decoded frames are all inside the timed region.  Two host threads with one
+           codec context each work on alternating steps (the C ABI's documented double-buffering pattern):
+           the copies of one step overlap the kernels of the other.
 N > 1    : one process per GPU (torchrun), the batch is sharded by frame index -- frames are independent, so there
            is no data-path collective (weak scaling: every rank encodes+decodes its own `batch` frames); time is the
-           max over ranks of the device-timed region.
+           max over ranks of the device-timed region.  `--single-process` instead drives all N GPUs from ONE process
+           through icer_b200_*_batch_multi (the C ABI's own multi-GPU entry point).
+
+The line's top-level keys describe BASELINE.json configs[1] (`c2`, the configuration the metric is quoted on).  The default
+run then measures the other BASELINE configurations with a bounded number of steps and reports each of them -- value, e2e,
+roofline, cpu_baseline, parity -- under `configs` (N = 1: c2noise, c3, c4, c5; N > 1: c5, the configuration BASELINE.json
+shards across the GPUs of one box).
+
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/libicer_ref*.so, lib_icer compiled with its own
 -O2 flags) on the box's host cores, one forked worker per core because lib_icer is non-re-entrant.
 """
@@ -37,11 +46,12 @@ WORKLOADS = {
                     batch=1024, w=512, h=512, chan=1, stages=6, segments=10, planes=9, max_stages=6, quota=2 * 512 * 512, kind=1, seed=20260922 + 2),
     "c3": dict(desc="batch=1024 512x512 YUV planar uint16, 4 stages, 10 segments, 9 bit planes, filter A, quota=70000 B",
                batch=1024, w=512, h=512, chan=3, stages=4, segments=10, planes=9, max_stages=6, quota=70000, kind=0, seed=20260922 + 3),
-    "c4": dict(desc="batch=64 4096x4096 12-bit-in-uint16 gray, 7 stages, 10 segments, 15 bit planes, filter A, quota=2*W*H",
-               batch=64, w=4096, h=4096, chan=1, stages=7, segments=10, planes=15, max_stages=7, quota=2 * 4096 * 4096, kind=2, seed=20260922 + 4),
+    "c4": dict(desc="batch=256 4096x4096 12-bit-in-uint16 gray, 7 stages, 10 segments, 15 bit planes, filter A, quota=2*W*H",
+               batch=256, w=4096, h=4096, chan=1, stages=7, segments=10, planes=15, max_stages=7, quota=2 * 4096 * 4096, kind=2, seed=20260922 + 4),
     "c5": dict(desc="batch=1024/GPU 1024x1024 uint8-in-uint16 gray, 6 stages, 10 segments, 9 bit planes, filter A, quota=W*H",
                batch=1024, w=1024, h=1024, chan=1, stages=6, segments=10, planes=9, max_stages=6, quota=1024 * 1024, kind=0, seed=20260922 + 5),
 }
+METRIC = "encode+decode Mpixels/s"
 
 
 def usable_cores():
@@ -67,6 +77,15 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def config_of(wl, world, frames_per_gpu):
+    """The `config` object of a line: identical for our arm and the reference arm of the same workload."""
+    n, w, h, chan = frames_per_gpu, wl["w"], wl["h"], wl["chan"]
+    return {"workload": wl["desc"], "frames_per_gpu": n,
+            "parallelism": "frames sharded across %d GPU(s), no data-path collective" % world,
+            "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (n * chan * w * h * 2 / 1e6),
+            "timing": "CUDA events on the launching stream, max over ranks"}
 
 
 class ClockSampler:
@@ -107,6 +126,25 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
 
 
+def gpu_numa_cpus(index):
+    """CPUs of the NUMA node the GPU hangs off (pinned staging buffers should be allocated and touched from there)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------------
 # CPU reference leg (the only place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------------------
@@ -131,7 +169,7 @@ def _cpu_worker(args):
         dec = ref.decompress(enc["stream"], wl["chan"], wl["w"] * wl["h"], wl["stages"], 0, wl["segments"])
         t2 = time.perf_counter()
         t_enc += t1 - t0; t_dec += t2 - t1
-        out.append((f, enc["rc"], enc["stream"], b"".join(i.tobytes() for i in dec["images"])))
+        out.append((f, enc["rc"], enc["stream"], dec["rc"], b"".join(i.tobytes() for i in dec["images"]) if dec["images"] is not None else None))
     return t_enc, t_dec, out
 
 
@@ -161,224 +199,315 @@ def frames_per_core_for(wl, target_s=6.0):
     return max(1, int(target_s / est))
 
 
-def run_reference_arm(args, wl, rank, world):
-    if rank != 0:
-        return
+def reference_line(args, wl, steps, warmup):
     fpc = frames_per_core_for(wl)
     if os.environ.get("ICER_BENCH_FRAMES_PER_CORE"):       # test hook: a shorter sample (tests/test_bench_contract_cpu.py)
         fpc = max(1, int(os.environ["ICER_BENCH_FRAMES_PER_CORE"]))
     vals = []
-    for it in range(args.warmup + args.steps):
+    for it in range(warmup + steps):
         r = cpu_reference_run(wl, fpc)
-        if it >= args.warmup:
+        if it >= warmup:
             vals.append(r)
     v = float(np.mean([r["mpix_s"] for r in vals]))
     px = vals[0]["frames"] * wl["w"] * wl["h"]
-    line = {"impl": "reference", "metric": "encode+decode Mpixels/s", "value": round(v, 3), "unit": "Mpixels/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * px / (v * 1e6), 3), "higher_is_better": True,
+    return {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "Mpixels/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(1e3 * px / (v * 1e6), 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": wl["desc"], "sample": "%d frames per step (%d per core)" % (vals[0]["frames"], fpc)},
+            "config": config_of(wl, args.gpus, wl["batch"]),
             "cpu_baseline": {"value": round(v, 3), "unit": "Mpixels/s", "cores": vals[0]["cores"], "kind": "reference",
-                             "sample": "%d frames of the workload per step, one forked lib_icer worker per core (oracle/_ref)" % vals[0]["frames"],
+                             "sample": "%d frames of the workload per step (%d per core), one forked lib_icer worker per core (oracle/_ref)"
+                                       % (vals[0]["frames"], fpc),
                              "one_core_mpix_s": round(float(np.mean([r["mpix_s_1core"] for r in vals])), 3)},
             "e2e": {"value": round(v, 3), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+
+
+def run_reference_arm(args, names, rank):
+    if rank != 0:
+        return
+    line = reference_line(args, dict(WORKLOADS[names[0]], **batch_override(args, names[0])), args.steps, args.warmup)
+    rest = []
+    for nm in names[1:]:
+        r = reference_line(args, WORKLOADS[nm], 1, 0)
+        r["name"] = nm
+        rest.append(r)
+    if rest:
+        line["configs"] = rest
     print(json.dumps(line), flush=True)
+
+
+def batch_override(args, name):
+    if not args.batch:
+        return {}
+    wl = WORKLOADS[name]
+    return {"batch": args.batch, "desc": wl["desc"].replace("batch=%d" % wl["batch"], "batch=%d" % args.batch)}
 
 
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-def run_ours(args, wl, rank, world, local_rank):
-    import torch
-    import icer_compression_b200 as icer
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    ctx = icer.IcerB200(device=local_rank, planes=wl["planes"], max_stages=wl["max_stages"])
-    n, w, h, chan, quota = wl["batch"], wl["w"], wl["h"], wl["chan"], wl["quota"]
-    params = (w, h, chan, wl["stages"], 0, wl["segments"], quota)
-    st = torch.cuda.current_stream().cuda_stream
+class Bench:
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import icer_compression_b200 as icer
+        self.torch, self.icer, self.args = torch, icer, args
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.devices = list(range(args.gpus)) if args.single_process else [local_rank]
+        torch.cuda.set_device(self.devices[0])
+        self.dev = torch.device("cuda", self.devices[0])
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.ngpu = world * len(self.devices)
 
-    frames = torch.empty((n, chan, h, w), dtype=torch.int16, device=dev)
-    if chan == 1:
-        ctx.synth_frames(frames, n, w, h, rank * n, wl["seed"], wl["kind"], st)
-    else:
-        tmp = torch.empty((n, h, w), dtype=torch.int16, device=dev)
-        for c in range(3):   # Y,U,V = generator frames f, f+1000, f+2000
-            ctx.synth_frames(tmp, n, w, h, rank * n + 1000 * c, wl["seed"], wl["kind"], st)
-            frames[:, c] = tmp
-        del tmp
-    out = torch.empty((n, quota), dtype=torch.uint8, device=dev)
-    used = torch.zeros(n, dtype=torch.int64, device=dev)
-    rc = torch.zeros(n, dtype=torch.int32, device=dev)
-    dec = torch.empty((n, chan, h * w), dtype=torch.int16, device=dev)
-    dims = torch.zeros((n, 2), dtype=torch.int32, device=dev)
-    drc = torch.zeros(n, dtype=torch.int32, device=dev)
-    torch.cuda.synchronize()
+    def barrier(self):
+        for d in self.devices:
+            self.torch.cuda.synchronize(d)
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    def step_device():
-        ctx.compress_batch_raw(params, frames, n, out, quota, None, None, used, rc, icer.MEM_DEVICE, st)
-        ctx.decompress_batch_raw(params, out, quota, used, n, dec, dims, drc, icer.MEM_DEVICE, st)
+    def max_over_ranks(self, vals):
+        from icer_compression_b200.shard import max_over_ranks
+        return max_over_ranks(vals, device=self.dev)
 
-    def barrier():
+    # ---- one workload ---------------------------------------------------------------------------------------------
+    def run(self, name, wl, steps, warmup, e2e_steps, with_cpu):
+        torch, icer = self.torch, self.icer
+        G = len(self.devices)
+        n_gpu, w, h, chan, quota = wl["batch"], wl["w"], wl["h"], wl["chan"], wl["quota"]
+        n = n_gpu * G                                   # frames this process codes per step
+        params = (w, h, chan, wl["stages"], 0, wl["segments"], quota)
+        multi = icer.IcerMulti(self.devices, planes=wl["planes"], max_stages=wl["max_stages"])
+        ctx = multi.ctxs[0]
+        dev = self.dev
+        st = torch.cuda.current_stream().cuda_stream
+        first = self.rank * n
+
+        frames = torch.empty((n, chan, h, w), dtype=torch.int16, device=dev)
+        if chan == 1:
+            ctx.synth_frames(frames, n, w, h, first, wl["seed"], wl["kind"], st)
+        else:
+            tmp = torch.empty((n, h, w), dtype=torch.int16, device=dev)
+            for c in range(3):   # Y,U,V = generator frames f, f+1000, f+2000
+                ctx.synth_frames(tmp, n, w, h, first + 1000 * c, wl["seed"], wl["kind"], st)
+                frames[:, c] = tmp
+            del tmp
+        out = torch.empty((n, quota), dtype=torch.uint8, device=dev)
+        used = torch.zeros(n, dtype=torch.int64, device=dev)
+        rc = torch.zeros(n, dtype=torch.int32, device=dev)
+        dec = torch.empty((n, chan, h * w), dtype=torch.int16, device=dev)
+        dims = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+        drc = torch.zeros(n, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
 
-    ctx.enable_timing(True)
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
-    kern_enc_ms, kern_dec_ms, enc_dwt_ms = [], [], []
-    ev[0].record()
-    for k in range(args.steps):
-        ctx.compress_batch_raw(params, frames, n, out, quota, None, None, used, rc, icer.MEM_DEVICE, st)
-        ev[2 * k + 1].record()
-        kern_enc_ms.append(ctx.phase_ms(2)); enc_dwt_ms.append(ctx.phase_ms(1))
-        ctx.decompress_batch_raw(params, out, quota, used, n, dec, dims, drc, icer.MEM_DEVICE, st)
-        ev[2 * k + 2].record()
-        kern_dec_ms.append(ctx.phase_ms(2))
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    enc_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)) / args.steps
-    dec_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)) / args.steps
-    from icer_compression_b200.shard import max_over_ranks
-    total_ms, enc_ms, dec_ms = max_over_ranks([total_ms, enc_ms, dec_ms], device=dev)   # the slowest rank defines the step
-    ms_per_step = total_ms / args.steps
-    px_step = world * n * w * h
-    value = px_step / (ms_per_step * 1e-3) / 1e6
+        # every call goes through the library's multi-context entry points (one context per GPU of this process)
+        def encode():
+            multi.compress_batch_raw(params, frames, n, out, quota, used, rc, icer.MEM_DEVICE)
 
-    used_h = used.cpu().numpy()
-    rc_h = rc.cpu().numpy()
-    drc_h = drc.cpu().numpy()
-    stream_bytes = int(used_h.sum())
-    ok_frames = int(((rc_h == 0) | (rc_h == -5)).sum())
+        def decode():
+            multi.decompress_batch_raw(params, out, quota, used, n, dec, dims, drc, icer.MEM_DEVICE)
 
-    # ---- round trip sanity on the device results (lossless workloads decode to the input) ---------------------
-    roundtrip = None
-    if (rc_h == 0).all() and wl["planes"] >= 9 and wl["kind"] in (0,):
-        roundtrip = bool(torch.equal(dec.view(n, chan, h, w), frames))
+        for c in multi.ctxs:
+            c.enable_timing(True)
+        for _ in range(warmup):
+            encode(); decode()
+        self.barrier()
+        launches0 = multi.launch_count()
+        sampler = ClockSampler(self.devices[0])
+        if self.rank == 0:
+            sampler.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+        kern_enc_ms, kern_dec_ms, enc_dwt_ms, dec_dwt_ms = [], [], [], []
+        ev[0].record()
+        for k in range(steps):
+            encode()
+            ev[2 * k + 1].record()
+            kern_enc_ms.append(ctx.phase_ms(2)); enc_dwt_ms.append(ctx.phase_ms(1))
+            decode()
+            ev[2 * k + 2].record()
+            kern_dec_ms.append(ctx.phase_ms(2)); dec_dwt_ms.append(ctx.phase_ms(1))
+        self.barrier()
+        clocks = sampler.stop() if self.rank == 0 else None
+        launches = multi.launch_count() - launches0
+        total_ms = ev[0].elapsed_time(ev[-1])
+        enc_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(steps)) / steps
+        dec_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(steps)) / steps
+        total_ms, enc_ms, dec_ms = self.max_over_ranks([total_ms, enc_ms, dec_ms])   # the slowest rank defines the step
+        ms_per_step = total_ms / steps
+        px_step = self.world * n * w * h
+        value = px_step / (ms_per_step * 1e-3) / 1e6
+        for c in multi.ctxs:
+            c.enable_timing(False)
 
-    # ---- end to end through the C ABI with host buffers ---------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        fh = torch.empty((n, chan, h, w), dtype=torch.int16).pin_memory()
-        fh.copy_(frames)
-        oh = torch.empty((n, quota), dtype=torch.uint8).pin_memory()
-        uh = torch.zeros(n, dtype=torch.int64)
-        rh = torch.zeros(n, dtype=torch.int32)
-        dh = torch.empty((n, chan, h * w), dtype=torch.int16).pin_memory()
-        dimh = torch.zeros((n, 2), dtype=torch.int32)
-        drh = torch.zeros(n, dtype=torch.int32)
+        used_h = used.cpu().numpy()
+        rc_h = rc.cpu().numpy()
+        drc_h = drc.cpu().numpy()
+        stream_bytes = int(used_h.sum())
+        ok_frames = int(((rc_h == 0) | (rc_h == -5)).sum())
+        roundtrip = None
+        if (rc_h == 0).all() and wl["kind"] in (0, 2) and wl["planes"] >= (9 if wl["kind"] == 0 else 13):
+            roundtrip = bool(torch.equal(dec.view(n, chan, h, w), frames))      # lossless workloads decode to the input
 
-        def step_host():
-            ctx.compress_batch_raw(params, fh, n, oh, quota, None, None, uh, rh, icer.MEM_HOST, st)
-            ctx.decompress_batch_raw(params, oh, quota, uh, n, dh, dimh, drh, icer.MEM_HOST, st)
+        # ---- CPU baseline on a bounded sample of the same workload + bit-exactness of that sample (rank 0) -----------------
+        cpu_baseline = parity = None
+        if with_cpu and self.rank == 0:
+            fpc = frames_per_core_for(wl, 5.0)
+            cores = usable_cores()
+            while cores * fpc > n and fpc > 1:
+                fpc -= 1
+            cores = min(cores, n)
+            r = cpu_reference_run(wl, fpc, cores=cores, keep=True)
+            idx = sorted(o[0] for o in r["outs"])
+            out_h = out[idx].cpu().numpy()
+            dec_h = dec[idx].cpu().numpy()
+            bad = 0
+            for f, rrc, rstream, rdrc, rdec in r["outs"]:     # encode status + stream bytes, decode status + the REFERENCE'S decoded samples
+                j = idx.index(f)
+                ln = int(used_h[f])
+                if rrc != int(rc_h[f]) or bytes(out_h[j, :ln]) != rstream or rdrc != int(drc_h[f]) or (rdec is not None and dec_h[j].tobytes() != rdec):
+                    bad += 1
+            cpu_baseline = {"value": round(r["mpix_s"], 3), "unit": "Mpixels/s", "cores": r["cores"], "kind": "reference",
+                            "sample": "%d frames of the workload (%d per core), lib_icer compiled -O2 (oracle/_ref), one forked worker per core"
+                                      % (r["frames"], fpc), "one_core_mpix_s": round(r["mpix_s_1core"], 3)}
+            parity = {"frames_checked": len(r["outs"]), "mismatches": bad, "against": "oracle/_ref (unmodified lib_icer): encode rc + stream "
+                      "bytes, decode rc + decoded samples"}
+        if self.dist is not None:
+            self.dist.barrier()
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_host()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ksteps = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(ksteps):
-            step_host()
-        e1.record()
-        torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t0) * 1e3 / ksteps
-        ev_ms = e0.elapsed_time(e1) / ksteps
-        e2e_ms = max(wall_ms, ev_ms)
-        e2e_ms = max_over_ranks([e2e_ms], device=dev)[0]
-        sb = int(uh.sum().item())
-        e2e = {"value": round(px_step / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mpixels/s", "ms_per_step": round(e2e_ms, 3),
-               "h2d_bytes_per_step": int(n * chan * h * w * 2 + n * quota), "d2h_bytes_per_step": int(sb + n * chan * h * w * 2),
-               "note": "host pinned frames -> C ABI -> host streams -> C ABI -> host frames; stream slots are uploaded whole (n*quota), only used bytes come back"}
-        del fh, oh, dh
+        # ---- end to end through the C ABI with host buffers ---------------------------------------------------------------
+        e2e = None
+        if e2e_steps > 0:
+            e2e = self.run_e2e(name, wl, multi, frames, params, e2e_steps, px_step)
+        multi.close()
 
-    if rank != 0:
-        return
-    # ---- roofline of the dominant kernel -------------------------------------------------------------------
-    # The step is dominated by the two coder kernels; whichever took longer is reported as THE roofline object, the
-    # other one under roofline_other.  Algorithmic bytes: K4 = coefficients read once + streams written
-    # once; K7 = streams read once + coefficients written once (the same number).
-    peak, peak_src = measured_peak_gbs()
-    alg_bytes = n * chan * w * h * 2 + stream_bytes
-    k4_ms = float(np.mean(kern_enc_ms))
-    k7_ms = float(np.mean(kern_dec_ms))
-    step_bytes = 2 * (n * chan * w * h * 2 + stream_bytes)       # encode: in + stream ; decode: stream + out
-    traffic = {}
-    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
-    if os.path.exists(tp):
+        peak, peak_src = measured_peak_gbs()
+        alg_bytes = n * chan * w * h * 2 + stream_bytes                 # per process = per launch set
+        k4_ms, k7_ms = float(np.mean(kern_enc_ms)), float(np.mean(kern_dec_ms))
+        step_bytes = 2 * alg_bytes                                       # encode: in + stream ; decode: stream + out
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(name, {})
+            except Exception:
+                traffic = {}
+        alg1 = alg_bytes // G                                            # one GPU's launch
+
+        def roof(kname, desc, ms):
+            ach = alg1 / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            return {"bound": "hbm", "kernel": desc, "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
+                    "traffic": traffic.get(kname), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg1, "kernel_ms": round(ms, 3)}
+
+        r_enc = roof("k_encode", "k_encode (bit-plane context model + interleaved entropy coder)", k4_ms)
+        r_dec = roof("k_decode", "k_decode (bit-plane context model + interleaved entropy decoder)", k7_ms)
+        roofline, roofline_other = (r_dec, r_enc) if k7_ms >= k4_ms else (r_enc, r_dec)
+        roofline["encode_dwt_ms"] = round(float(np.mean(enc_dwt_ms)), 3)
+        roofline["decode_dwt_ms"] = round(float(np.mean(dec_dwt_ms)), 3)
+        roofline["step_frac"] = round(step_bytes / G / (ms_per_step * 1e-3) / 1e9 / peak, 5)
+        roofline["note"] = "instruction-issue bound integer kernels: the HBM fraction is reported as the contract asks, it is not the limiter"
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": self.ngpu, "steps": steps,
+            "warmup": warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": config_of(wl, self.ngpu, n_gpu),
+            "encode_mpix_s": round(px_step / (enc_ms * 1e-3) / 1e6, 2), "decode_mpix_s": round(px_step / (dec_ms * 1e-3) / 1e6, 2),
+            "encode_ms": round(enc_ms, 3), "decode_ms": round(dec_ms, 3),
+            # a planar Y,U,V frame counts w*h pixels but 3*w*h samples: both are reported
+            "samples_per_pixel": chan, "value_msamples_s": round(value * chan, 2),
+            "compressed_bytes_per_step": stream_bytes, "frames_ok": ok_frames, "decode_rc_ok": int((drc_h == 0).sum()),
+            "roundtrip_lossless": roundtrip,
+            "roofline": roofline, "roofline_other": roofline_other,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if self.args.single_process:
+            line["config"]["parallelism"] = "ONE process drives %d GPU(s) through icer_b200_*_batch_multi (frames sharded by index, peer scatter/gather from device 0)" % G
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+            line["parity"] = parity
+        del frames, out, dec
+        torch.cuda.empty_cache()
+        return line
+
+    # ---- e2e: host buffers, two workers on alternating steps ----------------------------------------------------------
+    def run_e2e(self, name, wl, multi, frames, params, ksteps, px_step):
+        torch, icer = self.torch, self.icer
+        n, chan, h, w = frames.shape
+        quota = wl["quota"]
+        big = n * chan * h * w * 2 > (3 << 30)
+        nworkers = 1 if (big or len(self.devices) > 1 or self.args.e2e_workers < 2) else 2
+        old_aff = os.sched_getaffinity(0)
+        cpus = gpu_numa_cpus(self.devices[0]) if len(self.devices) == 1 else None
+        if cpus:
+            os.sched_setaffinity(0, cpus)          # pinned staging memory gets allocated and first-touched on the GPU's NUMA node
         try:
-            traffic = json.load(open(tp))
-        except Exception:
-            traffic = {}
+            fh = torch.empty((n, chan, h, w), dtype=torch.int16).pin_memory()
+            fh.copy_(frames)
+            workers = []
+            for k in range(nworkers):
+                m = multi if k == 0 else icer.IcerMulti(self.devices, planes=wl["planes"], max_stages=wl["max_stages"])
+                workers.append(dict(m=m, oh=torch.empty((n, quota), dtype=torch.uint8).pin_memory(), uh=torch.zeros(n, dtype=torch.int64),
+                                    rh=torch.zeros(n, dtype=torch.int32), dh=torch.empty((n, chan, h * w), dtype=torch.int16).pin_memory(),
+                                    dimh=torch.zeros((n, 2), dtype=torch.int32), drh=torch.zeros(n, dtype=torch.int32)))
 
-    def roof(name, desc, ms):
-        ach = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return {"bound": "hbm", "kernel": desc, "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
-                "traffic": traffic.get(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(ms, 3)}
+            def step_host(wk):
+                wk["m"].compress_batch_raw(params, fh, n, wk["oh"], quota, wk["uh"], wk["rh"], icer.MEM_HOST)
+                wk["m"].decompress_batch_raw(params, wk["oh"], quota, wk["uh"], n, wk["dh"], wk["dimh"], wk["drh"], icer.MEM_HOST)
 
-    r_enc = roof("k_encode", "k_encode (bit-plane context model + interleaved entropy coder)", k4_ms)
-    r_dec = roof("k_decode", "k_decode (bit-plane context model + interleaved entropy decoder)", k7_ms)
-    roofline, roofline_other = (r_dec, r_enc) if k7_ms >= k4_ms else (r_enc, r_dec)
-    roofline["encode_dwt_ms"] = round(float(np.mean(enc_dwt_ms)), 3)
-    roofline["step_frac"] = round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 5)
-    roofline["note"] = "instruction-issue bound integer kernels: the HBM fraction is reported as the contract asks, it is not the limiter"
-    line = {
-        "metric": "encode+decode Mpixels/s", "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": wl["desc"], "frames_per_gpu": n, "parallelism": "frames sharded across %d GPU(s), no data-path collective" % world,
-                   "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (n * chan * w * h * 2 / 1e6),
-                   "timing": "CUDA events on the launching stream, max over ranks"},
-        "encode_mpix_s": round(px_step / (enc_ms * 1e-3) / 1e6, 2), "decode_mpix_s": round(px_step / (dec_ms * 1e-3) / 1e6, 2),
-        "encode_ms": round(enc_ms, 3), "decode_ms": round(dec_ms, 3),
-        # a planar Y,U,V frame counts w*h pixels but 3*w*h samples: both are reported
-        "samples_per_pixel": chan, "value_msamples_s": round(value * chan, 2),
-        "compressed_bytes_per_step": stream_bytes, "frames_ok": ok_frames, "decode_rc_ok": int((drc_h == 0).sum()),
-        "roundtrip_lossless": roundtrip,
-        "roofline": roofline, "roofline_other": roofline_other,
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-    }
-    # ---- CPU baseline on a bounded sample of the same workload + bit-exactness of that sample -------------------
-    if world == 1 and not args.no_cpu:
-        fpc = frames_per_core_for(wl, 5.0)
-        cores = usable_cores()
-        while cores * fpc > n and fpc > 1:
-            fpc -= 1
-        cores = min(cores, n)
-        r = cpu_reference_run(wl, fpc, cores=cores, keep=True)
-        # parity: the frames the reference just coded vs what the GPU produced for the same frame indices
-        idx = sorted(o[0] for o in r["outs"])
-        out_h = out[idx].cpu().numpy()
-        dec_h = dec[idx].cpu().numpy()
-        bad = 0
-        for f, rrc, rstream, rdec in r["outs"]:
-            j = idx.index(f)
-            ln = int(used_h[f])
-            if rrc != int(rc_h[f]) or bytes(out_h[j, :ln]) != rstream or dec_h[j].tobytes() != rdec:
-                bad += 1
-        line["cpu_baseline"] = {"value": round(r["mpix_s"], 3), "unit": "Mpixels/s", "cores": r["cores"], "kind": "reference",
-                                "sample": "%d frames of the workload (%d per core), lib_icer compiled -O2 (oracle/_ref), one forked worker per core"
-                                          % (r["frames"], fpc), "one_core_mpix_s": round(r["mpix_s_1core"], 3)}
-        line["parity"] = {"frames_checked": len(r["outs"]), "mismatches": bad, "against": "oracle/_ref (unmodified lib_icer)"}
-    print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+            def run_steps(count):
+                # worker k takes steps k, k + nworkers, ...; the ctypes calls release the GIL
+                def loop(k):
+                    for _ in range(k, count, nworkers):
+                        step_host(workers[k])
+                th = [threading.Thread(target=loop, args=(k,)) for k in range(1, nworkers)]
+                for t in th:
+                    t.start()
+                loop(0)
+                for t in th:
+                    t.join()
+
+            run_steps(max(nworkers, min(self.args.warmup, 2)))
+            self.barrier()
+            ksteps = max(ksteps, nworkers)
+            t0 = time.perf_counter()
+            run_steps(ksteps)
+            for d in self.devices:
+                torch.cuda.synchronize(d)
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / ksteps
+            e2e_ms = self.max_over_ranks([e2e_ms])[0]
+            ok = all(bool(torch.equal(wk["dh"], workers[0]["dh"])) and bool(torch.equal(wk["uh"], workers[0]["uh"])) for wk in workers[1:])
+            sb = int(workers[0]["uh"].sum().item())
+            res = {"value": round(px_step / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mpixels/s", "ms_per_step": round(e2e_ms, 3), "steps": ksteps,
+                   "h2d_bytes_per_step": int(n * chan * h * w * 2 + sb), "d2h_bytes_per_step": int(sb + n * chan * h * w * 2),
+                   "host_workers": nworkers, "workers_agree": ok,
+                   "note": "host pinned frames -> C ABI -> host streams -> C ABI -> host frames, wall clock over all steps; %s; only the used bytes "
+                           "of every stream slot cross PCIe" % ("%d host threads with one context each work on alternating steps, so the copies of one "
+                           "step overlap the kernels of the other" % nworkers if nworkers > 1 else "one host thread")}
+            for wk in workers[1:]:
+                wk["m"].close()
+            return res
+        finally:
+            os.sched_setaffinity(0, old_aff)
+
+
+def run_ours(args, names, rank, world, local_rank):
+    b = Bench(args, rank, world, local_rank)
+    head = dict(WORKLOADS[names[0]], **batch_override(args, names[0]))
+    line = b.run(names[0], head, args.steps, args.warmup, 0 if args.no_e2e else max(2, min(args.steps, 6)), not args.no_cpu)
+    rest = []
+    for nm in names[1:]:
+        wl = WORKLOADS[nm]
+        r = b.run(nm, wl, max(1, min(args.steps, 3)), max(1, min(args.warmup, 3)), 0 if args.no_e2e else 2, not args.no_cpu)
+        r["name"] = nm
+        rest.append(r)
+    if rank == 0:
+        if rest:
+            line["configs"] = rest
+        print(json.dumps(line), flush=True)
+    if b.dist is not None:
+        b.dist.destroy_process_group()
 
 
 def main():
@@ -387,25 +516,30 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None)
-    ap.add_argument("--batch", type=int, default=None, help="override frames per GPU")
+    ap.add_argument("--workload", default=None, help="one of %s, or 'all'; default: c2 as the headline + the other BASELINE configs under `configs`" % ", ".join(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="override frames per GPU of the headline workload")
+    ap.add_argument("--single-process", action="store_true", help="drive all --gpus devices from this one process through icer_b200_*_batch_multi")
+    ap.add_argument("--e2e-workers", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--watchdog", type=float, default=600.0, help="dump every Python stack and exit if the run takes longer than this many seconds")
+    ap.add_argument("--watchdog", type=float, default=1500.0, help="dump every Python stack and exit if the run takes longer than this many seconds")
     args = ap.parse_args()
     import faulthandler
     faulthandler.dump_traceback_later(args.watchdog, exit=True)     # a stalled run must not hold a GPU box until the outer limit
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = dict(WORKLOADS[args.workload or "c2"])
-    if args.batch:
-        wl["batch"] = args.batch
-        wl["desc"] = wl["desc"].replace("batch=1024", "batch=%d" % args.batch)
-    if args.impl == "reference":
-        run_reference_arm(args, wl, rank, world)
+    if args.workload in (None, "all"):
+        # the headline + the rest of BASELINE.json's configurations: everything that runs on one GPU at N = 1, config 5 at N > 1
+        names = ["c2", "c2noise", "c3", "c4", "c5"] if args.gpus == 1 else ["c2", "c5"]
     else:
-        run_ours(args, wl, rank, world, local_rank)
+        names = [args.workload]
+    if args.impl == "reference":
+        if args.workload is None:
+            names = ["c2"] if args.gpus == 1 else ["c2", "c5"]      # the reference arm of the headline (+ config 5 when the job is sharded)
+        run_reference_arm(args, names, rank)
+    else:
+        run_ours(args, names, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -48,6 +48,12 @@ struct icer_b200_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float phase_ms[4] = {0, 0, 0, 0};
     size_t workspace_budget = (size_t) 64 << 30;
+    // priority-prefix encoding: statistics of the last quota walk (pinned, read lazily), the plan / quota they belong to
+    uint32_t *h_stat = nullptr;
+    cudaEvent_t ev_stat = nullptr;
+    Plan *stat_plan = nullptr;
+    uint64_t stat_quota = 0;
+    uint32_t force_prefix = 0;        // ICER_B200_FORCE_PREFIX=n: always code the first n streams of the priority order first (tests)
     // host-buffer pipeline: chunks of `pipe_chunk` frames, H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i
     bool bulk_copy = true;        // strided bulk copies (one cudaMemcpy2DAsync per direction) on the host paths; ICER_B200_BULK_COPY=0 falls back to one copy per frame
     size_t pipe_chunk = 0;        // 0 = off (default): on B200 the per-chunk kernel tails cost more than the overlap saves; ICER_B200_PIPE_CHUNK=n enables it
@@ -64,6 +70,7 @@ Plan *get_plan(icer_b200_ctx *c, uint32_t w, uint32_t h, uint32_t chan, uint32_t
     auto it = c->plans.find(key);
     if (it != c->plans.end()) return it->second;
     if (c->plans.size() > 64) {   // keep the cache bounded
+        c->stat_plan = nullptr;
         for (auto &kv : c->plans) { free_plan_device(*kv.second); delete kv.second; }
         c->plans.clear();
     }
@@ -126,6 +133,7 @@ int icer_b200_create(icer_b200_ctx **out, int device) {
     c->device = device;
     { const char *pc = getenv("ICER_B200_PIPE_CHUNK"); if (pc) c->pipe_chunk = (size_t) atol(pc); }
     { const char *bc = getenv("ICER_B200_BULK_COPY"); if (bc) c->bulk_copy = atoi(bc) != 0; }
+    { const char *fp = getenv("ICER_B200_FORCE_PREFIX"); if (fp) c->force_prefix = (uint32_t) atoi(fp); }
     const char *gb = getenv("ICER_B200_WORKSPACE_GB");
     if (gb && atof(gb) > 0) c->workspace_budget = (size_t) (atof(gb) * (double) ((size_t) 1 << 30));
     *out = c;
@@ -150,10 +158,13 @@ void icer_b200_destroy(icer_b200_ctx *c) {
     if (c->cs_out) cudaStreamDestroy(c->cs_out);
     if (c->cs_own) cudaStreamDestroy(c->cs_own);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->ev_stat) cudaEventDestroy(c->ev_stat);
+    if (c->h_stat) cudaFreeHost(c->h_stat);
     delete c;
 }
 
 static void drop_plans(icer_b200_ctx *c) {
+    c->stat_plan = nullptr;
     for (auto &kv : c->plans) { free_plan_device(*kv.second); delete kv.second; }
     c->plans.clear();
 }
@@ -335,6 +346,22 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
     }
     const size_t plane_px = (size_t) w * h, frame_px = plane_px * chan;
     if (c->ring_threads == 0) c->ring_threads = encode_resident_threads(c->device);
+    if (c->stat_plan && c->ev_stat && cudaEventQuery(c->ev_stat) == cudaSuccess) {
+        // the previous batch's quota walk: if its frames kept well under 3/4 of their streams, the next batch of that shape and quota
+        // codes a prefix (what was kept + 1/8 + 32 streams) first
+        Plan *sp = c->stat_plan;
+        c->stat_plan = nullptr;
+        bool alive = false;
+        for (auto &kv : c->plans) alive = alive || kv.second == sp;
+        if (alive) {
+            const uint32_t kept = c->h_stat[0];
+            const uint64_t want = (uint64_t) kept + kept / 8 + 32;
+            sp->enc_prefix = (want * 4 < (uint64_t) sp->nstreams * 3) ? (uint32_t) want : 0;
+            sp->enc_prefix_quota = c->stat_quota;
+        }
+    } else if (c->stat_plan) {
+        (void) cudaGetLastError();
+    }
 
     ev_record(c, 0, st);
     float ms_dwt = 0, ms_enc = 0, ms_asm = 0;
@@ -346,6 +373,10 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
                                  (size_t) pl->nstreams * 24 + (host ? out_stride * (out_prio ? 2 : 1) : 0) + 64;
         size_t nb = std::max<size_t>(1, c->workspace_budget / per_frame);
         if (nb > 32) nb &= ~(size_t) 31;             // whole coder groups
+        if (nb < n - done) {                         // several chunks: equal ones (a short last chunk pays the coder's serial tail alone)
+            const size_t chunks = (n - done + nb - 1) / nb;
+            nb = std::min(nb, (((n - done + chunks - 1) / chunks) + 31) & ~(size_t) 31);
+        }
         nb = std::min(nb, n - done);
         int e;
         uint32_t ngroups = 0;
@@ -415,8 +446,10 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
             CUDA_TRY(cudaMemcpyAsync(d_coefs, d_in, nb * frame_px * 2, cudaMemcpyDeviceToDevice, st));
             if ((e = launch_dwt_forward(d_coefs, c->tmp.as<uint16_t>(), nb * chan, w, h, p->stages, p->filter, c->ovf.as<int>(), st, c->ls, native8))) return e;
         }
+        // sign-magnitude is applied on the way into the coder's layout unless the caller wants the planar coefficients back
+        const bool fuse_sm = !native8 && !coefs_out && frames_to_T_fuses_signmag(d_coefs, c->tmp.as<uint16_t>(), w, h);
         if ((e = launch_ll_mean_signmag(d_coefs, nb * chan, w, h, (uint32_t) dim_low(w, p->stages), (uint32_t) dim_low(h, p->stages),
-                                        c->mean.as<uint16_t>(), c->ovf.as<int>(), st, c->ls, native8))) return e;
+                                        c->mean.as<uint16_t>(), c->ovf.as<int>(), st, c->ls, native8, fuse_sm))) return e;
         if (coefs_out && !native8) if ((e = copy_out(coefs_out + done * frame_px, d_coefs, nb * frame_px * 2, mem, st))) return e;
         if (coefs_out && native8) {     // the uint8 codec leaves 8-bit sign-magnitude coefficients behind
             if ((e = c->pix.ensure(nb * frame_px))) return e;
@@ -425,37 +458,87 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
         }
         // frame-interleave the coefficients for the coder (lane = frame); the wavelet scratch is free again
         uint16_t *d_T = c->tmp.as<uint16_t>();
-        if ((e = launch_frames_to_T(d_coefs, d_T, (uint32_t) nb, ngroups, chan, w, h, st, c->ls))) return e;
+        if ((e = launch_frames_to_T(d_coefs, d_T, (uint32_t) nb, ngroups, chan, w, h, st, c->ls, fuse_sm))) return e;
         ev_record(c, 2, st);
-        // entropy coder, retried with a larger payload scratch in the (rare) case a stream outgrows its slot
-        for (; pl->enc_status == ICER_RESULT_OK;) {
+        // entropy coder + segment assembly.
+        //  * a stream that outgrows its payload slot (rare) restarts the coder with a larger scratch budget;
+        //  * priority-prefix encoding: with a byte quota far below the lossless size most streams are coded only to be dropped by
+        //    the quota walk (lib_icer itself stops coding at the first packet that does not fit, icer_compress.c:404-406).  When the
+        //    previous batch of this shape kept only a fraction of its streams, the coder first produces a prefix of the priority
+        //    order, the quota walk tells whether any frame wants more, and only then the rest is coded.  Results do not depend
+        //    on the prefix length (tests/test_gpu_parity.py::test_priority_prefix_encoding).
+        uint32_t *d_stat = c->misc.as<uint32_t>() + 8;
+        AssembleArgs aa;
+        auto fill_aa = [&]() {
+            aa.nframes = (uint32_t) nb; aa.nstreams = pl->nstreams; aa.planes = pl->planes; aa.chan = chan; aa.w = w; aa.h = h;
+            aa.units = pl->d_units; aa.prio = pl->d_prio; aa.rearr = pl->d_rearr; aa.soff = pl->d_soff; aa.scratch_words = pl->scratch_words;
+            aa.scratch = c->scratch.as<uint32_t>(); aa.bits = c->bits.as<uint32_t>(); aa.crc = c->crc.as<uint32_t>();
+            aa.mean = c->mean.as<uint16_t>(); aa.ovf = c->ovf.as<int>(); aa.plan_status = pl->enc_status; aa.quota = p->byte_quota;
+            aa.out = d_out; aa.out_stride = out_stride; aa.out_prio = d_prio; aa.size_used = d_used; aa.rc = d_rc;
+            aa.keep = c->keep.as<uint32_t>(); aa.off_prio = c->offp.as<uint64_t>(); aa.off_rearr = c->offr.as<uint64_t>();
+            aa.stat = d_stat; aa.limit = pl->nstreams; aa.phase = 0;
+        };
+        // run the coder over list[lo, hi) of the plan's prefix / remainder lists (nullptr = every stream); returns the overflow flag
+        auto run_coder = [&](const uint32_t *list, uint32_t nlist, int *ovf) -> int {
             if ((e = c->scratch.ensure(nb * pl->scratch_words * 4))) return e;
-            CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 64, st));
+            CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 32, st));      // work counter + overflow flag (the quota statistics live behind them)
             EncodeArgs ea;
             ea.coefsT = d_T; ea.nframes = (uint32_t) nb; ea.ngroups = ngroups; ea.w = w; ea.h = h; ea.chan = chan; ea.planes = pl->planes;
             ea.units = pl->d_units; ea.nunits = (uint32_t) pl->units.size(); ea.soff = pl->d_soff; ea.scap = pl->d_scap;
             ea.scratch_words = pl->scratch_words; ea.scratch = c->scratch.as<uint32_t>(); ea.bits = c->bits.as<uint32_t>();
             ea.rings = c->rings.as<uint16_t>(); ea.nring_threads = c->ring_threads;
             ea.work_counter = c->misc.as<unsigned long long>(); ea.overflow = c->misc.as<int>() + 4;
+            ea.list = list; ea.nlist = nlist;
             if ((e = launch_encode(ea, st, c->ls))) return e;
-            int ovf = 0;
-            CUDA_TRY(cudaMemcpyAsync(&ovf, c->misc.as<int>() + 4, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(ovf, c->misc.as<int>() + 4, 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            if (!ovf) break;
+            return ICER_RESULT_OK;
+        };
+        static const bool no_prefix = getenv("ICER_B200_NO_PREFIX") != nullptr;
+        for (bool coded = false; !coded && pl->enc_status == ICER_RESULT_OK;) {
+            uint32_t prefix = 0;
+            if (!no_prefix && pl->enc_prefix && pl->enc_prefix < pl->nstreams && pl->enc_prefix_quota == p->byte_quota && p->byte_quota < ((uint64_t) 1 << 28))
+                prefix = pl->enc_prefix;
+            if (c->force_prefix && c->force_prefix < pl->nstreams && p->byte_quota < ((uint64_t) 1 << 28)) prefix = c->force_prefix;     // test hook
+            int ovf = 0;
+            if (!prefix) {
+                if ((e = run_coder(nullptr, 0, &ovf))) return e;
+            } else {
+                if ((e = upload_prefix_lists(*pl, prefix, st))) return e;
+                CUDA_TRY(cudaMemsetAsync(c->bits.p, 0xF0, nb * pl->nstreams * 4, st));      // ICER_BITS_NOT_CODED everywhere
+                if ((e = run_coder(pl->d_list, prefix, &ovf))) return e;
+                if (!ovf) {
+                    // does any frame keep the whole prefix?  then it may keep more: code the remainder as well
+                    fill_aa();
+                    aa.limit = prefix; aa.phase = 1;
+                    CUDA_TRY(cudaMemsetAsync(d_stat, 0, 8, st));
+                    if ((e = launch_assemble(aa, st, c->ls))) return e;
+                    uint32_t stat[2] = {0, 0};
+                    CUDA_TRY(cudaMemcpyAsync(stat, d_stat, 8, cudaMemcpyDeviceToHost, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    if (stat[1]) { if ((e = run_coder(pl->d_list + prefix, pl->nstreams - prefix, &ovf))) return e; }
+                }
+            }
+            if (!ovf) { coded = true; break; }
             if (c->scratch_bits >= 24) { fprintf(stderr, "[icer_b200] payload scratch overflow at the worst-case bound\n"); return ICER_FATAL_ERROR; }
             c->scratch_bits = std::min(24, c->scratch_bits * 2);
+            const uint32_t keep_prefix = pl->enc_prefix; const uint64_t keep_q = pl->enc_prefix_quota;
             pl = get_plan(c, w, h, chan, p->stages, p->segments, native8);
             if (pl->status != ICER_RESULT_OK) return ICER_FATAL_ERROR;
+            pl->enc_prefix = keep_prefix; pl->enc_prefix_quota = keep_q;
         }
         ev_record(c, 3, st);
-        AssembleArgs aa;
-        aa.nframes = (uint32_t) nb; aa.nstreams = pl->nstreams; aa.planes = pl->planes; aa.chan = chan; aa.w = w; aa.h = h;
-        aa.units = pl->d_units; aa.prio = pl->d_prio; aa.rearr = pl->d_rearr; aa.soff = pl->d_soff; aa.scratch_words = pl->scratch_words;
-        aa.scratch = c->scratch.as<uint32_t>(); aa.bits = c->bits.as<uint32_t>(); aa.crc = c->crc.as<uint32_t>();
-        aa.mean = c->mean.as<uint16_t>(); aa.ovf = c->ovf.as<int>(); aa.plan_status = pl->enc_status; aa.quota = p->byte_quota;
-        aa.out = d_out; aa.out_stride = out_stride; aa.out_prio = d_prio; aa.size_used = d_used; aa.rc = d_rc;
-        aa.keep = c->keep.as<uint32_t>(); aa.off_prio = c->offp.as<uint64_t>(); aa.off_rearr = c->offr.as<uint64_t>();
+        fill_aa();
+        CUDA_TRY(cudaMemsetAsync(d_stat, 0, 8, st));
         if ((e = launch_assemble(aa, st, c->ls))) return e;
+        // learn the prefix for the next batch of this shape and quota from how many streams the frames kept (read lazily: the copy is
+        // consumed at the start of the next call)
+        if (pl->enc_status == ICER_RESULT_OK && !no_prefix) {
+            if (!c->h_stat) { CUDA_TRY(cudaMallocHost((void **) &c->h_stat, 16)); CUDA_TRY(cudaEventCreateWithFlags(&c->ev_stat, cudaEventDisableTiming)); }
+            CUDA_TRY(cudaMemcpyAsync(c->h_stat, d_stat, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaEventRecord(c->ev_stat, st));
+            c->stat_plan = pl; c->stat_quota = p->byte_quota;
+        }
         ev_record(c, 4, st);
         if (host) {
             CUDA_TRY(cudaMemcpyAsync(size_used + done, d_used, nb * 8, cudaMemcpyDeviceToHost, st));
@@ -744,11 +827,24 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         ev_record(c, 3, st);
         // 4. back to planar frames (from sign-magnitude, + LL mean), inverse wavelet, clamp
         const uint32_t llw = (uint32_t) dim_low(w, p->stages), llh = (uint32_t) dim_low(h, p->stages);
-        if ((e = launch_T_to_frames(d_T, d_frames, c->frame_ok.as<int32_t>(), c->mean.as<uint16_t>(), ngroups, chan, w, h, cap_px,
+        const bool dense = plane_px == cap_px;
+        static const bool no_tma = getenv("ICER_B200_NO_TMA") != nullptr;
+        bool fused = false;
+        if (!native8 && !no_tma && dense && g.second.size() == n && p->filter == ICER_FILTER_A) {
+            // fused inverse stages (TMA-staged sub-band tiles): coefficients go to their own planar buffer, the intermediate LL regions
+            // ping-pong between the (now free) T buffer and `fin`, the last stage writes the caller-visible planes
+            if ((e = c->tmp2.ensure(n * chan * plane_px * 2))) return e;
+            if ((e = c->fin.ensure(n * chan * plane_px * 2))) return e;
+            fused = dwt_inverse_fused_applicable(c->tmp2.p, d_frames, w, h, p->stages, p->filter) && ((uintptr_t) c->fin.p % 16) == 0;
+        }
+        uint16_t *d_planar = fused ? c->tmp2.as<uint16_t>() : d_frames;
+        if ((e = launch_T_to_frames(d_T, d_planar, c->frame_ok.as<int32_t>(), c->mean.as<uint16_t>(), ngroups, chan, w, h, cap_px,
                                     llw, llh, st, c->ls, native8))) return e;
         if (native8 && (e = ensure_perms8(c, w, h, p->stages))) return e;
-        const bool dense = plane_px == cap_px;
-        if (dense && g.second.size() == n) {
+        if (fused) {
+            if ((e = launch_dwt_inverse_fused(d_planar, c->tmp.as<uint16_t>(), c->fin.as<uint16_t>(), d_frames, n * chan, w, h, p->stages,
+                                              p->filter, true, st, c->ls))) return e;
+        } else if (dense && g.second.size() == n) {
             if ((e = launch_dwt_inverse(d_frames, c->tmp.as<uint16_t>(), n * chan, w, h, p->stages, p->filter, true, st, c->ls, native8, &c->perms8))) return e;
         } else {
             for (size_t i : g.second)
@@ -1006,6 +1102,13 @@ int icer_b200_dwt_batch_u16(icer_b200_ctx *c, uint16_t *planes, size_t n, uint32
         if ((e = c->tmp2.ensure(n * ps * 2))) return e;
         if ((e = launch_dwt_forward_fused(d, ps, c->coefs.as<uint16_t>(), c->tmp.as<uint16_t>(), c->tmp2.as<uint16_t>(), n, width, height, stages,
                                           filter, c->ovf.as<int>(), st, c->ls))) return e;
+        CUDA_TRY(cudaMemcpyAsync(d, c->coefs.p, n * ps * 2, cudaMemcpyDeviceToDevice, st));
+        e = ICER_RESULT_OK;
+    } else if (inverse && !no_tma && !c->coefs.ensure(n * ps * 2) && !c->tmp2.ensure(n * ps * 2) &&
+               dwt_inverse_fused_applicable(d, c->coefs.p, width, height, stages, filter) && ((uintptr_t) c->tmp.p % 16) == 0 && ((uintptr_t) c->tmp2.p % 16) == 0) {
+        // same fused TMA path as the decoder; the result replaces the input planes
+        if ((e = launch_dwt_inverse_fused(d, c->tmp.as<uint16_t>(), c->tmp2.as<uint16_t>(), c->coefs.as<uint16_t>(), n, width, height, stages, filter,
+                                          false, st, c->ls))) return e;
         CUDA_TRY(cudaMemcpyAsync(d, c->coefs.p, n * ps * 2, cudaMemcpyDeviceToDevice, st));
         e = ICER_RESULT_OK;
     } else if (inverse) e = launch_dwt_inverse(d, c->tmp.as<uint16_t>(), n, width, height, stages, filter, false, st, c->ls);

@@ -27,6 +27,13 @@
 namespace {
 
 constexpr int NT = 128;   // threads per block (both kernels)
+// Codewords that complete behind an older open one wait in the interleave window (lib_icer's 2048-slot circular buffer).  The
+// window of every resident thread lives in global memory (2048 x 2 B x ~150 k threads); most codewords, however, complete within
+// a few sequence numbers of the emission point: those are parked in a small per-thread shared-memory window instead and never
+// touch global memory.  Must be a power of two (0 = everything goes through the global ring).
+#ifndef ICER_ENC_MINI
+#define ICER_ENC_MINI 8
+#endif
 
 struct DevTables {
     uint32_t cutoff[16];
@@ -225,6 +232,88 @@ __global__ void __launch_bounds__(256) k_T_to_frames(const uint16_t *__restrict_
     }
 }
 
+// 128-bit versions: a block moves a tile of 32 frames x 64 pixels; global reads and writes are 16-byte vectors (8 consecutive pixels
+// of one frame on the planar side, 8 frames of one pixel on the T side -- a warp then covers 512 contiguous bytes of T).  The
+// encode-side kernel also applies the sign-magnitude mapping (icer_wavelet.c:871-877), so the planar coefficients are read once.
+// Requirements (else the scalar kernels above): plane_px, cap_px and W multiples of 8, 16-byte aligned bases.
+constexpr int TT_PX = 64, TT_LD = TT_PX + 8;
+
+template <bool SIGNMAG>
+__global__ void __launch_bounds__(256) k_frames_to_T_v(const uint16_t *__restrict__ src, uint16_t *__restrict__ T, uint32_t nframes,
+                                                       uint32_t chan, uint32_t plane_px) {
+    __shared__ __align__(16) uint16_t tile[32][TT_LD];
+    const uint32_t g = blockIdx.z, c = blockIdx.y;
+    const size_t px0 = (size_t) blockIdx.x * TT_PX;
+    const int t = threadIdx.x;
+    {
+        const int f = t >> 3, k = t & 7;
+        const uint32_t frame = g * 32 + f;
+        const size_t px = px0 + 8 * k;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (frame < nframes && px < plane_px) v = *reinterpret_cast<const uint4 *>(src + ((size_t) frame * chan + c) * plane_px + px);
+        if (SIGNMAG) {
+            uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int lo = (int) (int16_t) (w[j] & 0xFFFF), hi = (int) (int16_t) (w[j] >> 16);
+                const uint32_t a = lo < 0 ? ((uint32_t) (-lo) & 0x7FFFu) | 0x8000u : (uint32_t) lo;
+                const uint32_t b = hi < 0 ? ((uint32_t) (-hi) & 0x7FFFu) | 0x8000u : (uint32_t) hi;
+                w[j] = a | (b << 16);
+            }
+        }
+        *reinterpret_cast<uint4 *>(&tile[f][8 * k]) = v;
+    }
+    __syncthreads();
+    {
+        const int px = t >> 2, fq = t & 3;
+        if (px0 + px < plane_px) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) w[j] = (uint32_t) tile[8 * fq + 2 * j][px] | ((uint32_t) tile[8 * fq + 2 * j + 1][px] << 16);
+            *reinterpret_cast<uint4 *>(T + (((size_t) g * chan + c) * plane_px + px0 + px) * 32 + 8 * fq) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_T_to_frames_v(const uint16_t *__restrict__ T, uint16_t *__restrict__ dst,
+                                                       const int32_t *__restrict__ frame_of, const uint16_t *__restrict__ mean,
+                                                       uint32_t chan, uint32_t plane_px, uint64_t cap_px, int W, int llw, int llh) {
+    __shared__ __align__(16) uint16_t tile[32][TT_LD];
+    const uint32_t g = blockIdx.z, c = blockIdx.y;
+    const size_t px0 = (size_t) blockIdx.x * TT_PX;
+    const int t = threadIdx.x;
+    {
+        const int px = t >> 2, fq = t & 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (px0 + px < plane_px) v = *reinterpret_cast<const uint4 *>(T + (((size_t) g * chan + c) * plane_px + px0 + px) * 32 + 8 * fq);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { tile[8 * fq + 2 * j][px] = (uint16_t) (w[j] & 0xFFFF); tile[8 * fq + 2 * j + 1][px] = (uint16_t) (w[j] >> 16); }
+    }
+    __syncthreads();
+    {
+        const int f = t >> 3, k = t & 7;
+        const int32_t frame = frame_of[g * 32 + f];
+        const size_t px = px0 + 8 * k;
+        if (frame < 0 || px >= plane_px) return;
+        uint4 v = *reinterpret_cast<const uint4 *>(&tile[f][8 * k]);
+        uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+        const int r = (int) (px / (size_t) W), cc = (int) (px % (size_t) W);       // the 8 pixels lie in one row (W % 8 == 0)
+        const int m = (int) (int16_t) mean[(size_t) frame * chan + c];
+        const bool ll_row = r < llh;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t a = w[j] & 0xFFFF, b = w[j] >> 16;
+            a = (a & 0x8000u) ? ((0x8000u - a) & 0xFFFFu) : a;                      // icer_wavelet.c:880-886
+            b = (b & 0x8000u) ? ((0x8000u - b) & 0xFFFFu) : b;
+            if (ll_row && cc + 2 * j < llw) a = (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) a + m);        // icer_compress.c:524-531
+            if (ll_row && cc + 2 * j + 1 < llw) b = (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) b + m);
+            w[j] = a | (b << 16);
+        }
+        *reinterpret_cast<uint4 *>(dst + ((size_t) frame * chan + c) * cap_px + px) = v;
+    }
+}
+
 // =========================================================================================================
 // K4: encoder
 // =========================================================================================================
@@ -233,6 +322,9 @@ struct EncSmem {
     uint32_t cnt[17][NT];      // zero << 16 | total, per context
     uint16_t bseq[17][NT];     // sequence number (low 16 bits; the window spans 2048) of the codeword each bin is building
     uint32_t bst[17][NT];      // Golomb: zeros counted; custom: input word (first bit = bit 0) | bits gathered << 16
+#if ICER_ENC_MINI > 0
+    uint16_t mini[ICER_ENC_MINI][NT];   // parked codewords close to the emission point (see Enc::complete)
+#endif
 };
 
 // Interleave-window bookkeeping.  A codeword gets a sequence number when its first bit arrives (lib_icer: a ring
@@ -248,6 +340,7 @@ struct Enc {
     int nacc = 0;
     uint32_t head = 0, tail = 0, open_mask = 0;   // head: first sequence number that is not complete yet (lib_icer's head)
     uint32_t emit_pos = 0;                        // next sequence number to pack into the payload (<= head)
+    // bits 24.. of open_mask: which slots of S.mini hold a parked codeword (one register for both masks)
     int oldest = 0;
     bool overflow = false;
 
@@ -265,11 +358,19 @@ struct Enc {
     __device__ __forceinline__ void complete(int bin, uint32_t code, uint32_t nb) {
         const uint32_t seq = S.bseq[bin][t];
         open_mask &= ~(1u << bin);
+#if ICER_ENC_MINI > 0
+        // a parked entry is live until emitted, and emit_pos only grows: every live entry of the small window has a sequence
+        // number in [emit_pos, emit_pos + ICER_ENC_MINI), so slot = seq mod ICER_ENC_MINI is unambiguous (checked in pump())
+        if (((seq - emit_pos) & 0xFFFFu) < (uint32_t) ICER_ENC_MINI) {
+            S.mini[seq & (ICER_ENC_MINI - 1)][t] = (uint16_t) ((nb << 11) | code);
+            open_mask |= 0x1000000u << (seq & (ICER_ENC_MINI - 1));
+        } else
+#endif
         ring[seq & (ICER_RING - 1)] = (uint16_t) ((nb << 11) | code);
         if (seq != (head & 0xFFFFu)) return;
         const uint32_t h1 = head + 1;
         uint32_t dist = tail - h1;                       // every other open codeword lies in [head + 1, tail)
-        for (uint32_t m = open_mask; m; m &= m - 1) {
+        for (uint32_t m = open_mask & 0x1FFFFu; m; m &= m - 1) {
             const int b = __ffs(m) - 1;
             const uint32_t d = ((uint32_t) S.bseq[b][t] - h1) & 0xFFFFu;
             if (d < dist) { dist = d; oldest = b; }
@@ -281,7 +382,14 @@ struct Enc {
     // per pixel so that the lanes of a warp emit together instead of each draining its backlog alone.
     __device__ __forceinline__ void pump() {
         if (emit_pos == head) return;
+#if ICER_ENC_MINI > 0
+        uint32_t v;
+        const uint32_t slot = emit_pos & (ICER_ENC_MINI - 1);
+        if ((open_mask >> (24 + slot)) & 1u) { v = S.mini[slot][t]; open_mask &= ~(0x1000000u << slot); }
+        else v = ring[emit_pos & (ICER_RING - 1)];
+#else
         const uint32_t v = ring[emit_pos & (ICER_RING - 1)];
+#endif
         emit_pos++;
         acc |= (unsigned long long) (v & 0x7FF) << nacc;
         nacc += (int) (v >> 11);
@@ -315,14 +423,14 @@ struct Enc {
     __device__ __forceinline__ void open_bin(int bin) {
         if (open_mask & (1u << bin)) return;
         while (tail - emit_pos >= ICER_RING) pump();       // physical ring space (emission may lag behind `head`)
-        if (open_mask == 0) oldest = bin;
+        if ((open_mask & 0x1FFFFu) == 0) oldest = bin;
         S.bseq[bin][t] = (uint16_t) tail++;
         S.bst[bin][t] = 0;
         open_mask |= 1u << bin;
     }
 
     __device__ void finish(uint32_t &bits_out) {
-        while (open_mask) {                                    // icer_context_modeller.c:452-455
+        while (open_mask & 0x1FFFFu) {                         // icer_context_modeller.c:452-455
             uint32_t nb;
             const int bin = oldest;
             const uint32_t code = forced_word(bin, nb);
@@ -343,7 +451,7 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
     __syncthreads();
 
     const uint32_t nstreams = a.nunits * a.planes;
-    const unsigned long long total = (unsigned long long) a.ngroups * nstreams;
+    const unsigned long long total = (unsigned long long) a.ngroups * (a.list ? a.nlist : nstreams);
     const int lane = t & 31;
     uint16_t *ring = a.rings + (size_t) (blockIdx.x * NT + t) * ICER_RING;
     const size_t plane_px = (size_t) a.w * a.h;
@@ -356,7 +464,8 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
         wid = __shfl_sync(0xffffffffu, wid, 0);
         if (wid >= total) break;
         // stream-major order: the largest streams of ALL groups first, so the tail of the kernel consists of small streams
-        const uint32_t g = (uint32_t) (wid % a.ngroups), s = (uint32_t) (wid / a.ngroups);
+        const uint32_t g = (uint32_t) (wid % a.ngroups);
+        const uint32_t s = a.list ? a.list[wid / a.ngroups] : (uint32_t) (wid / a.ngroups);
         const Unit u = a.units[s / a.planes];
         const int lsb = (int) (s % a.planes);
         const uint32_t frame = g * 32 + lane;
@@ -534,13 +643,13 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
 #define ICER_DEC_RECHECK 32          /* pixels a plane decodes between two looks at the progress of the plane above */
 #endif
 #ifndef ICER_DEC_BACKOFF_NS
-#define ICER_DEC_BACKOFF_NS 300      /* sleep when the plane above is not far enough ahead */
+#define ICER_DEC_BACKOFF_NS 5000     /* sleep when the plane above is not far enough ahead */
 #endif
 #ifndef ICER_DEC_SLOTWAIT_NS
-#define ICER_DEC_SLOTWAIT_NS 200     /* poll interval while a chain waits for a free slot (chains last milliseconds) */
+#define ICER_DEC_SLOTWAIT_NS 20000    /* poll interval while a chain waits for a free slot (chains last milliseconds) */
 #endif
 #ifndef ICER_DEC_CHAINWAIT_NS
-#define ICER_DEC_CHAINWAIT_NS 100    /* poll interval while a plane waits for its chain's slot to be published */
+#define ICER_DEC_CHAINWAIT_NS 5000   /* poll interval while a plane waits for its chain's slot to be published */
 #endif
 constexpr int DEC_WARPS = ICER_DEC_WARPS;
 constexpr int DEC_BT = DEC_WARPS * 32;
@@ -569,7 +678,7 @@ struct DecShared {
 struct Dec {
     const SmemTables &T;
     const uint32_t *wp = nullptr;   // next aligned stream word to load
-    const uint8_t *end = nullptr;   // end of THIS FRAME's stream (bytes at or beyond it read as zero, like the oracle and the legacy calls)
+    int left = 0;                   // bytes from wp to the end of THIS FRAME's stream (bytes at or beyond it read as zero, like the oracle and the legacy calls)
     unsigned long long bb = 0;      // bit buffer, LSB = next stream bit
     int bbn = 0;                    // bits in bb that came from loads (zeros beyond)
     uint32_t total_bits = 0;
@@ -579,20 +688,24 @@ struct Dec {
     __device__ Dec(const SmemTables &tt) : T(tt) {}
 
     __device__ __forceinline__ uint32_t load_word() {
-        const ptrdiff_t left = end - reinterpret_cast<const uint8_t *>(wp);
         uint32_t w = 0;
         if (left >= 4) w = *wp;
         else if (left > 0) {           // tail: byte loads, nothing behind `end` is touched (the caller's buffer may stop there)
             const uint8_t *bp = reinterpret_cast<const uint8_t *>(wp);
-            for (int i = 0; i < (int) left; i++) w |= (uint32_t) bp[i] << (8 * i);
+            w = bp[0];
+            if (left > 1) w |= (uint32_t) bp[1] << 8;
+            if (left > 2) w |= (uint32_t) bp[2] << 16;
         }
         wp++;
+        left -= 4;
         return w;
     }
     __device__ __forceinline__ void start(const uint8_t *base, const uint8_t *e, uint32_t nbits) {
-        end = e; total_bits = nbits;
+        total_bits = nbits;
         const uintptr_t ad = reinterpret_cast<uintptr_t>(base);
         wp = reinterpret_cast<const uint32_t *>(ad & ~(uintptr_t) 3);
+        const ptrdiff_t room = e - reinterpret_cast<const uint8_t *>(wp);
+        left = room > 0x7FFFFFF0 ? 0x7FFFFFF0 : (int) room;
         const int sh = (int) (ad & 3) * 8;
         bb = (unsigned long long) (load_word() >> sh);
         bbn = 32 - sh;
@@ -946,6 +1059,7 @@ __global__ void __launch_bounds__(128) k_payload_crc(AssembleArgs a) {
     const unsigned long long id = (unsigned long long) blockIdx.x * 128 + threadIdx.x;
     if (id >= (unsigned long long) a.nframes * a.nstreams) return;
     const uint32_t f = (uint32_t) (id / a.nstreams), s = (uint32_t) (id % a.nstreams);
+    if (a.bits[id] == ICER_BITS_NOT_CODED) return;
     const uint32_t nbytes = (a.bits[id] + 7) >> 3;
     const uint32_t *w = a.scratch + (size_t) f * a.scratch_words + a.soff[s];
     uint32_t c = 0xFFFFFFFFu, i = 0;
@@ -1039,6 +1153,9 @@ __global__ void __launch_bounds__(128) k_quota_scan(AssembleArgs a) {
         a.size_used[f] = (rc == ICER_RESULT_OK || rc == ICER_BYTE_QUOTA_EXCEEDED) ? used : 0;
         a.rc[f] = rc;
         a.keep[f] = kept;
+        atomicMax(&a.stat[0], kept);
+        // priority-prefix encoding: the walk reached the first stream the encoder has not produced yet -> code more, walk again
+        if (kept >= a.limit && a.limit < a.nstreams && (rc == ICER_RESULT_OK || rc == ICER_BYTE_QUOTA_EXCEEDED)) atomicOr(&a.stat[1], 1u);
     }
 }
 
@@ -1090,6 +1207,10 @@ __global__ void __launch_bounds__(256) k_gather(AssembleArgs a) {
 
 }  // namespace
 
+bool frames_to_T_fuses_signmag(const uint16_t *frames, const uint16_t *T, uint32_t w, uint32_t h) {
+    return (((size_t) w * h) % 8) == 0 && ((uintptr_t) frames % 16) == 0 && ((uintptr_t) T % 16) == 0;
+}
+
 uint32_t encode_resident_threads(int device) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -1101,8 +1222,23 @@ uint32_t encode_resident_threads(int device) {
 }
 
 int launch_frames_to_T(const uint16_t *frames, uint16_t *T, uint32_t nframes, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h,
-                       cudaStream_t st, LaunchStats &ls) {
+                       cudaStream_t st, LaunchStats &ls, bool signmag) {
     const size_t plane_px = (size_t) w * h;
+    if ((plane_px % 8) == 0 && ((uintptr_t) frames % 16) == 0 && ((uintptr_t) T % 16) == 0) {
+        for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
+            const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
+            dim3 grid((unsigned) ((plane_px + TT_PX - 1) / TT_PX), chan, cnt);
+            const uint32_t f0 = g0 * 32;
+            const uint16_t *src = frames + (size_t) f0 * chan * plane_px;
+            uint16_t *dstT = T + (size_t) g0 * chan * plane_px * 32;
+            if (signmag) k_frames_to_T_v<true><<<grid, 256, 0, st>>>(src, dstT, nframes - f0, chan, (uint32_t) plane_px);
+            else k_frames_to_T_v<false><<<grid, 256, 0, st>>>(src, dstT, nframes - f0, chan, (uint32_t) plane_px);
+            ls.launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return ICER_RESULT_OK;
+    }
+    if (signmag) return ICER_INVALID_INPUT;      // the scalar kernel expects sign-magnitude input (callers check frames_to_T_fuses_signmag)
     for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
         const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
         dim3 grid((unsigned) ((plane_px + 31) / 32), chan, cnt);
@@ -1119,6 +1255,17 @@ int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame
                        uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, uint32_t llw, uint32_t llh, cudaStream_t st,
                        LaunchStats &ls, bool bits8) {
     const size_t plane_px = (size_t) w * h;
+    if (!bits8 && (plane_px % 8) == 0 && (cap_px % 8) == 0 && (w % 8) == 0 && ((uintptr_t) frames % 16) == 0 && ((uintptr_t) T % 16) == 0) {
+        for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
+            const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
+            dim3 grid((unsigned) ((plane_px + TT_PX - 1) / TT_PX), chan, cnt);
+            k_T_to_frames_v<<<grid, 256, 0, st>>>(T + (size_t) g0 * chan * plane_px * 32, frames, frame_of + (size_t) g0 * 32, mean, chan,
+                                                  (uint32_t) plane_px, cap_px, (int) w, (int) llw, (int) llh);
+            ls.launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return ICER_RESULT_OK;
+    }
     for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
         const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
         dim3 grid((unsigned) ((plane_px + 31) / 32), chan, cnt);
@@ -1134,7 +1281,7 @@ int launch_encode(const EncodeArgs &a, cudaStream_t st, LaunchStats &ls) {
     int rc = upload_tables();
     if (rc) return rc;
     CUDA_TRY(cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EncSmem)));
-    const unsigned long long total = (unsigned long long) a.ngroups * a.nunits * a.planes;   // warps of work
+    const unsigned long long total = (unsigned long long) a.ngroups * (a.list ? a.nlist : a.nunits * a.planes);   // warps of work
     unsigned blocks = a.nring_threads / NT;
     const unsigned long long need = (total + (NT / 32) - 1) / (NT / 32);
     if (need < blocks) blocks = (unsigned) need;
@@ -1150,13 +1297,15 @@ int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls) {
     if (rc) return rc;
     const unsigned long long nst = (unsigned long long) a.nframes * a.nstreams;
     const bool coded = a.plan_status == ICER_RESULT_OK;     // otherwise the coder did not run: only the per-frame status is produced
-    if (nst && coded) k_payload_crc<<<(unsigned) ((nst + 127) / 128), 128, 0, st>>>(a);
-    k_quota_scan<<<(a.nframes + 3) / 4, 128, 0, st>>>(a);
+    if (a.phase != 2) {
+        if (nst && coded) { k_payload_crc<<<(unsigned) ((nst + 127) / 128), 128, 0, st>>>(a); ls.launches++; }
+        k_quota_scan<<<(a.nframes + 3) / 4, 128, 0, st>>>(a);
+        ls.launches++;
+    }
     const unsigned long long warps = (unsigned long long) a.nframes * a.nstreams;
     const unsigned long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0x7FFFFFFFull) return ICER_FATAL_ERROR;
-    if (blocks && coded) k_gather<<<(unsigned) blocks, 256, 0, st>>>(a);
-    ls.launches += 3;
+    if (a.phase != 1 && blocks && coded) { k_gather<<<(unsigned) blocks, 256, 0, st>>>(a); ls.launches++; }
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;
 }

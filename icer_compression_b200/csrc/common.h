@@ -64,7 +64,14 @@ struct Plan {
     uint32_t *d_unit_lut = nullptr;
     // lookup (chan, level, subband, seg) -> unit index, for the decoder's segment table
     std::map<std::tuple<int, int, int, int>, uint32_t> unit_of;
+    // priority-prefix encoding (byte quotas far below the lossless size): how many streams of the priority order the encoder
+    // produces first; learned from the previous batch of this shape (0 = all at once)
+    uint32_t enc_prefix = 0;
+    uint64_t enc_prefix_quota = 0;       // the quota the hint was learned for
+    uint32_t *d_list = nullptr;          // [nstreams]: the first `list_prefix` streams of the priority order, then the rest; each part big streams first
+    uint32_t list_prefix = 0;
 };
+int upload_prefix_lists(Plan &pl, uint32_t prefix, cudaStream_t st);
 
 int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages, uint32_t segments, uint32_t planes,
                uint32_t max_stages, uint32_t max_packets, int scratch_bits, bool native_u8 = false);
@@ -88,7 +95,7 @@ int launch_dwt_inverse(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t
                        const std::map<uint32_t, const uint32_t *> *perms = nullptr);
 // LL mean removal + sign-magnitude (encode); the decode-side inverse is fused into launch_T_to_frames
 int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
-                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8 = false);
+                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8 = false, bool skip_signmag = false);
 
 struct EncodeArgs {
     const uint16_t *coefsT;    // [ngroups][chan][h][w][32] sign-magnitude, frame-interleaved (32 frames per group)
@@ -102,7 +109,11 @@ struct EncodeArgs {
     uint32_t nring_threads;
     unsigned long long *work_counter;  // dynamic work fetch, pre-zeroed
     int *overflow;                 // set when any stream outgrew its scratch
+    const uint32_t *list;          // optional: the streams to code (a prefix of the priority order, big ones first); nullptr = all
+    uint32_t nlist;
 };
+// bit count of a stream the encoder has not produced (priority-prefix encoding): larger than any quota, so the quota walk stops there
+#define ICER_BITS_NOT_CODED 0xF0F0F0F0u      /* a memset pattern */
 int launch_encode(const EncodeArgs &a, cudaStream_t st, LaunchStats &ls);
 uint32_t encode_resident_threads(int device);
 
@@ -123,6 +134,9 @@ struct AssembleArgs {
     uint64_t *size_used; int32_t *rc;         // [nframes]
     uint32_t *keep;                           // [nframes] number of streams (in priority order) kept
     uint64_t *off_prio, *off_rearr;           // [nframes][nstreams] byte offsets (scratch)
+    uint32_t limit;                           // streams (in priority order) the encoder has produced so far; nstreams = all
+    uint32_t *stat;                           // [0] max over frames of `keep`, [1] != 0: some frame kept all `limit` streams and wants more
+    int phase;                                // 0: CRC + quota walk + gather; 1: CRC + quota walk only; 2: gather only
 };
 int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls);
 
@@ -140,8 +154,11 @@ struct DecodeArgs {
 };
 int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls);
 // planar frames [n][chan][h][w]  <->  frame-interleaved T layout [ngroups][chan][h][w][32]
+// signmag: the planes hold two's-complement coefficients and the kernel applies the sign-magnitude mapping on the way (only
+// when frames_to_T_fuses_signmag() says the vector kernel applies)
 int launch_frames_to_T(const uint16_t *frames, uint16_t *T, uint32_t nframes, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h,
-                       cudaStream_t st, LaunchStats &ls);
+                       cudaStream_t st, LaunchStats &ls, bool signmag = false);
+bool frames_to_T_fuses_signmag(const uint16_t *frames, const uint16_t *T, uint32_t w, uint32_t h);
 // also undoes sign-magnitude and adds the header LL mean; frame_of maps (group, lane) to the batch index (-1 = none)
 int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame_of, const uint16_t *mean, uint32_t ngroups,
                        uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, uint32_t llw, uint32_t llh, cudaStream_t st,
@@ -184,5 +201,9 @@ int launch_yuv_to_rgb(const uint16_t *yuv, uint8_t *rgb, size_t n, size_t px, si
 
 // ---- fused forward DWT stage with TMA-staged tiles (wavelet_tma.cu) -------------------------------------
 bool dwt_fused_applicable(const void *src, uint32_t w, uint32_t h, size_t src_plane_stride);
+// fused inverse stages (filter A): coefs is read-only, pp0 / pp1 hold the intermediate LL regions, dst receives the planes
+bool dwt_inverse_fused_applicable(const void *coefs, const void *dst, uint32_t w, uint32_t h, uint32_t stages, uint32_t filt);
+int launch_dwt_inverse_fused(const uint16_t *coefs, uint16_t *pp0, uint16_t *pp1, uint16_t *dst, size_t nplanes, uint32_t w, uint32_t h,
+                             uint32_t stages, uint32_t filt, bool clamp_negative, cudaStream_t st, LaunchStats &ls);
 int launch_dwt_forward_fused(const uint16_t *src, size_t src_plane_stride, uint16_t *dst, uint16_t *pp0, uint16_t *pp1, size_t nplanes,
                              uint32_t w, uint32_t h, uint32_t stages, uint32_t filt, int *d_ovf, cudaStream_t st, LaunchStats &ls);

@@ -306,6 +306,7 @@ void u8_interleave_dst(uint32_t len, std::vector<uint32_t> &dst) {
 void free_plan_device(Plan &pl) {
     cudaFree(pl.d_units); cudaFree(pl.d_prio); cudaFree(pl.d_rearr); cudaFree(pl.d_soff); cudaFree(pl.d_scap); cudaFree(pl.d_unit_lut);
     pl.d_unit_lut = nullptr;
+    cudaFree(pl.d_list); pl.d_list = nullptr; pl.list_prefix = 0;
     pl.d_units = nullptr; pl.d_prio = pl.d_rearr = pl.d_soff = pl.d_scap = nullptr;
 }
 
@@ -324,5 +325,18 @@ int upload_plan(Plan &pl) {
     CUDA_TRY(cudaMemcpy(pl.d_scap, pl.scratch_cap.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&pl.d_unit_lut, pl.unit_lut.size() * 4));
     CUDA_TRY(cudaMemcpy(pl.d_unit_lut, pl.unit_lut.data(), pl.unit_lut.size() * 4, cudaMemcpyHostToDevice));
+    return ICER_RESULT_OK;
+}
+
+// priority-prefix encoding: work lists of the coder.  Units are numbered big-first, so ascending stream ids = big streams first.
+int upload_prefix_lists(Plan &pl, uint32_t prefix, cudaStream_t st) {
+    if (pl.d_list && pl.list_prefix == prefix) return ICER_RESULT_OK;
+    if (!pl.d_list) CUDA_TRY(cudaMalloc(&pl.d_list, (size_t) pl.nstreams * 4));
+    std::vector<uint32_t> l(pl.prio_order);
+    std::sort(l.begin(), l.begin() + prefix);
+    std::sort(l.begin() + prefix, l.end());
+    CUDA_TRY(cudaMemcpyAsync(pl.d_list, l.data(), (size_t) pl.nstreams * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));       // `l` is a local
+    pl.list_prefix = prefix;
     return ICER_RESULT_OK;
 }

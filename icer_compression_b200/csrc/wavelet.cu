@@ -293,7 +293,7 @@ int launch_dwt_inverse(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t
 }
 
 int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
-                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8) {
+                           uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8, bool skip_signmag) {
     const size_t ps = (size_t) w * h;
     const size_t count = ps * nplanes;
     unsigned blocks = (unsigned) ((count / 8 + 255) / 256);
@@ -304,9 +304,9 @@ int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_
         k_to_signmag<true><<<blocks, 256, 0, st>>>(planes, count);
     } else {
         k_ll_mean<false><<<(unsigned) nplanes, 256, 0, st>>>(planes, ps, (int) w, (int) llw, (int) llh, d_mean, d_ovf);
-        k_to_signmag<false><<<blocks, 256, 0, st>>>(planes, count);
+        if (!skip_signmag) k_to_signmag<false><<<blocks, 256, 0, st>>>(planes, count);
     }
-    ls.launches += 2;
+    ls.launches += skip_signmag ? 1 : 2;
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;
 }

@@ -329,6 +329,40 @@ def rgb_to_yuv(rgb):
     return [y.astype(np.uint16), cb.astype(np.uint16), cr.astype(np.uint16)]
 
 
+class ColorRef:
+    """The reference tools' colour macros, compiled (oracle/_ref/libcolor_ref.so = oracle/color_ref.c + the reference's own
+    example/inc/color_util.h)."""
+
+    def __init__(self):
+        path = os.path.join(ORACLE_DIR, "_ref", "libcolor_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        u8, u16 = C.POINTER(C.c_uint8), C.POINTER(C.c_uint16)
+        self.lib.colorref_rgb888_to_yuv.argtypes = [u8, u16, u16, u16, C.c_size_t]
+        self.lib.colorref_rgb888_to_yuv.restype = None
+        self.lib.colorref_yuv_to_rgb888.argtypes = [u16, u16, u16, u8, C.c_size_t]
+        self.lib.colorref_yuv_to_rgb888.restype = None
+
+    def rgb_to_yuv(self, rgb):
+        """rgb: uint8 [..., 3] -> three uint16 arrays of the leading shape."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        n = rgb.size // 3
+        out = [np.zeros(n, dtype=np.uint16) for _ in range(3)]
+        self.lib.colorref_rgb888_to_yuv(_u8p(rgb), _u16p(out[0]), _u16p(out[1]), _u16p(out[2]), n)
+        return [o.reshape(rgb.shape[:-1]) for o in out]
+
+    def yuv_to_rgb(self, y, u, v):
+        y, u, v = [np.ascontiguousarray(a, dtype=np.uint16) for a in (y, u, v)]
+        rgb = np.zeros(y.shape + (3,), dtype=np.uint8)
+        self.lib.colorref_yuv_to_rgb888(_u16p(y), _u16p(u), _u16p(v), _u8p(rgb), y.size)
+        return rgb
+
+
+def have_color_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libcolor_ref.so"))
+
+
 def load_boatcolor_yuv():
     """512x512 Y,U,V planes (uint16) of the reference's boatcolor.512.bmp after the tools' RGB->YCbCr."""
     return rgb_to_yuv(load_boatcolor_rgb())

@@ -51,7 +51,10 @@ def case_input(c, orc):
 @pytest.mark.parametrize("filt", range(7))
 def test_dwt_forward_inverse_vs_oracle(filt, ctx9, oracle9):
     rng = np.random.default_rng(200 + filt)
-    for (w, h, st) in ((64, 48, 3), (37, 53, 2), (5, 5, 1), (129, 65, 5), (96, 96, 5), (200, 7, 1), (512, 512, 6), (301, 203, 5)):
+    # widths that are multiples of 8 take the fused TMA stage kernels (odd region sizes appear at their later stages: 200 -> 25,
+    # 120 -> 15, 56 -> 7); the others the two-pass kernels
+    for (w, h, st) in ((64, 48, 3), (37, 53, 2), (5, 5, 1), (129, 65, 5), (96, 96, 5), (200, 7, 1), (512, 512, 6), (301, 203, 5),
+                       (200, 56, 4), (120, 56, 4), (128, 70, 3), (256, 7, 1), (72, 40, 3), (1024, 64, 4)):
         imgs = np.stack([rng.integers(0, 256, (h, w)).astype(np.uint16),
                          rng.integers(0, 4096, (h, w)).astype(np.uint16),
                          rng.integers(0, 65536, (h, w)).astype(np.uint16)])
@@ -392,6 +395,59 @@ def test_pixel_formats_at_the_boundary(ctx9, oracle9):
         assert o["stream"] == enc["streams"][i]
         od = oracle9.decompress(o["stream"], 1, 96 * 128, 3, 0, 6)["images"][0].ravel()
         assert (dec["frames"][i, 0] == np.minimum(od, 255).astype(np.uint8)).all()
+
+
+def test_device_color_kernels_vs_compiled_reference_macros(ctx15):
+    """k_rgb_to_yuv / k_yuv_to_rgb against the reference tools' own macros, compiled (example/inc/color_util.h:27-34 behind
+    oracle/color_ref.c -> oracle/_ref/libcolor_ref.so): every one of the 2^24 RGB triples forward, and a dense sweep of (Y, Cb, Cr)
+    back -- the conversions themselves, not a stream round trip."""
+    if not harness.have_color_ref():
+        pytest.skip("oracle/_ref/libcolor_ref.so not present")
+    cr = harness.ColorRef()
+    g = np.arange(256, dtype=np.uint8)
+    rgb = np.stack(np.broadcast_arrays(g[:, None, None], g[None, :, None], g[None, None, :]), axis=-1).reshape(4096, 4096, 3).copy()
+    want = cr.rgb_to_yuv(rgb)
+    # 15 bit planes: lossless for any 8-bit input.  The conversion kernels sit behind the *_pix batch calls; drive them through a 1-stage lossless round trip of the planes:
+    # encode RGB888 -> decode as planar uint16 gives exactly the Y, Cb, Cr planes the device produced
+    quota = 3 * 4096 * 4096 * 2
+    enc = ctx15.compress_batch_pix(rgb[None], 2, 4096, 4096, 3, 1, 0, 32, quota)          # PIX_RGB888
+    assert int(enc["rc"][0]) == 0
+    dec = ctx15.decompress_batch(enc["streams"], 3, 4096, 4096, 1, 0, 32)
+    for c in range(3):
+        assert (dec["frames"][0, c].reshape(4096, 4096) == want[c]).all(), c
+    # back: planes (Y, Cb, Cr) in 0..255 (what an 8-bit colour image decodes to) -> packed RGB on the device
+    yy, cb, crr = [a.reshape(4096, 4096).astype(np.uint16) for a in np.meshgrid(g, g, g, indexing="ij")]
+    planes = np.stack([yy, cb, crr])[None]
+    enc2 = ctx15.compress_batch(planes, 1, 0, 32, quota)
+    assert int(enc2["rc"][0]) == 0
+    got = ctx15.decompress_batch_pix(enc2["streams"], 2, 3, 4096, 4096, 1, 0, 32)["frames"][0].reshape(4096, 4096, 3)
+    assert (got == cr.yuv_to_rgb(yy, cb, crr)).all()
+
+
+def test_priority_prefix_encoding(oracle9):
+    """Byte quotas far below the lossless size: the encoder codes a prefix of the priority order first and the rest only if some
+    frame keeps the whole prefix.  Streams, sizes and status codes must not depend on the prefix length -- forced here to several
+    values (ICER_B200_FORCE_PREFIX), on a batch whose frames hit the quota at very different places -- nor on the learned hint."""
+    import icer_compression_b200 as icer
+    w, h, n = 160, 128, 36
+    frames = np.stack([oracle9.synth(w, h, f, 99, (f % 3 == 2) * 1) if f % 5 else np.full((h, w), 7, dtype=np.uint16) for f in range(n)])[:, None]
+    for quota in (900, 6000, 40000):
+        want = [oracle9.compress([frames[i, 0]], 4, 0, 8, quota) for i in range(n)]
+        for prefix in ("1", "37", "300", "600", "935", None):
+            if prefix is None:
+                os.environ.pop("ICER_B200_FORCE_PREFIX", None)
+            else:
+                os.environ["ICER_B200_FORCE_PREFIX"] = prefix
+            try:
+                c = icer.IcerB200(device=0)
+            finally:
+                os.environ.pop("ICER_B200_FORCE_PREFIX", None)
+            for rep in range(3 if prefix is None else 1):          # without forcing: the 2nd and 3rd call use the learned prefix
+                enc = c.compress_batch(frames, 4, 0, 8, quota, want_prio=True)
+                for i in range(n):
+                    assert int(enc["rc"][i]) == want[i]["rc"], (quota, prefix, rep, i)
+                    assert enc["streams"][i] == want[i]["stream"] and enc["prio"][i] == want[i]["prio"], (quota, prefix, rep, i)
+            c.close()
 
 
 def test_host_pipeline_chunks(oracle9):

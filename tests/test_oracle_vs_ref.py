@@ -184,3 +184,16 @@ def test_15_plane_build_vs_ref(ref15, oracle15):
     da = ref15.decompress(a["stream"], 1, fr.size, 4, 0, 10)
     db = oracle15.decompress(a["stream"], 1, fr.size, 4, 0, 10)
     assert (da["images"][0] == db["images"][0]).all()
+
+
+@pytest.mark.skipif(not harness.have_color_ref(), reason="oracle/_ref/libcolor_ref.so not built")
+def test_color_restatement_vs_compiled_macros():
+    """harness.rgb_to_yuv (the numpy restatement the fixtures were made with) against the reference's own macros, compiled
+    (example/inc/color_util.h:27-29 behind oracle/color_ref.c) -- over ALL 2^24 RGB triples."""
+    cr = harness.ColorRef()
+    g = np.arange(256, dtype=np.uint8)
+    for r in range(0, 256, 1):
+        rgb = np.stack(np.broadcast_arrays(np.uint8(r), g[:, None], g[None, :]), axis=-1)
+        want = cr.rgb_to_yuv(rgb)
+        got = harness.rgb_to_yuv(rgb)
+        assert all((a == b).all() for a, b in zip(want, got)), r
