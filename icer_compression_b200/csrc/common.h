@@ -10,6 +10,7 @@
 
 #include "../../include/icer.h"
 #include "../../include/icer_b200.h"
+#include "coder_tables.h"
 
 #define ICER_HDR_BYTES 28
 #define ICER_RING 2048
@@ -25,14 +26,6 @@
     } while (0)
 
 // ---- code tables (ICER standard; lib_icer builds the same at run time in src/icer_init.c) ---------------
-struct V2VEntry { uint8_t in_bits, out_bits, out; };
-struct HostTables {
-    V2VEntry enc[8][32];       // [bin 0..7][input word]   (bin 0 unused)
-    V2VEntry dec[8][32];       // [bin][emitted word] -> input word, bit-reversed
-    uint8_t flush[8][9][6];    // [bin][prefix][len] -> pad_word | pad_len << 4
-    uint16_t gol_m[17], gol_l[17], gol_i[17];
-    uint32_t cutoff[17];
-};
 const HostTables &icer_host_tables();
 
 // ---- plan: everything that depends only on (w, h, channels, stages, segments, planes) ---------------------

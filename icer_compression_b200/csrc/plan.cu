@@ -10,62 +10,10 @@
 // ---------------------------------------------------------------------------------------------------------
 // tables
 // ---------------------------------------------------------------------------------------------------------
-namespace {
-// {bin, input word (first bit = bit 0), input bits, output word (first emitted bit = bit 0), output bits}
-const uint8_t kV2V[][5] = {
-    {1, 0x01, 2, 0x02, 2}, {1, 0x03, 3, 0x03, 3}, {1, 0x07, 4, 0x0F, 4}, {1, 0x0F, 4, 0x10, 5}, {1, 0x02, 2, 0x01, 2},
-    {1, 0x04, 3, 0x04, 3}, {1, 0x08, 4, 0x08, 4}, {1, 0x10, 5, 0x00, 5}, {1, 0x00, 5, 0x07, 4},
-    {2, 0x02, 2, 0x01, 2}, {2, 0x04, 3, 0x00, 2}, {2, 0x00, 4, 0x03, 3}, {2, 0x18, 5, 0x12, 5}, {2, 0x08, 5, 0x0F, 4},
-    {2, 0x01, 2, 0x06, 3}, {2, 0x03, 4, 0x07, 4}, {2, 0x0B, 4, 0x02, 5}, {2, 0x07, 3, 0x0A, 4},
-    {3, 0x02, 2, 0x02, 2}, {3, 0x04, 3, 0x03, 3}, {3, 0x00, 3, 0x00, 2}, {3, 0x01, 2, 0x01, 2}, {3, 0x03, 2, 0x07, 3},
-    {4, 0x00, 2, 0x01, 1}, {4, 0x02, 3, 0x00, 3}, {4, 0x06, 3, 0x0A, 4}, {4, 0x05, 3, 0x02, 4}, {4, 0x09, 4, 0x0E, 4},
-    {4, 0x01, 5, 0x04, 4}, {4, 0x11, 5, 0x06, 5}, {4, 0x03, 3, 0x0C, 4}, {4, 0x07, 3, 0x16, 5},
-    {5, 0x01, 1, 0x02, 2}, {5, 0x02, 3, 0x03, 3}, {5, 0x06, 3, 0x0F, 4}, {5, 0x04, 3, 0x05, 3}, {5, 0x08, 4, 0x01, 3},
-    {5, 0x10, 5, 0x07, 4}, {5, 0x00, 5, 0x00, 2},
-    {6, 0x00, 3, 0x00, 1}, {6, 0x04, 3, 0x01, 3}, {6, 0x02, 3, 0x05, 3}, {6, 0x06, 3, 0x0F, 5}, {6, 0x03, 2, 0x07, 4},
-    {6, 0x01, 3, 0x03, 3}, {6, 0x05, 3, 0x1F, 5},
-    {7, 0x02, 2, 0x05, 3}, {7, 0x04, 3, 0x01, 3}, {7, 0x00, 4, 0x00, 1}, {7, 0x08, 5, 0x07, 4}, {7, 0x18, 5, 0x0F, 5},
-    {7, 0x01, 2, 0x03, 3}, {7, 0x03, 2, 0x1F, 5}};
-// {bin, incomplete prefix, prefix bits, pad word, pad bits}: what a forced flush appends
-const uint8_t kFlush[][5] = {
-    {1, 0x1, 1, 0, 1}, {1, 0x3, 2, 0, 1}, {1, 0x7, 3, 0, 1}, {1, 0x0, 1, 1, 1}, {1, 0x0, 2, 1, 1}, {1, 0x0, 3, 1, 1},
-    {1, 0x0, 4, 0, 1},
-    {2, 0x0, 1, 1, 1}, {2, 0x0, 2, 1, 1}, {2, 0x0, 3, 0, 1}, {2, 0x8, 4, 0, 1}, {2, 0x1, 1, 0, 1}, {2, 0x3, 2, 1, 1},
-    {2, 0x3, 3, 0, 1},
-    {3, 0x0, 1, 1, 1}, {3, 0x0, 2, 0, 1}, {3, 0x1, 1, 0, 1},
-    {4, 0x0, 1, 0, 1}, {4, 0x2, 2, 0, 1}, {4, 0x1, 2, 1, 1}, {4, 0x1, 3, 1, 1}, {4, 0x1, 4, 0, 1}, {4, 0x1, 1, 1, 2},
-    {4, 0x3, 2, 0, 1},
-    {5, 0x0, 1, 1, 2}, {5, 0x1, 2, 0, 1}, {5, 0x0, 2, 1, 1}, {5, 0x0, 3, 1, 1}, {5, 0x0, 4, 0, 1},
-    {6, 0x0, 1, 0, 2}, {6, 0x0, 2, 0, 1}, {6, 0x2, 2, 0, 1}, {6, 0x1, 1, 1, 1}, {6, 0x1, 2, 0, 1},
-    {7, 0x0, 1, 1, 1}, {7, 0x0, 2, 1, 1}, {7, 0x0, 3, 0, 1}, {7, 0x8, 4, 0, 1}, {7, 0x1, 1, 0, 1}};
-const int kGolombM[17] = {0, 0, 0, 0, 0, 0, 0, 0, 5, 6, 7, 11, 17, 31, 70, 200, 512};
-const uint32_t kCutoff[17] = {35298, 37345, 40503, 43591, 47480, 50133, 53645, 55902, 57755,
-                              58894, 60437, 62267, 63613, 64557, 65134, 65392, 65536};
-
-unsigned rev(unsigned v, unsigned n) { unsigned r = 0; while (n--) { r = (r << 1) | (v & 1); v >>= 1; } return r; }
-
-HostTables make_tables() {
-    HostTables t;
-    memset(&t, 0, sizeof t);
-    for (auto &e : kV2V) {
-        t.enc[e[0]][e[1]] = V2VEntry{e[2], e[4], e[3]};
-        t.dec[e[0]][e[3]] = V2VEntry{e[4], e[2], (uint8_t) rev(e[1], e[2])};
-    }
-    for (auto &e : kFlush) t.flush[e[0]][e[1]][e[2]] = (uint8_t) (e[3] | (e[4] << 4));
-    for (int b = 0; b < 17; b++) {
-        t.cutoff[b] = kCutoff[b];
-        if (kGolombM[b] > 0) {
-            unsigned m = (unsigned) kGolombM[b], l = 0;
-            while ((1u << l) < m) l++;
-            t.gol_m[b] = (uint16_t) m; t.gol_l[b] = (uint16_t) l; t.gol_i[b] = (uint16_t) ((1u << l) - m);
-        }
-    }
-    return t;
-}
-}  // namespace
+#include "coder_tables.h"
 
 const HostTables &icer_host_tables() {
-    static const HostTables t = make_tables();
+    static const HostTables t = icer_tables::make_tables();
     return t;
 }
 
