@@ -42,7 +42,7 @@ struct icer_b200_ctx {
     std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int, int>, Plan *> plans;
     LaunchStats ls;
     DevBuf coefs, tmp, scratch, bits, crc, rings, out, out_prio, size_used, rc, keep, offp, offr, mean, ovf, misc,
-        streams, segoff, dims, frame_ok, cand, ncand, pinfo, list, pix, fin, tmp2;
+        streams, segoff, dims, frame_ok, cand, ncand, pinfo, list, pix, fin, tmp2, slices, pstat;
     uint32_t ring_threads = 0;
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -147,7 +147,7 @@ void icer_b200_destroy(icer_b200_ctx *c) {
     for (auto &kv : c->perms8) cudaFree((void *) kv.second);
     DevBuf *all[] = {&c->coefs, &c->tmp, &c->scratch, &c->bits, &c->crc, &c->rings, &c->out, &c->out_prio, &c->size_used, &c->rc,
                      &c->keep, &c->offp, &c->offr, &c->mean, &c->ovf, &c->misc, &c->streams, &c->segoff, &c->dims, &c->frame_ok,
-                     &c->cand, &c->ncand, &c->pinfo, &c->list, &c->pix, &c->fin, &c->tmp2};
+                     &c->cand, &c->ncand, &c->pinfo, &c->list, &c->pix, &c->fin, &c->tmp2, &c->slices, &c->pstat};
     for (auto b : all) b->release();
     for (int k = 0; k < 2; k++) {
         c->p_in[k].release(); c->p_out[k].release(); c->p_used[k].release(); c->p_rc[k].release(); c->p_dims[k].release();
@@ -369,7 +369,8 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
     while (done < n) {
         // chunk size under the workspace budget: every per-frame buffer counts (coefs, tmp rounded up to 32-frame groups, tmp2
         // and fin at 2 B/sample each, the 8-bit staging, payload scratch, per-stream arrays, host staging of the output slots)
-        const size_t per_frame = frame_px * 2 * 4 + (pixfmt != ICER_B200_PIX_U16 ? frame_px : 0) + pl->scratch_words * 4 +
+        const size_t slice_bytes_per_frame = enc_slice_words(pl->planes, pl->nslots) * 4 / 32;
+        const size_t per_frame = frame_px * 2 * 4 + slice_bytes_per_frame + (pixfmt != ICER_B200_PIX_U16 ? frame_px : 0) + pl->scratch_words * 4 +
                                  (size_t) pl->nstreams * 24 + (host ? out_stride * (out_prio ? 2 : 1) : 0) + 64;
         size_t nb = std::max<size_t>(1, c->workspace_budget / per_frame);
         if (nb > 32) nb &= ~(size_t) 31;             // whole coder groups
@@ -383,7 +384,8 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
         for (;;) {      // a failed allocation halves the chunk instead of failing the call
             ngroups = (uint32_t) ((nb + 31) / 32);
             e = c->coefs.ensure(nb * frame_px * 2);
-            if (!e) e = c->tmp.ensure((size_t) ngroups * 32 * frame_px * 2);
+            if (!e) e = c->tmp.ensure(nb * frame_px * 2);
+            if (!e) e = c->slices.ensure((size_t) ngroups * enc_slice_words(pl->planes, pl->nslots) * 4);
             if (!e) e = c->fin.ensure(host || pixfmt != ICER_B200_PIX_U16 ? nb * frame_px * 2 : 0);
             if (!e) e = c->scratch.ensure(nb * pl->scratch_words * 4);
             if (!e) e = c->bits.ensure(nb * pl->nstreams * 4);
@@ -447,7 +449,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
             if ((e = launch_dwt_forward(d_coefs, c->tmp.as<uint16_t>(), nb * chan, w, h, p->stages, p->filter, c->ovf.as<int>(), st, c->ls, native8))) return e;
         }
         // sign-magnitude is applied on the way into the coder's layout unless the caller wants the planar coefficients back
-        const bool fuse_sm = !native8 && !coefs_out && frames_to_T_fuses_signmag(d_coefs, c->tmp.as<uint16_t>(), w, h);
+        const bool fuse_sm = !native8 && !coefs_out;
         if ((e = launch_ll_mean_signmag(d_coefs, nb * chan, w, h, (uint32_t) dim_low(w, p->stages), (uint32_t) dim_low(h, p->stages),
                                         c->mean.as<uint16_t>(), c->ovf.as<int>(), st, c->ls, native8, fuse_sm))) return e;
         if (coefs_out && !native8) if ((e = copy_out(coefs_out + done * frame_px, d_coefs, nb * frame_px * 2, mem, st))) return e;
@@ -456,9 +458,9 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
             if ((e = launch_sm16_to_sm8(d_coefs, c->pix.as<uint8_t>(), nb * frame_px, st, c->ls))) return e;
             if ((e = copy_out((uint8_t *) coefs_out + done * frame_px, c->pix.p, nb * frame_px, mem, st))) return e;
         }
-        // frame-interleave the coefficients for the coder (lane = frame); the wavelet scratch is free again
-        uint16_t *d_T = c->tmp.as<uint16_t>();
-        if ((e = launch_frames_to_T(d_coefs, d_T, (uint32_t) nb, ngroups, chan, w, h, st, c->ls, fuse_sm))) return e;
+        // bit slices of the coefficients for the coder (lane = frame of a group of 32)
+        uint32_t *d_bs = c->slices.as<uint32_t>();
+        if ((e = launch_bitslice(d_coefs, d_bs, pl->d_slots, pl->d_units, pl->nslots, (uint32_t) nb, ngroups, chan, w, h, pl->planes, fuse_sm, st, c->ls))) return e;
         ev_record(c, 2, st);
         // entropy coder + segment assembly.
         //  * a stream that outgrows its payload slot (rare) restarts the coder with a larger scratch budget;
@@ -483,7 +485,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
             if ((e = c->scratch.ensure(nb * pl->scratch_words * 4))) return e;
             CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 32, st));      // work counter + overflow flag (the quota statistics live behind them)
             EncodeArgs ea;
-            ea.coefsT = d_T; ea.nframes = (uint32_t) nb; ea.ngroups = ngroups; ea.w = w; ea.h = h; ea.chan = chan; ea.planes = pl->planes;
+            ea.bs = d_bs; ea.nslots = pl->nslots; ea.nframes = (uint32_t) nb; ea.ngroups = ngroups; ea.planes = pl->planes;
             ea.units = pl->d_units; ea.nunits = (uint32_t) pl->units.size(); ea.soff = pl->d_soff; ea.scap = pl->d_scap;
             ea.scratch_words = pl->scratch_words; ea.scratch = c->scratch.as<uint32_t>(); ea.bits = c->bits.as<uint32_t>();
             ea.rings = c->rings.as<uint16_t>(); ea.nring_threads = c->ring_threads;
@@ -758,8 +760,6 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
     if ((e = c->misc.ensure(64))) return e;
     uint16_t *d_frames = own16 ? c->coefs.as<uint16_t>() : frames;
     float ms_dec = 0, ms_dwt = 0;
-    uint32_t dbg_flags = 0;
-    { const char *dbg = getenv("ICER_B200_DEBUG"); dbg_flags = dbg ? (uint32_t) atoi(dbg) : 0u; }
     for (auto &g : groups) {
         const uint32_t w = g.first.first, h = g.first.second;
         Plan *pl = get_plan(c, w, h, chan, p->stages, p->segments, native8);
@@ -781,8 +781,9 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
             if (!info[i].overflow) list.push_back((uint32_t) i);
             for (uint32_t ch = 0; ch < chan; ch++) hmean[i * chan + ch] = info[i].mean[ch];
         }
-        const size_t t_bytes = (size_t) ngroups * 32 * chan * plane_px * 2;
-        if ((e = c->tmp.ensure(std::max(t_bytes, n * chan * plane_px * 2)))) return e;
+        if ((e = c->tmp.ensure(n * chan * plane_px * 2))) return e;
+        if ((e = c->slices.ensure((size_t) ngroups * dec_slice_words(pl->planes, pl->nslots) * 4))) return e;
+        if ((e = c->pstat.ensure(n * pl->units.size() * pl->planes + 16))) return e;
         if ((e = c->segoff.ensure(n * (size_t) pl->nstreams * 4))) return e;
         if ((e = c->frame_ok.ensure(frame_of.size() * 4))) return e;
         if ((e = c->list.ensure(list.size() * 4 + 4))) return e;
@@ -812,17 +813,14 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         CUDA_TRY(cudaMemcpyAsync(c->mean.p, hmean.data(), hmean.size() * 2, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(c->frame_ok.p, frame_of.data(), frame_of.size() * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 64, st));
-        uint16_t *d_T = c->tmp.as<uint16_t>();
-        CUDA_TRY(cudaMemsetAsync(d_T, 0, t_bytes, st));          // icer_compress.c:470: the image starts at zero
         ev_record(c, 2, st);
         DecodeArgs da;
-        da.coefsT = d_T; da.ngroups = ngroups; da.chan = chan; da.planes = pl->planes;
-        da.units = pl->d_units; da.nunits = (uint32_t) pl->units.size(); da.plan_w = w; da.plan_h = h;
+        da.bs = c->slices.as<uint32_t>(); da.nslots = pl->nslots; da.pstat = c->pstat.as<uint8_t>(); da.ngroups = ngroups; da.planes = pl->planes;
+        da.units = pl->d_units; da.nunits = (uint32_t) pl->units.size();
         da.frame_of = c->frame_ok.as<int32_t>();
         da.streams = d_streams; da.stream_stride = stream_stride; da.stream_len = d_lens;
         da.seg_off = c->segoff.as<uint32_t>();
         da.work_counter = c->misc.as<unsigned long long>();
-        da.debug_flags = dbg_flags;
         if ((e = launch_decode(da, st, c->ls))) return e;
         ev_record(c, 3, st);
         // 4. back to planar frames (from sign-magnitude, + LL mean), inverse wavelet, clamp
@@ -838,8 +836,10 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
             fused = dwt_inverse_fused_applicable(c->tmp2.p, d_frames, w, h, p->stages, p->filter) && ((uintptr_t) c->fin.p % 16) == 0;
         }
         uint16_t *d_planar = fused ? c->tmp2.as<uint16_t>() : d_frames;
-        if ((e = launch_T_to_frames(d_T, d_planar, c->frame_ok.as<int32_t>(), c->mean.as<uint16_t>(), ngroups, chan, w, h, cap_px,
-                                    llw, llh, st, c->ls, native8))) return e;
+        // every pixel of the frames of this group is written (icer_compress.c:470: the image starts at zero)
+        if ((e = launch_unslice(c->slices.as<uint32_t>(), d_planar, pl->d_slots, pl->d_units, c->pstat.as<uint8_t>(), c->frame_ok.as<int32_t>(),
+                                c->mean.as<uint16_t>(), pl->nslots, (uint32_t) pl->units.size(), ngroups, chan, w, h, cap_px, pl->planes, llw, llh,
+                                st, c->ls, native8))) return e;
         if (native8 && (e = ensure_perms8(c, w, h, p->stages))) return e;
         if (fused) {
             if ((e = launch_dwt_inverse_fused(d_planar, c->tmp.as<uint16_t>(), c->fin.as<uint16_t>(), d_frames, n * chan, w, h, p->stages,

@@ -1,32 +1,28 @@
-// coder.cu -- K4 (bit-plane context model + interleaved entropy ENCODER), K7 (the DECODER) and K5 (segment assembly).
+// coder.cu -- K3 (bit slicing), K4 (bit-plane context model + interleaved entropy ENCODER), K7 (the DECODER), K8 (un-slicing) and
+// K5 (segment assembly).
 //
-// Granularity.  lib_icer resets its context model and entropy coder for every (channel, level, subband, bit plane,
-// segment) (icer_partition.c:315-322), so each such STREAM is independent on the encode side.  On the decode side
-// the planes of one segment form a chain (MSB -> LSB, icer_partition.c:427-443), but plane p only needs plane p+1
-// to be a row + 1 pixel ahead (its right/down neighbours are taken at plane p+1, icer_context_modeller.c:510-521).
+// Granularity.  lib_icer resets its context model and entropy coder for every (channel, level, subband, bit plane, segment)
+// (icer_partition.c:315-322), so each such STREAM is independent on the encode side.  On the decode side the planes of one
+// segment form a chain (MSB -> LSB, icer_partition.c:427-443), but plane p only needs plane p+1 to be a row + 1 pixel ahead (its
+// right/down neighbours are taken one plane up, icer_context_modeller.c:510-521).
 //
-// Mapping (both kernels): one LANE per stream; the lanes of a warp are the bit planes of the same few segments, so
-// they walk the same pixels (shared sectors) -- in lockstep for the encoder, as an asynchronous pipeline for the
-// decoder (every tick a lane advances one pixel if the plane above is far enough ahead; positions travel by shfl).
-// Warps fetch work dynamically, largest segments first.
+// Mapping (both coder kernels): a WARP per (group of 32 frames, stream), lane = frame.  The lanes run the per-lane state machines
+// of coder_core.h on BIT SLICES of their frame: per chunk of 30 pixels of a segment row a handful of 32-bit words (magnitude bit,
+// "significant at plane p", sign), stored [group][slot][field][lane] so that a warp's load of one field is one 128-byte line.  A lane
+// steps through its chunk at its own pace (a sign decision, a codeword completion or a quiet run cost that lane a step, not the
+// whole warp); the warp only re-converges at chunk borders.  K3 produces the slices from the planar wavelet coefficients, K8 turns
+// the slices the decoder wrote back into planar coefficients.
 //
-// Two things keep the SIMT lanes together:
-//   * every pixel is turned into at most three micro-ops (flush-fast-run, magnitude decision, sign decision) that
-//     run through ONE code site for bin selection, ONE for codeword completion and ONE for bit emission;
-//   * the "quiet" fast path: when the 3x3 neighbourhood has no bit at or above the current plane the decision is
-//     (context 0, bit 0); runs of those only bump counters (adaptive counts, Golomb run length) until the next event
-//     (run completes a codeword, probability bin changes, counts rescale), computed in closed form.
-//
-// Reference behaviour restated (lib_icer/src): icer_context_modeller.c:312-602 (contexts, adaptive counts with the
-// discarded-ceil_div rescale), icer_encoding.c:37-189 and icer_decoding.c:46-194 (bin choice, Golomb /
-// variable-to-variable / uncoded bins, 2048-codeword interleave window with forced flush and its decoder mirror),
-// icer_util.c:48-56 (bin cut-offs), icer_partition.c:328-334 + icer_encoding.c:210-234 (segment header, quota).
+// Reference behaviour restated (lib_icer/src): see coder_core.h; icer_partition.c:328-334 + icer_encoding.c:210-234 (segment
+// header, quota) for K5.
 #include "common.h"
 #include <mutex>
 
 namespace {
 
-constexpr int NT = 128;   // threads per block (both kernels)
+using icer_core::CoreTables;
+
+constexpr int NT = 128;   // threads per encoder block
 // Codewords that complete behind an older open one wait in the interleave window (lib_icer's 2048-slot circular buffer).  The
 // window of every resident thread lives in global memory (2048 x 2 B x ~150 k threads); most codewords, however, complete within
 // a few sequence numbers of the emission point: those are parked in a small per-thread shared-memory window instead and never
@@ -34,28 +30,19 @@ constexpr int NT = 128;   // threads per block (both kernels)
 #ifndef ICER_ENC_MINI
 #define ICER_ENC_MINI 8
 #endif
+#ifndef ICER_ENC_MINBLOCKS
+#define ICER_ENC_MINBLOCKS 8
+#endif
 
 struct DevTables {
-    uint32_t cutoff[16];
+    CoreTables enc, dec;
     uint32_t crc[256];
-    uint16_t enc[8][32];       // in_bits | out_bits << 4 | out << 8        (keyed by the gathered input word)
-    uint16_t dec[8][32];       // in_bits | out_bits << 4 | out << 8        (keyed by the received word)
-    uint16_t dlut[8][32];      // keyed by the NEXT 5 stream bits: codeword length | out_bits << 4 | out << 8 (0 = none)
-    uint16_t gol_m[17], gol_l[17], gol_i[17];
-    uint8_t flush[8][9][6];    // pad_word | pad_len << 4
-    uint8_t ctx_hv[45], ctx_hh[25], ctx_sign[25], sign_pred[25];   // icer_config.c:26-67
 };
 __constant__ DevTables c_tab;
 // __constant__ memory has one instance PER DEVICE: the upload is tracked per device ordinal (a process may hold contexts on
 // several GPUs, e.g. icer_b200_*_batch_multi)
 std::mutex g_tab_mu;
 bool g_tables_uploaded[64] = {false};
-
-const uint8_t h_ctx_hv[45] = {0, 1, 2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 6, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7,
-                              8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8};
-const uint8_t h_ctx_hh[25] = {0, 3, 6, 8, 8, 1, 4, 7, 8, 8, 2, 5, 7, 8, 8, 2, 5, 7, 8, 8, 2, 5, 7, 8, 8};
-const uint8_t h_ctx_sign[25] = {14, 14, 15, 16, 16, 14, 14, 15, 16, 16, 13, 13, 12, 13, 13, 16, 16, 15, 14, 14, 16, 16, 15, 14, 14};
-const uint8_t h_sign_pred[25] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 int upload_tables() {
     int dev = 0;
@@ -65,252 +52,131 @@ int upload_tables() {
     if (g_tables_uploaded[dev]) return ICER_RESULT_OK;
     const HostTables &h = icer_host_tables();
     static DevTables d;
-    for (int b = 0; b < 8; b++)
-        for (int v = 0; v < 32; v++) {
-            d.enc[b][v] = (uint16_t) (h.enc[b][v].in_bits | (h.enc[b][v].out_bits << 4) | (h.enc[b][v].out << 8));
-            d.dec[b][v] = (uint16_t) (h.dec[b][v].in_bits | (h.dec[b][v].out_bits << 4) | (h.dec[b][v].out << 8));
-        }
-    memcpy(d.flush, h.flush, sizeof d.flush);
-    // the variable-to-variable codes are complete prefix codes of at most 5 bits: the next 5 stream bits select the
-    // codeword directly (same first-match order as the bit-by-bit loop of icer_decoding.c:155-177)
-    for (int b = 0; b < 8; b++)
-        for (int x = 0; x < 32; x++) {
-            d.dlut[b][x] = 0;
-            for (int L = 1; L <= 5; L++) {
-                const V2VEntry &e = h.dec[b][x & ((1 << L) - 1)];
-                if (e.in_bits == L) { d.dlut[b][x] = (uint16_t) (L | (e.out_bits << 4) | (e.out << 8)); break; }
-            }
-        }
-    for (int b = 0; b < 17; b++) { d.gol_m[b] = h.gol_m[b]; d.gol_l[b] = h.gol_l[b]; d.gol_i[b] = h.gol_i[b]; }
-    for (int b = 0; b < 16; b++) d.cutoff[b] = h.cutoff[b];
+    icer_tables::fill_core_tables(d.enc, h, false);
+    icer_tables::fill_core_tables(d.dec, h, true);
     for (uint32_t n = 0; n < 256; n++) {
         uint32_t c = n;
         for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
         d.crc[n] = c;
     }
-    memcpy(d.ctx_hv, h_ctx_hv, 45); memcpy(d.ctx_hh, h_ctx_hh, 25);
-    memcpy(d.ctx_sign, h_ctx_sign, 25); memcpy(d.sign_pred, h_sign_pred, 25);
     CUDA_TRY(cudaMemcpyToSymbol(c_tab, &d, sizeof d));      // synchronous: complete before any later launch on any stream
     g_tables_uploaded[dev] = true;
     return ICER_RESULT_OK;
 }
 
 // tables every lane needs with divergent indices: staged in shared memory once per block
-struct SmemTables {
-    uint2 cutp[17];            // per bin: (cut-off below it, cut-off above it) with sentinels 0 / 65537 -- one 64-bit load validates a cached bin
-    uint32_t cutoff[16];
-    uint16_t v2v[8][32];
-    uint16_t gol_m[17], gol_l[17], gol_i[17];
-    uint8_t flush[8][9][6];
-    uint8_t ctx_hv[45], ctx_hh[25], ctx_sign[25], sign_pred[25];
-};
-
-__device__ __forceinline__ void load_tables(SmemTables &T, bool decoder) {
-    const int t = threadIdx.x;
-    for (int i = t; i < 8 * 32; i += NT) (&T.v2v[0][0])[i] = decoder ? (&c_tab.dlut[0][0])[i] : (&c_tab.enc[0][0])[i];
-    for (int i = t; i < 8 * 9 * 6; i += NT) (&T.flush[0][0][0])[i] = (&c_tab.flush[0][0][0])[i];
-    for (int i = t; i < 45; i += NT) T.ctx_hv[i] = c_tab.ctx_hv[i];
-    for (int i = t; i < 25; i += NT) { T.ctx_hh[i] = c_tab.ctx_hh[i]; T.ctx_sign[i] = c_tab.ctx_sign[i]; T.sign_pred[i] = c_tab.sign_pred[i]; }
-    for (int i = t; i < 17; i += NT) { T.gol_m[i] = c_tab.gol_m[i]; T.gol_l[i] = c_tab.gol_l[i]; T.gol_i[i] = c_tab.gol_i[i]; }
-    for (int i = t; i < 16; i += NT) T.cutoff[i] = c_tab.cutoff[i];
-    for (int i = t; i < 17; i += NT) T.cutp[i] = make_uint2(i ? c_tab.cutoff[i - 1] : 0u, i < 16 ? c_tab.cutoff[i] : 65537u);
-}
-
-// probability bin: number of cut-offs c with zz * 65536 >= tot * c (icer_util.c:48-56); cut-offs ascend
-__device__ __forceinline__ int bin_of(const SmemTables &T, uint32_t zz, uint32_t tot) {
-    const uint32_t lhs = zz << 16;
-    int bin = 0;
-    if (lhs >= tot * T.cutoff[7]) bin = 8;
-    if (lhs >= tot * T.cutoff[bin + 3]) bin += 4;
-    if (lhs >= tot * T.cutoff[bin + 1]) bin += 2;
-    if (lhs >= tot * T.cutoff[bin]) bin += 1;
-    if (bin == 15 && lhs >= tot * T.cutoff[15]) bin = 16;
-    return bin;
-}
-
-// The bin of a context moves slowly, so each context remembers its last bin (bits 27..31 of its count word); the guess is
-// validated with two products (it holds iff cut[guess-1] * tot <= zz * 65536 < cut[guess] * tot) and the 5-step dependent
-// search only runs when the context has crossed into another bin.
-__device__ __forceinline__ int bin_cached(const SmemTables &T, uint32_t zz, uint32_t tot, int guess) {
-    const uint32_t lhs = zz << 16;
-    const uint2 c = T.cutp[guess];
-    if (lhs >= tot * c.x && lhs < tot * c.y) return guess;
-    return bin_of(T, zz, tot);
-}
-#define CNT_Z(zt) (((zt) >> 16) & 0x7FFu)
-#define CNT_TOT(zt) ((zt) & 0xFFFFu)
-#define CNT_BIN(zt) ((int) ((zt) >> 27))
-#define CNT_PACK(bin, z, tot) (((uint32_t) (bin) << 27) | ((z) << 16) | (tot))
-
-// number of consecutive all-zero decisions, starting at counts (z, tot), that stay in Golomb bin `bin`
-__device__ __forceinline__ uint32_t zeros_in_same_bin(const SmemTables &T, int bin, uint32_t z, uint32_t tot) {
-    if (bin >= 16) return 0x7FFFFFFFu;
-    const uint32_t cut = T.cutoff[bin];
-    const uint32_t num = tot * cut - (z << 16);       // > 0 because the cut-off test for `bin` failed
-    return (num - 1) / (65536u - cut) + 1;
-}
-
-__device__ __forceinline__ int sig(uint32_t v, int plane) { return ((v & 0x7FFF) >> plane) != 0; }
-
-// magnitude context of a pixel of category 0/1/2 (icer_context_modeller.c:355-391)
-__device__ __forceinline__ int mag_context(const SmemTables &T, int cat, int lsb, int sb, uint32_t a0, uint32_t a1, uint32_t a2,
-                                           uint32_t b0, uint32_t b2, uint32_t c0, uint32_t c1, uint32_t c2) {
-    if (cat == 2) return 11;
-    const int prev = lsb + 1;
-    int hh = sig(b0, lsb) + sig(b2, prev);
-    int vv = sig(a1, lsb) + sig(c1, prev);
-    if (cat == 1) return (hh + vv == 0) ? 9 : 10;
-    const int dd = sig(a0, lsb) + sig(a2, lsb) + sig(c0, prev) + sig(c2, prev);
-    if (sb == 1) { const int tmp = hh; hh = vv; vv = tmp; }
-    return (sb == 3) ? T.ctx_hh[(hh + vv) * 5 + dd] : T.ctx_hv[(hh * 3 + vv) * 5 + dd];
-}
-// sign context index into the 5x5 tables (icer_context_modeller.c:404-428)
-__device__ __forceinline__ int sign_index(int lsb, int sb, uint32_t a1, uint32_t b0, uint32_t b2, uint32_t c1) {
-    const int prev = lsb + 1;
-    int shh = 2 - (int) ((b0 >> 15) & sig(b0, lsb)) - (int) ((b2 >> 15) & sig(b2, prev));
-    int svv = 2 - (int) ((a1 >> 15) & sig(a1, lsb)) - (int) ((c1 >> 15) & sig(c1, prev));
-    if (sb == 1) { const int tmp = shh; shh = svv; svv = tmp; }
-    return shh * 5 + svv;
+__device__ __forceinline__ void stage_tables(CoreTables &T, const CoreTables &src, int nthreads) {
+    static_assert(sizeof(CoreTables) % 4 == 0, "CoreTables is copied word by word");
+    uint32_t *d = reinterpret_cast<uint32_t *>(&T);
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(&src);
+    for (int i = threadIdx.x; i < (int) (sizeof(CoreTables) / 4); i += nthreads) d[i] = s[i];
 }
 
 // =========================================================================================================
-// Frame-interleaved coefficient layout ("T" layout)
+// Bit slices
 // =========================================================================================================
-// The coder kernels give every LANE of a warp the same stream of a different FRAME (32 consecutive frames = one
-// group): identical geometry, so all loop bounds and edge tests are warp-uniform, and similar statistics, so the
-// lanes mostly take the same branches.  To make their pixel accesses one coalesced 64-byte line, the sign-magnitude
-// coefficients are stored as  T[group][channel][y][x][lane]  (uint16).  These two kernels convert between the planar
-// frame layout the wavelet kernels use and T; the decode-side one also undoes sign-magnitude and adds the LL mean
-// (icer_compress.c:520-531).
+// A SLOT is one chunk of ICER_CHUNK (30) pixels of one row of one unit (segment); slots of a unit are numbered row-major from the
+// unit's slot0.  For every slot the slice buffer holds F fields of 32 words (one per frame of the group):
+//     [group][slot][field][lane]      word bit b <-> plane column x0 - 1 + b  (bit 0 / bit 31: the neighbours left / right of the chunk,
+//                                                                                zero outside the unit)
+// Encoder fields (K3 writes, K4 reads), P = planes coded, PS = min(P + 2, 14):
+//     B_p (p < P): p            S_p (1 <= p <= PS): P + p - 1            N (sign): P + PS                F = P + PS + 1
+//     (S_0 = S_1 | B_0; S_p = 0 for p > 14: magnitudes have 15 bits; the coder of plane lsb needs S up to lsb + 3, and the bits ABOVE the
+//      top coded plane matter: they make encoder and decoder disagree for such coefficients exactly like lib_icer's do)
+// Decoder fields (K7 writes and reads, K8 reads):
+//     B_p: p            S_p (0 <= p < P): P + p            N_p (signs known after plane p, 0 <= p < P): 2P + p            F = 3P
+//     (nothing is known above the top coded plane: S_p = N_p = 0 for p >= P)
+struct SliceGeom { int P, PS, F; };
+__host__ __device__ inline SliceGeom enc_geom(int P) { SliceGeom g; g.P = P; g.PS = P + 2 < 14 ? P + 2 : 14; g.F = P + g.PS + 1; return g; }
+__host__ __device__ inline int dec_fields(int P) { return 3 * P; }
 
-__global__ void __launch_bounds__(256) k_frames_to_T(const uint16_t *__restrict__ src, uint16_t *__restrict__ T, uint32_t nframes,
-                                                     uint32_t chan, uint32_t plane_px) {
-    // block: 32 frames (one group) x 32 consecutive pixels of one channel
-    __shared__ uint16_t tile[32][34];
-    const uint32_t g = blockIdx.z, c = blockIdx.y;
-    const size_t px0 = (size_t) blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32
-    for (int f = ty; f < 32; f += 8) {
-        const uint32_t frame = g * 32 + f;
-        const size_t px = px0 + tx;
-        tile[f][tx] = (frame < nframes && px < plane_px) ? src[((size_t) frame * chan + c) * plane_px + px] : (uint16_t) 0;
-    }
-    __syncthreads();
-    for (int q = ty; q < 32; q += 8) {
-        const size_t px = px0 + q;
-        if (px < plane_px) T[(((size_t) g * chan + c) * plane_px + px) * 32 + tx] = tile[tx][q];
+template <bool B8>
+__device__ __forceinline__ uint32_t to_signmag16(uint32_t v) {          // icer_wavelet.c:871-877 (uint8 codec: :851-857, sign kept in bit 15)
+    const int s = (int) (int16_t) v;
+    return s < 0 ? (uint32_t) ((-s) & (B8 ? 0x7F : 0x7FFF)) | 0x8000u : (uint32_t) s;
+}
+
+// K3: planar coefficients -> encoder slices.  Block = 32 warps = the 32 frames of a group; a warp reads the 32 window columns of its
+// frame (one 64-byte access) and turns every field into a word with one ballot; the block then writes the slot's F x 32 words as
+// F contiguous 128-byte lines.
+__global__ void __launch_bounds__(1024) k_bitslice(const uint16_t *__restrict__ coefs, uint32_t *__restrict__ bs, const SlotDesc *__restrict__ slots,
+                                                   const Unit *__restrict__ units, uint32_t nslots, uint32_t nframes, uint32_t chan, uint32_t W, uint32_t H,
+                                                   int P, int twos) {
+    __shared__ uint32_t tile[32][33];
+    const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.y;
+    const uint32_t frame = g * 32 + f;
+    const SliceGeom G = enc_geom(P);
+    for (uint32_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+        const SlotDesc d = slots[slot];
+        const uint32_t ch = units[d.unit].chan;
+        const bool inwin = (lane >= 1 && lane <= (int) d.ncols) || (lane == 0 && (d.flags & 1)) || (lane == (int) d.ncols + 1 && (d.flags & 2));
+        uint32_t v = 0;
+        if (inwin && frame < nframes) v = coefs[(((size_t) frame * chan + ch) * H + d.y) * W + d.x0 - 1 + lane];
+        if (twos) v = to_signmag16<false>(v);
+        const uint32_t mag = v & 0x7FFFu;
+        uint32_t mine = 0;
+        for (int p = 0; p < P; p++) {
+            const uint32_t w = __ballot_sync(0xffffffffu, (mag >> p) & 1u);
+            if (lane == p) mine = w;
+        }
+        for (int p = 1; p <= G.PS; p++) {
+            const uint32_t w = __ballot_sync(0xffffffffu, (mag >> p) != 0u);
+            if (lane == P + p - 1) mine = w;
+        }
+        {
+            const uint32_t w = __ballot_sync(0xffffffffu, (v >> 15) & 1u);
+            if (lane == P + G.PS) mine = w;
+        }
+        tile[lane][f] = mine;
+        __syncthreads();
+        uint32_t *dst = bs + ((size_t) g * nslots + slot) * G.F * 32;
+        if ((int) threadIdx.x < G.F * 32) dst[threadIdx.x] = tile[threadIdx.x >> 5][threadIdx.x & 31];
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(256) k_T_to_frames(const uint16_t *__restrict__ T, uint16_t *__restrict__ dst,
-                                                     const int32_t *__restrict__ frame_of, const uint16_t *__restrict__ mean,
-                                                     uint32_t chan, uint32_t plane_px, uint64_t cap_px, int W, int llw, int llh,
-                                                     int bits8) {
-    __shared__ uint16_t tile[32][34];
-    const uint32_t g = blockIdx.z, c = blockIdx.y;
-    const size_t px0 = (size_t) blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int q = ty; q < 32; q += 8) {
-        const size_t px = px0 + q;
-        tile[q][tx] = px < plane_px ? T[(((size_t) g * chan + c) * plane_px + px) * 32 + tx] : (uint16_t) 0;
-    }
-    __syncthreads();
-    for (int f = ty; f < 32; f += 8) {
-        const int32_t frame = frame_of[g * 32 + f];
-        const size_t px = px0 + tx;
-        if (frame < 0 || px >= plane_px) continue;
-        uint32_t v = tile[tx][f];
+// K8: decoder slices -> planar coefficients.  Warp = frame, lane = window column.  Which planes of a (frame, unit) count is decided
+// by their status bytes: a plane is decoded only if it and every plane above it are present (icer_partition.c:431), and lib_icer
+// stops a chain at the first plane that fails (:441) -- that plane keeps the bits it decoded before the error, the planes below
+// were decoded ahead of time by the pipeline and are ignored here.  Also undoes sign-magnitude (icer_wavelet.c:880-886) and adds the
+// header LL mean (icer_compress.c:520-531).
+enum { PST_OK = 0, PST_ERROR = 1, PST_ABSENT = 2 };
+__global__ void __launch_bounds__(1024) k_unslice(const uint32_t *__restrict__ bs, uint16_t *__restrict__ dst, const SlotDesc *__restrict__ slots,
+                                                  const Unit *__restrict__ units, const uint8_t *__restrict__ pstat, const int32_t *__restrict__ frame_of,
+                                                  const uint16_t *__restrict__ mean, uint32_t nslots, uint32_t nunits, uint32_t chan, uint32_t W, uint32_t H,
+                                                  uint64_t cap_px, int P, int llw, int llh, int bits8) {
+    const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.y;
+    const int32_t frame = frame_of[g * 32 + f];
+    if (frame < 0) return;
+    const int F = dec_fields(P);
+    for (uint32_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+        const SlotDesc d = slots[slot];
+        const Unit u = units[d.unit];
+        // lowest plane that counts
+        uint32_t st = PST_OK;
+        if (lane < P) st = pstat[((size_t) frame * nunits + d.unit) * P + lane];
+        const uint32_t flagged = __ballot_sync(0xffffffffu, st != PST_OK), absent = __ballot_sync(0xffffffffu, st == PST_ABSENT);
+        int vp = 0;
+        if (flagged) { const int hp = 31 - __clz((int) flagged); vp = ((absent >> hp) & 1u) ? hp + 1 : hp; }
+        const uint32_t *src = bs + ((size_t) g * nslots + slot) * F * 32 + f;
+        uint32_t wB = 0;
+        if (lane < P && lane >= vp) wB = src[lane * 32];
+        const uint32_t wN = vp < P ? src[(2 * P + vp) * 32] : 0u;        // same address in every lane: one broadcast load
+        uint32_t mag = 0;
+        for (int p = 0; p < P; p++) mag |= ((__shfl_sync(0xffffffffu, wB, p) >> lane) & 1u) << p;
+        if (lane < 1 || lane > (int) d.ncols) continue;
+        uint32_t v = mag ? (mag | (((wN >> lane) & 1u) << 15)) : 0u;
         v = (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;                      // icer_wavelet.c:880-886
-        const int r = (int) (px / (size_t) W), cc = (int) (px % (size_t) W);
-        if (r < llh && cc < llw) {
-            const int m = (int) mean[(size_t) frame * chan + c];
+        const int x = (int) d.x0 - 1 + lane, y = (int) d.y;
+        if (y < llh && x < llw) {
+            const int m = (int) mean[(size_t) frame * chan + u.chan];
             // uint16 API: int16 add (icer_compress.c:524-531); native uint8 API: int8 add of the header value's low byte (:258-265)
             v = bits8 ? (uint32_t) (uint16_t) (int16_t) (int8_t) ((int) (int16_t) v + (int) (int8_t) m)
                       : (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + (int) (int16_t) m);
         }
-        dst[((size_t) frame * chan + c) * cap_px + px] = (uint16_t) v;
-    }
-}
-
-// 128-bit versions: a block moves a tile of 32 frames x 64 pixels; global reads and writes are 16-byte vectors (8 consecutive pixels
-// of one frame on the planar side, 8 frames of one pixel on the T side -- a warp then covers 512 contiguous bytes of T).  The
-// encode-side kernel also applies the sign-magnitude mapping (icer_wavelet.c:871-877), so the planar coefficients are read once.
-// Requirements (else the scalar kernels above): plane_px, cap_px and W multiples of 8, 16-byte aligned bases.
-constexpr int TT_PX = 64, TT_LD = TT_PX + 8;
-
-template <bool SIGNMAG>
-__global__ void __launch_bounds__(256) k_frames_to_T_v(const uint16_t *__restrict__ src, uint16_t *__restrict__ T, uint32_t nframes,
-                                                       uint32_t chan, uint32_t plane_px) {
-    __shared__ __align__(16) uint16_t tile[32][TT_LD];
-    const uint32_t g = blockIdx.z, c = blockIdx.y;
-    const size_t px0 = (size_t) blockIdx.x * TT_PX;
-    const int t = threadIdx.x;
-    {
-        const int f = t >> 3, k = t & 7;
-        const uint32_t frame = g * 32 + f;
-        const size_t px = px0 + 8 * k;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (frame < nframes && px < plane_px) v = *reinterpret_cast<const uint4 *>(src + ((size_t) frame * chan + c) * plane_px + px);
-        if (SIGNMAG) {
-            uint32_t *w = reinterpret_cast<uint32_t *>(&v);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int lo = (int) (int16_t) (w[j] & 0xFFFF), hi = (int) (int16_t) (w[j] >> 16);
-                const uint32_t a = lo < 0 ? ((uint32_t) (-lo) & 0x7FFFu) | 0x8000u : (uint32_t) lo;
-                const uint32_t b = hi < 0 ? ((uint32_t) (-hi) & 0x7FFFu) | 0x8000u : (uint32_t) hi;
-                w[j] = a | (b << 16);
-            }
-        }
-        *reinterpret_cast<uint4 *>(&tile[f][8 * k]) = v;
-    }
-    __syncthreads();
-    {
-        const int px = t >> 2, fq = t & 3;
-        if (px0 + px < plane_px) {
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) w[j] = (uint32_t) tile[8 * fq + 2 * j][px] | ((uint32_t) tile[8 * fq + 2 * j + 1][px] << 16);
-            *reinterpret_cast<uint4 *>(T + (((size_t) g * chan + c) * plane_px + px0 + px) * 32 + 8 * fq) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_T_to_frames_v(const uint16_t *__restrict__ T, uint16_t *__restrict__ dst,
-                                                       const int32_t *__restrict__ frame_of, const uint16_t *__restrict__ mean,
-                                                       uint32_t chan, uint32_t plane_px, uint64_t cap_px, int W, int llw, int llh) {
-    __shared__ __align__(16) uint16_t tile[32][TT_LD];
-    const uint32_t g = blockIdx.z, c = blockIdx.y;
-    const size_t px0 = (size_t) blockIdx.x * TT_PX;
-    const int t = threadIdx.x;
-    {
-        const int px = t >> 2, fq = t & 3;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (px0 + px < plane_px) v = *reinterpret_cast<const uint4 *>(T + (((size_t) g * chan + c) * plane_px + px0 + px) * 32 + 8 * fq);
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(&v);
-#pragma unroll
-        for (int j = 0; j < 4; j++) { tile[8 * fq + 2 * j][px] = (uint16_t) (w[j] & 0xFFFF); tile[8 * fq + 2 * j + 1][px] = (uint16_t) (w[j] >> 16); }
-    }
-    __syncthreads();
-    {
-        const int f = t >> 3, k = t & 7;
-        const int32_t frame = frame_of[g * 32 + f];
-        const size_t px = px0 + 8 * k;
-        if (frame < 0 || px >= plane_px) return;
-        uint4 v = *reinterpret_cast<const uint4 *>(&tile[f][8 * k]);
-        uint32_t *w = reinterpret_cast<uint32_t *>(&v);
-        const int r = (int) (px / (size_t) W), cc = (int) (px % (size_t) W);       // the 8 pixels lie in one row (W % 8 == 0)
-        const int m = (int) (int16_t) mean[(size_t) frame * chan + c];
-        const bool ll_row = r < llh;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t a = w[j] & 0xFFFF, b = w[j] >> 16;
-            a = (a & 0x8000u) ? ((0x8000u - a) & 0xFFFFu) : a;                      // icer_wavelet.c:880-886
-            b = (b & 0x8000u) ? ((0x8000u - b) & 0xFFFFu) : b;
-            if (ll_row && cc + 2 * j < llw) a = (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) a + m);        // icer_compress.c:524-531
-            if (ll_row && cc + 2 * j + 1 < llw) b = (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) b + m);
-            w[j] = a | (b << 16);
-        }
-        *reinterpret_cast<uint4 *>(dst + ((size_t) frame * chan + c) * cap_px + px) = v;
+        dst[((size_t) frame * chan + u.chan) * cap_px + (size_t) y * W + x] = (uint16_t) v;
     }
 }
 
@@ -318,145 +184,27 @@ __global__ void __launch_bounds__(256) k_T_to_frames_v(const uint16_t *__restric
 // K4: encoder
 // =========================================================================================================
 struct EncSmem {
-    SmemTables T;
-    uint32_t cnt[17][NT];      // zero << 16 | total, per context
+    CoreTables T;
+    uint32_t cnt[17][NT];      // cached bin << 27 | zero << 16 | total, per context
     uint16_t bseq[17][NT];     // sequence number (low 16 bits; the window spans 2048) of the codeword each bin is building
-    uint32_t bst[17][NT];      // Golomb: zeros counted; custom: input word (first bit = bit 0) | bits gathered << 16
-#if ICER_ENC_MINI > 0
-    uint16_t mini[ICER_ENC_MINI][NT];   // parked codewords close to the emission point (see Enc::complete)
-#endif
-};
-
-// Interleave-window bookkeeping.  A codeword gets a sequence number when its first bit arrives (lib_icer: a ring
-// slot, icer_encoding.c:59-67); `head` is the next sequence number to emit.  Everything in [head, oldest open) is
-// complete by construction, so only codewords that complete BEHIND an older open one are parked in the ring.
-struct Enc {
-    EncSmem &S;
-    const int t;
-    uint16_t *ring;
-    uint32_t *out;
-    uint32_t cap, nwords = 0;
-    unsigned long long acc = 0;
-    int nacc = 0;
-    uint32_t head = 0, tail = 0, open_mask = 0;   // head: first sequence number that is not complete yet (lib_icer's head)
-    uint32_t emit_pos = 0;                        // next sequence number to pack into the payload (<= head)
-    // bits 24.. of open_mask: which slots of S.mini hold a parked codeword (one register for both masks)
-    int oldest = 0;
-    bool overflow = false;
-
-    __device__ Enc(EncSmem &s, int tid, uint16_t *r, uint32_t *o, uint32_t c) : S(s), t(tid), ring(r), out(o), cap(c) {}
-
-    __device__ __forceinline__ uint32_t golomb_word(int bin, uint32_t k, uint32_t &nb) {   // icer_encoding.c:72-77
-        const uint32_t i = S.T.gol_i[bin], l = S.T.gol_l[bin];
-        const uint32_t longer = k >= i;
-        nb = l + longer;
-        return __brev(k + (longer ? i : 0)) >> (32 - nb);
-    }
-
-    // codeword of `bin` is complete (single call site in the pixel loop): park it in the ring; if it was the oldest
-    // one, everything up to the next open codeword is now ready for emission
-    __device__ __forceinline__ void complete(int bin, uint32_t code, uint32_t nb) {
-        const uint32_t seq = S.bseq[bin][t];
-        open_mask &= ~(1u << bin);
-#if ICER_ENC_MINI > 0
-        // a parked entry is live until emitted, and emit_pos only grows: every live entry of the small window has a sequence
-        // number in [emit_pos, emit_pos + ICER_ENC_MINI), so slot = seq mod ICER_ENC_MINI is unambiguous (checked in pump())
-        if (((seq - emit_pos) & 0xFFFFu) < (uint32_t) ICER_ENC_MINI) {
-            S.mini[seq & (ICER_ENC_MINI - 1)][t] = (uint16_t) ((nb << 11) | code);
-            open_mask |= 0x1000000u << (seq & (ICER_ENC_MINI - 1));
-        } else
-#endif
-        ring[seq & (ICER_RING - 1)] = (uint16_t) ((nb << 11) | code);
-        if (seq != (head & 0xFFFFu)) return;
-        const uint32_t h1 = head + 1;
-        uint32_t dist = tail - h1;                       // every other open codeword lies in [head + 1, tail)
-        for (uint32_t m = open_mask & 0x1FFFFu; m; m &= m - 1) {
-            const int b = __ffs(m) - 1;
-            const uint32_t d = ((uint32_t) S.bseq[b][t] - h1) & 0xFFFFu;
-            if (d < dist) { dist = d; oldest = b; }
-        }
-        head = h1 + dist;
-    }
-
-    // pack one ready codeword into the payload, LSB first (icer_encoding.c:114-139).  Called from ONE convergent site
-    // per pixel so that the lanes of a warp emit together instead of each draining its backlog alone.
-    __device__ __forceinline__ void pump() {
-        if (emit_pos == head) return;
-#if ICER_ENC_MINI > 0
-        uint32_t v;
-        const uint32_t slot = emit_pos & (ICER_ENC_MINI - 1);
-        if ((open_mask >> (24 + slot)) & 1u) { v = S.mini[slot][t]; open_mask &= ~(0x1000000u << slot); }
-        else v = ring[emit_pos & (ICER_RING - 1)];
-#else
-        const uint32_t v = ring[emit_pos & (ICER_RING - 1)];
-#endif
-        emit_pos++;
-        acc |= (unsigned long long) (v & 0x7FF) << nacc;
-        nacc += (int) (v >> 11);
-        if (nacc >= 32) {
-            if (nwords < cap) out[nwords] = (uint32_t) acc; else overflow = true;
-            nwords++;
-            acc >>= 32;
-            nacc -= 32;
-        }
-    }
-
-    // the word a forced completion gives the oldest codeword (icer_encoding.c:141-189): window full, or end of stream
-    __device__ __forceinline__ uint32_t forced_word(int bin, uint32_t &nb) {
-        const uint32_t st = S.bst[bin][t];
-        if (bin > 7) {
-            if (st == (uint32_t) S.T.gol_m[bin] - 1) { nb = 1; return 1; }
-            return golomb_word(bin, st, nb);
-        }
-        const uint32_t pre = st & 0xFFFF, fill = st >> 16;
-        const uint32_t fl = S.T.flush[bin][pre][fill];
-        const uint32_t word = (pre | ((fl & 0xF) << fill)) & 0x3FF;
-        const uint32_t e = S.T.v2v[bin][word & 31];
-        nb = (e >> 4) & 0xF;
-        return e >> 8;
-    }
-    // true when `bin` needs a new codeword but 2048 are already outstanding (icer_encoding.c:59-64)
-    __device__ __forceinline__ bool window_full_for(int bin) const {
-        return !((open_mask >> bin) & 1u) && tail - head >= ICER_RING;
-    }
-    // make sure `bin` has an open codeword (icer_encoding.c:56-67); the caller has dealt with a full window
-    __device__ __forceinline__ void open_bin(int bin) {
-        if (open_mask & (1u << bin)) return;
-        while (tail - emit_pos >= ICER_RING) pump();       // physical ring space (emission may lag behind `head`)
-        if ((open_mask & 0x1FFFFu) == 0) oldest = bin;
-        S.bseq[bin][t] = (uint16_t) tail++;
-        S.bst[bin][t] = 0;
-        open_mask |= 1u << bin;
-    }
-
-    __device__ void finish(uint32_t &bits_out) {
-        while (open_mask & 0x1FFFFu) {                         // icer_context_modeller.c:452-455
-            uint32_t nb;
-            const int bin = oldest;
-            const uint32_t code = forced_word(bin, nb);
-            complete(bin, code, nb);
-        }
-        while (emit_pos != head) pump();
-        bits_out = nwords * 32u + (uint32_t) nacc;
-        if (nacc > 0) { if (nwords < cap) out[nwords] = (uint32_t) acc; else overflow = true; }
-    }
+    uint32_t bst[17][NT];      // Golomb: zeros counted; variable-to-variable: input word (first bit = bit 0) | bits gathered << 16
+    uint16_t mini[ICER_ENC_MINI > 0 ? ICER_ENC_MINI : 1][NT];   // parked codewords close to the emission point
 };
 
 // One warp per (frame group, stream); lane = frame of the group.
-__global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
+__global__ void __launch_bounds__(NT, ICER_ENC_MINBLOCKS) k_encode(EncodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EncSmem &S = *reinterpret_cast<EncSmem *>(smem_raw);
     const int t = threadIdx.x;
-    load_tables(S.T, false);
+    stage_tables(S.T, c_tab.enc, NT);
     __syncthreads();
 
+    const int P = (int) a.planes;
+    const SliceGeom G = enc_geom(P);
     const uint32_t nstreams = a.nunits * a.planes;
     const unsigned long long total = (unsigned long long) a.ngroups * (a.list ? a.nlist : nstreams);
     const int lane = t & 31;
     uint16_t *ring = a.rings + (size_t) (blockIdx.x * NT + t) * ICER_RING;
-    const size_t plane_px = (size_t) a.w * a.h;
-    const int W = (int) a.w;
-    const int RS = W * 32;     // row stride of the T layout, in elements
 
     for (;;) {
         unsigned long long wid = 0;
@@ -470,146 +218,42 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
         const int lsb = (int) (s % a.planes);
         const uint32_t frame = g * 32 + lane;
         const bool valid = frame < a.nframes;
-        const uint16_t *seg = a.coefsT + (((size_t) g * a.chan + u.chan) * plane_px + (size_t) u.y * W + u.x) * 32 + lane;
-        Enc cd(S, t, ring, valid ? a.scratch + (size_t) frame * a.scratch_words + a.soff[s] : nullptr, valid ? a.scap[s] : 0);
-#pragma unroll
-        for (int c = 0; c < 17; c++) S.cnt[c][t] = (2u << 16) | 4u;    // icer.h:147-148
-        const int sw = u.w, sh = u.h, sb = u.subband;
-
-        uint32_t fz_left = 0, fz_run = 0;    // quiet fast path: zeros still absorbable / absorbed but not yet applied
-        int fz_bin = 0;
-
-        for (int row = 0; row < sh; row++) {
+        icer_core::EncLane<NT, ICER_ENC_MINI> ln(S.T, &S.cnt[0][t], &S.bseq[0][t], &S.bst[0][t], &S.mini[0][t], ring,
+                                                 valid ? a.scratch + (size_t) frame * a.scratch_words + a.soff[s] : nullptr, valid ? a.scap[s] : 0);
+        const int sw = u.w, sh = u.h, sb = u.subband, cw = (int) u.cw;
+        // field offsets (in words) inside a slot; -1: the field is identically zero
+        const int oB = lsb * 32, oN = (P + G.PS) * 32;
+        const int oP = lsb + 1 <= G.PS ? (P + lsb) * 32 : -1, o2 = lsb + 2 <= G.PS ? (P + lsb + 1) * 32 : -1, o3 = lsb + 3 <= G.PS ? (P + lsb + 2) * 32 : -1;
+        const size_t slot_words = (size_t) G.F * 32, row_words = slot_words * cw;
+        const uint32_t *rowp = a.bs + ((size_t) g * a.nslots + u.slot0) * slot_words + lane;
+        for (int row = 0; row < sh; row++, rowp += row_words) {
             const bool up = row > 0, dn = row + 1 < sh;
-            const uint16_t *p = seg + (size_t) row * RS;
-            uint32_t a0 = 0, a1 = up ? p[-RS] : 0, a2, b0 = 0, b1 = p[0], b2, c0 = 0, c1 = dn ? p[RS] : 0, c2;
-            // the column after next is fetched one pixel early so that the loads overlap the coding of this pixel
-            uint32_t a2n = (up && sw > 1) ? p[32 - RS] : 0, b2n = sw > 1 ? p[32] : 0, c2n = (dn && sw > 1) ? p[32 + RS] : 0;
-            for (int col = 0; col < sw; col++, p += 32) {
-                a2 = a2n; b2 = b2n; c2 = c2n;
-                const bool rt2 = col + 2 < sw;
-                a2n = (up && rt2) ? p[64 - RS] : 0;
-                b2n = rt2 ? p[64] : 0;
-                c2n = (dn && rt2) ? p[64 + RS] : 0;
-                const uint32_t v = b1;
-                const bool quiet = ((((a0 | a1 | a2 | b0 | b1 | b2 | c0 | c1 | c2) & 0x7FFF) >> lsb) == 0);
-                // micro-ops: bit0 = apply the pending fast run, bit1 = magnitude decision, bit2 = sign decision
-                uint32_t todo;
-                if (quiet && fz_left) { fz_run++; fz_left--; todo = 0; }
-                else todo = (fz_run ? 1u : 0u) | 2u;
-                int cat = 0;
-                uint32_t mbit = 0;
-                if (todo & 2u) {
-                    const int msb = 31 - __clz((v & 0x7FFF) | 1);
-                    cat = msb - lsb;                                   // icer_context_modeller.c:631-634
-                    cat = cat < 0 ? 0 : (cat > 3 ? 3 : cat);
-                    mbit = (v >> lsb) & 1;
-                    if (cat == 0 && mbit) todo |= 4u;                  // first 1 of this coefficient: its sign follows
+            const uint32_t *p = rowp;
+            for (int j = 0; j < cw; j++, p += slot_words) {
+                const int ncols = sw - j * ICER_CHUNK < ICER_CHUNK ? sw - j * ICER_CHUNK : ICER_CHUNK;
+                icer_core::EncChunk k;
+                {
+                    const uint32_t *pa = p - row_words, *pc = p + row_words;
+                    const uint32_t bP = oP >= 0 ? p[oP] : 0u, bB = p[oB], bN = p[oN];
+                    const uint32_t b2 = o2 >= 0 ? p[o2] : 0u, b3 = o3 >= 0 ? p[o3] : 0u;
+                    const uint32_t aP = (up && oP >= 0) ? pa[oP] : 0u, aB = up ? pa[oB] : 0u, aN = up ? pa[oN] : 0u;
+                    const uint32_t cP = (dn && oP >= 0) ? pc[oP] : 0u, cN = dn ? pc[oN] : 0u;
+                    k.set(aP, aB, aN, bP, bB, bN, b2, b3, cP, cN, ncols);
                 }
-                while (todo) {
-                    const int st = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    bool done = false;
-                    uint32_t code = 0, nb = 0;
-                    int bin = 0;
-                    if (st == 0) {
-                        // apply `fz_run` (context 0, bit 0) decisions at once
-                        bin = fz_bin;
-                        const uint32_t zt = S.cnt[0][t];
-                        uint32_t z = CNT_Z(zt) + fz_run, tot = CNT_TOT(zt) + fz_run;
-                        if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
-                        S.cnt[0][t] = CNT_PACK(bin, z, tot);
-                        const uint32_t k = S.bst[bin][t] + fz_run;
-                        if (k >= S.T.gol_m[bin]) { done = true; code = 1; nb = 1; }
-                        else S.bst[bin][t] = k;
-                        fz_run = 0; fz_left = 0;
-                    } else {
-                        uint32_t bit;
-                        if (st == 1 && cat == 3) {
-                            bit = mbit; bin = 0;                              // p(0) = 1/2 -> uncoded bin
-                            if (cd.window_full_for(0)) {
-                                bin = cd.oldest; code = cd.forced_word(bin, nb); done = true; todo |= 1u << st;
-                                goto emit_site;
-                            }
-                        } else {
-                            int ctx;
-                            if (st == 1) {
-                                ctx = mag_context(S.T, cat, lsb, sb, a0, a1, a2, b0, b2, c0, c1, c2);
-                                bit = mbit;
-                            } else {
-                                const int si = sign_index(lsb, sb, a1, b0, b2, c1);
-                                ctx = S.T.ctx_sign[si];
-                                bit = (S.T.sign_pred[si] ^ (v >> 15)) & 1;
-                            }
-                            const uint32_t zt = S.cnt[ctx][t];
-                            uint32_t z = CNT_Z(zt), tot = CNT_TOT(zt);
-                            uint32_t zz = z;
-                            const bool inv = zz < (tot >> 1);
-                            if (inv) zz = tot - zz;
-                            bin = bin_cached(S.T, zz, tot, CNT_BIN(zt));
-                            const int cbin = bin;
-                            if (cd.window_full_for(bin)) {
-                                // window full: force-complete the oldest codeword first, then redo this decision
-                                bin = cd.oldest; code = cd.forced_word(bin, nb); done = true; todo |= 1u << st;
-                                goto emit_site;
-                            }
-                            if (st == 1 && quiet && !inv && bin > 7) {
-                                // enter the quiet fast path: this and the following quiet pixels only bump counters
-                                cd.open_bin(bin);
-                                const uint32_t n1 = (uint32_t) S.T.gol_m[bin] - S.bst[bin][t];
-                                const uint32_t n2 = zeros_in_same_bin(S.T, bin, z, tot);
-                                const uint32_t n3 = 500u - tot;
-                                fz_left = min(n1, min(n2, n3)) - 1;
-                                fz_run = 1;
-                                fz_bin = bin;
-                                continue;
-                            }
-                            tot++;
-                            z += bit ^ 1u;
-                            if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }   // icer_context_modeller.c:396-402
-                            S.cnt[ctx][t] = CNT_PACK(cbin, z, tot);
-                            bit ^= inv ? 1u : 0u;
-                        }
-                        cd.open_bin(bin);
-                        if (bin > 7) {                                        // Golomb run-length bins
-                            if (bit) {
-                                code = cd.golomb_word(bin, S.bst[bin][t], nb);
-                                done = true;
-                            } else {
-                                const uint32_t k = S.bst[bin][t] + 1;
-                                S.bst[bin][t] = k;
-                                if (k >= S.T.gol_m[bin]) { code = 1; nb = 1; done = true; }
-                            }
-                        } else if (bin != 0) {                                // variable-to-variable bins
-                            const uint32_t stt = S.bst[bin][t];
-                            const uint32_t fill = stt >> 16;
-                            const uint32_t word = (stt & 0xFFFF) | (bit << fill);
-                            const uint32_t e = S.T.v2v[bin][word & 31];
-                            if ((e & 0xF) == fill + 1) { code = e >> 8; nb = (e >> 4) & 0xF; done = true; }
-                            else S.bst[bin][t] = word | ((fill + 1) << 16);
-                        } else {                                              // uncoded bin
-                            code = bit & 1; nb = 1; done = true;
-                        }
-                    }
-                emit_site:
-                    if (done) cd.complete(bin, code, nb);
+                ln.begin_chunk();
+                for (;;) {
+                    const bool busy = !ln.chunk_done(ncols);
+                    if (!__any_sync(0xffffffffu, busy)) break;
+                    if (busy) ln.step(k, sb);
+                    ln.pump();
                 }
-                cd.pump();       // up to two codewords can start per pixel, so two emissions keep pace
-                cd.pump();
-                a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
             }
         }
-        if (fz_run) {   // tail of a fast run
-            const int bin = fz_bin;
-            const uint32_t k = S.bst[bin][t] + fz_run;
-            if (k >= S.T.gol_m[bin]) cd.complete(bin, 1, 1);
-            else S.bst[bin][t] = k;
-        }
         uint32_t bits;
-        cd.finish(bits);
+        ln.finish(bits);
         if (valid) {
             a.bits[(size_t) frame * nstreams + s] = bits;
-            if (cd.overflow) atomicOr(a.overflow, 1);
+            if (ln.overflow) atomicOr(a.overflow, 1);
         }
         __syncwarp();
     }
@@ -618,17 +262,13 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
 // =========================================================================================================
 // K7: decoder
 // =========================================================================================================
-// One BLOCK per (frame group, chain): warp j decodes bit plane (planes-1-j) of the chain for the 32 frames of the
-// group.  The warps form a pipeline: warp j may process pixel n once warp j-1 has finished pixel n + w + 1 (its
-// right/down neighbours are taken one plane up).  Progress is published in shared memory; a warp advances only when
-// all of its live lanes can, so its position -- and therefore every address and edge test -- stays warp-uniform.
-// Work items of the decoder are TASKS (chain, bit plane).  A block is a pool of DEC_WARPS warps that take tasks in
-// order (chain-major, most significant plane first); task (c, p) may process pixel n of frame f once task (c, p+1)
-// has finished pixel n + w + 1 of that frame (its right/down neighbours are taken one plane up).  A task with a
-// smaller number has always been taken by some warp already, so waiting on it cannot deadlock; there is no block
-// barrier anywhere, so the quick (quiet) upper planes run ahead into the next chains while the dense lower planes are
-// still being decoded.  Chains in flight occupy one of DEC_SLOTS slots of progress / flag state in shared memory.
-// Pool size (measured on config 2, k_decode ms): 8 warps x 4 blocks/SM 42.1, 16 x 2 38.0, 24 x 1 40.7, 32 x 1 (12 slots) 36.1 --
+// Work items of the decoder are TASKS (chain, bit plane).  A block is a pool of DEC_WARPS warps that take tasks in order
+// (chain-major, most significant plane first); task (c, p) may process slot n of the unit once task (c, p+1) has STORED slot
+// n + cw + 1 (the words of the row below, incl. the halo bit that depends on the chunk after it).  A task with a smaller number has
+// always been taken by some warp already, so waiting on it cannot deadlock; there is no block barrier anywhere, so the quick (quiet)
+// upper planes run ahead into the next chains while the dense lower planes are still being decoded.  Chains in flight occupy one of
+// DEC_SLOTS slots of progress state in shared memory.
+// Pool size (round 1, config 2, k_decode ms): 8 warps x 4 blocks/SM 42.1, 16 x 2 38.0, 24 x 1 40.7, 32 x 1 (12 slots) 36.1 --
 // one SM-wide pool balances the very unequal planes of a chain best (profiles/README.md).
 #ifndef ICER_DEC_WARPS
 #define ICER_DEC_WARPS 32
@@ -639,14 +279,11 @@ __global__ void __launch_bounds__(NT, 8) k_encode(EncodeArgs a) {
 #ifndef ICER_DEC_MINBLOCKS
 #define ICER_DEC_MINBLOCKS 1
 #endif
-#ifndef ICER_DEC_RECHECK
-#define ICER_DEC_RECHECK 32          /* pixels a plane decodes between two looks at the progress of the plane above */
-#endif
 #ifndef ICER_DEC_BACKOFF_NS
-#define ICER_DEC_BACKOFF_NS 5000     /* sleep when the plane above is not far enough ahead */
+#define ICER_DEC_BACKOFF_NS 2000     /* sleep when the plane above is not far enough ahead */
 #endif
 #ifndef ICER_DEC_SLOTWAIT_NS
-#define ICER_DEC_SLOTWAIT_NS 20000    /* poll interval while a chain waits for a free slot (chains last milliseconds) */
+#define ICER_DEC_SLOTWAIT_NS 20000   /* poll interval while a chain waits for a free slot (chains last milliseconds) */
 #endif
 #ifndef ICER_DEC_CHAINWAIT_NS
 #define ICER_DEC_CHAINWAIT_NS 5000   /* poll interval while a plane waits for its chain's slot to be published */
@@ -657,120 +294,19 @@ constexpr int DEC_SLOTS = ICER_DEC_SLOTS;
 
 struct DecSlot {
     volatile uint32_t chain;             // chain ordinal (within this block) that owns the slot; ~0 = never used
-    volatile uint32_t freed;             // all planes done and cleaned up: the slot may be re-used
+    volatile uint32_t freed;             // all planes done: the slot may be re-used
     volatile uint32_t done;              // planes finished
-    volatile uint32_t anyerr;            // some lane hit a decode error (rare): only then are deadf / errf consulted
-    volatile unsigned long long wid;     // global work id = group * nunits + unit
-    volatile uint32_t prog[15];          // pixels completed per plane (warp-uniform position)
-    volatile uint32_t posd[15][32];      // per lane: pixels it has (possibly) written -- needed to undo a voided plane
-    volatile uint8_t deadf[15][32];      // lane's plane is void because a plane above it hit a decode error
-    volatile uint8_t errf[15][32];       // lane hit a decode error in this plane
+    volatile unsigned long long wid;     // global work id = unit * ngroups + group
+    volatile uint32_t prog[15];          // slots STORED per plane (warp-uniform)
 };
 struct DecShared {
-    SmemTables T;
+    CoreTables T;
     DecSlot slot[DEC_SLOTS];
     uint32_t next_task;
     volatile uint32_t fetch_turn;        // chain ordinal whose first task may fetch its global work id next
     volatile uint32_t k_end;             // first chain ordinal that does not exist (work exhausted)
 };
 // followed in dynamic shared memory by: cnt[17][DEC_BT] u32, stlow[17][DEC_BT] u32, depth[17][DEC_BT] i16
-
-struct Dec {
-    const SmemTables &T;
-    const uint32_t *wp = nullptr;   // next aligned stream word to load
-    int left = 0;                   // bytes from wp to the end of THIS FRAME's stream (bytes at or beyond it read as zero, like the oracle and the legacy calls)
-    unsigned long long bb = 0;      // bit buffer, LSB = next stream bit
-    int bbn = 0;                    // bits in bb that came from loads (zeros beyond)
-    uint32_t total_bits = 0;
-    uint32_t consumed = 0;          // bits consumed
-    uint32_t words = 0;             // codewords consumed
-
-    __device__ Dec(const SmemTables &tt) : T(tt) {}
-
-    __device__ __forceinline__ uint32_t load_word() {
-        uint32_t w = 0;
-        if (left >= 4) w = *wp;
-        else if (left > 0) {           // tail: byte loads, nothing behind `end` is touched (the caller's buffer may stop there)
-            const uint8_t *bp = reinterpret_cast<const uint8_t *>(wp);
-            w = bp[0];
-            if (left > 1) w |= (uint32_t) bp[1] << 8;
-            if (left > 2) w |= (uint32_t) bp[2] << 16;
-        }
-        wp++;
-        left -= 4;
-        return w;
-    }
-    __device__ __forceinline__ void start(const uint8_t *base, const uint8_t *e, uint32_t nbits) {
-        total_bits = nbits;
-        const uintptr_t ad = reinterpret_cast<uintptr_t>(base);
-        wp = reinterpret_cast<const uint32_t *>(ad & ~(uintptr_t) 3);
-        const ptrdiff_t room = e - reinterpret_cast<const uint8_t *>(wp);
-        left = room > 0x7FFFFFF0 ? 0x7FFFFFF0 : (int) room;
-        const int sh = (int) (ad & 3) * 8;
-        bb = (unsigned long long) (load_word() >> sh);
-        bbn = 32 - sh;
-    }
-    __device__ __forceinline__ void fill() {           // afterwards at least 33 valid bits are buffered
-        if (bbn <= 32) { bb |= (unsigned long long) load_word() << bbn; bbn += 32; }
-    }
-    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t) bb & ((1u << n) - 1u); }
-    __device__ __forceinline__ void skip(uint32_t n) { bb >>= n; bbn -= (int) n; consumed += n; }
-
-    // icer_get_bits_from_codeword / icer_pop_bits_from_codeword (icer_decoding.c:59-105): byte-chunked read that
-    // fails only when a chunk is larger than the whole segment (`decoded_bits_total` is never advanced there)
-    __device__ __forceinline__ int rd(uint32_t n, bool consume) {
-        if (total_bits < 8) {
-            uint32_t off = consumed & 7, left = n;
-            while (left) {
-                uint32_t take = 8 - off; if (take > left) take = left;
-                if (take > total_bits) return ICER_DECODER_OUT_OF_DATA;
-                left -= take; off = (off + take) & 7;
-            }
-        }
-        const int v = (int) peek(n);
-        if (consume) skip(n);
-        return v;
-    }
-
-    // refill `bin` with the next codeword (icer_decoding.c:127-181); returns an error code or OK
-    __device__ __forceinline__ int refill(int bin, int &depth, uint32_t &low) {
-        depth = 0; low = 0;
-        fill();
-        if (bin > 7) {
-            const uint32_t l = T.gol_l[bin], gi = T.gol_i[bin];
-            if (peek(1)) {
-                rd(1, true);
-                depth = T.gol_m[bin];
-            } else {
-                uint32_t k = (__brev((uint32_t) rd(l, false) & 0xFFFFu) >> (32 - l)) & 0xFFFFu;
-                if (k < gi) {
-                    rd(l, true);
-                } else {
-                    k = (__brev((uint32_t) rd(l + 1, true) & 0xFFFFu) >> (31 - l)) & 0xFFFFu;
-                    k = (k - gi) & 0xFFFFu;
-                }
-                depth = 1 + (int) k;
-                low = 1;
-            }
-        } else if (bin != 0) {
-            const uint32_t e = T.v2v[bin][peek(5)];
-            const uint32_t L = e & 0xF;
-            if (L == 0) return ICER_DECODED_INVALID_DATA;          // cannot happen: the codes are complete
-            if (L >= total_bits) return ICER_DECODER_OUT_OF_DATA;  // the reference checks n + 1 >= total for every bit it reads
-            low = e >> 8;
-            depth = (int) ((e >> 4) & 0xF);
-            const int word = (int) peek(L);
-            if (word != rd(L, true)) return ICER_DECODED_INVALID_DATA;
-        } else {
-            const int v = rd(1, true);
-            if (v == ICER_DECODER_OUT_OF_DATA) return v;
-            low = v != 0;
-            depth = 1;
-        }
-        words++;
-        return ICER_RESULT_OK;
-    }
-};
 
 __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -779,26 +315,17 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
     constexpr int BT = DEC_BT;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(DecShared) + 15) & ~(size_t) 15));
     uint32_t *stlow = cnt + 17 * BT;
-    int16_t *depthA = reinterpret_cast<int16_t *>(stlow + 17 * BT);     // pending bits of a bin's stack: <= the largest Golomb m (512)
-    {   // tables + pool state
-        for (int i = t; i < 8 * 32; i += BT) (&S.T.v2v[0][0])[i] = (&c_tab.dlut[0][0])[i];
-        for (int i = t; i < 45; i += BT) S.T.ctx_hv[i] = c_tab.ctx_hv[i];
-        for (int i = t; i < 25; i += BT) { S.T.ctx_hh[i] = c_tab.ctx_hh[i]; S.T.ctx_sign[i] = c_tab.ctx_sign[i]; S.T.sign_pred[i] = c_tab.sign_pred[i]; }
-        for (int i = t; i < 17; i += BT) { S.T.gol_m[i] = c_tab.gol_m[i]; S.T.gol_l[i] = c_tab.gol_l[i]; S.T.gol_i[i] = c_tab.gol_i[i]; }
-        for (int i = t; i < 16; i += BT) S.T.cutoff[i] = c_tab.cutoff[i];
-        for (int i = t; i < 17; i += BT) S.T.cutp[i] = make_uint2(i ? c_tab.cutoff[i - 1] : 0u, i < 16 ? c_tab.cutoff[i] : 65537u);
-        if (t < DEC_SLOTS) { S.slot[t].chain = 0xFFFFFFFFu; S.slot[t].freed = 1; S.slot[t].done = 0; S.slot[t].anyerr = 0; }
-        if (t == 0) { S.next_task = 0; S.fetch_turn = 0; S.k_end = 0xFFFFFFFFu; }
-    }
+    int16_t *depthA = reinterpret_cast<int16_t *>(stlow + 17 * BT);
+    stage_tables(S.T, c_tab.dec, BT);
+    if (t < DEC_SLOTS) { S.slot[t].chain = 0xFFFFFFFFu; S.slot[t].freed = 1; S.slot[t].done = 0; }
+    if (t == 0) { S.next_task = 0; S.fetch_turn = 0; S.k_end = 0xFFFFFFFFu; }
     __syncthreads();
     const int lane = t & 31;
     const int P = (int) a.planes;
+    const int F = dec_fields(P);
+    const size_t slot_words = (size_t) F * 32;
     const unsigned long long total = (unsigned long long) a.ngroups * a.nunits;
     const uint32_t nstreams = a.nunits * a.planes;
-    const int W = (int) a.plan_w;
-    const int RS = W * 32;
-    const size_t plane_px = (size_t) a.plan_w * a.plan_h;
-    const bool fast_ok = !(a.debug_flags & 1u);
 
     for (;;) {
         uint32_t task = 0;
@@ -810,11 +337,9 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
         DecSlot &sl = S.slot[k % DEC_SLOTS];
         // ---- claim / find the slot of chain k ------------------------------------------------------------
         if (j == 0) {
-            // The first task of a chain fetches the global work item and recycles the slot of chain k - DEC_SLOTS.
-            // The fetch happens in CHAIN ORDER (ticket S.fetch_turn): work ids then grow with k inside a block, so "chain k
-            // got no work" implies the same for every later chain -- the invariant k_end and the early exits rely on.
-            // (Fetching after the slot wait let a later chain overtake an earlier one; an earlier chain that then drew
-            // the end-of-work id made the warps of the later, valid chain give up: a stall seen with the 32-warp pool.)
+            // The first task of a chain fetches the global work item and recycles the slot of chain k - DEC_SLOTS.  The fetch happens
+            // in CHAIN ORDER (ticket S.fetch_turn): work ids then grow with k inside a block, so "chain k got no work" implies the same
+            // for every later chain -- the invariant k_end and the early exits rely on.
             unsigned long long wid = 0;
             if (lane == 0) {
                 while (S.fetch_turn != k) __nanosleep(40);
@@ -825,16 +350,12 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
             }
             wid = __shfl_sync(0xffffffffu, wid, 0);
             if (wid >= total) break;
-            if (lane == 0 && k >= (uint32_t) DEC_SLOTS)
-                while (!(sl.chain == k - DEC_SLOTS && sl.freed)) __nanosleep(ICER_DEC_SLOTWAIT_NS);     // that chain is live: it will finish
-            __syncwarp();
-            __threadfence_block();
-            for (int q = 0; q < 15; q++) { sl.deadf[q][lane] = 0; sl.errf[q][lane] = 0; sl.posd[q][lane] = 0; }
-            __threadfence_block();
-            __syncwarp();
             if (lane == 0) {
+                if (k >= (uint32_t) DEC_SLOTS)
+                    while (!(sl.chain == k - DEC_SLOTS && sl.freed)) __nanosleep(ICER_DEC_SLOTWAIT_NS);     // that chain is live: it will finish
+                __threadfence_block();
                 for (int q = 0; q < 15; q++) sl.prog[q] = 0;
-                sl.done = 0; sl.anyerr = 0; sl.freed = 0; sl.wid = wid;
+                sl.done = 0; sl.freed = 0; sl.wid = wid;
                 __threadfence_block();
                 sl.chain = k;
             }
@@ -852,7 +373,8 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
         const Unit u = a.units[ui];
         const int32_t frame = a.frame_of[g * 32 + lane];
         bool alive = false;
-        Dec dc(S.T);
+        const uint8_t *pay = nullptr, *fend = nullptr;
+        uint32_t nbits = 0;
         if (frame >= 0) {
             // a plane is decoded only if it and every plane above it are present (icer_partition.c:431)
             const uint32_t *row = a.seg_off + (size_t) frame * nstreams + ui * a.planes;
@@ -866,147 +388,71 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
                 const uint8_t *fbase = a.streams + (size_t) frame * a.stream_stride;
                 const uint64_t flen = a.stream_len[frame] < a.stream_stride ? a.stream_len[frame] : a.stream_stride;
                 const uint8_t *hd = fbase + (off1 - 1);
-                dc.start(hd + ICER_HDR_BYTES, fbase + flen, hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24));
+                pay = hd + ICER_HDR_BYTES; fend = fbase + flen;
+                nbits = hd[16] | (hd[17] << 8) | (hd[18] << 16) | ((uint32_t) hd[19] << 24);
             }
         }
-        uint16_t *seg = a.coefsT + (((size_t) g * a.chan + u.chan) * plane_px + (size_t) u.y * W + u.x) * 32 + lane;
-        const int sw = u.w, sh = u.h, sb = u.subband;
-        const uint32_t px = (uint32_t) sw * (uint32_t) sh;
-        const uint32_t lag = (uint32_t) sw + 2;      // plane p stays this far behind plane p+1 (needs pixel n + w + 1, prefetches n + w + 2)
-#pragma unroll
-        for (int c = 0; c < 17; c++) { cnt[c * BT + t] = (2u << 16) | 4u; depthA[c * BT + t] = 0; stlow[c * BT + t] = 0; }
-
-        uint32_t pos = 0;                  // warp-uniform
-        int row = 0, col = 0;
-        uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0, a2n = 0, b2n = 0, c2n = 0;
-        uint32_t fz_left = 0, fz_run = 0;
-        int fz_bin = 0;
-        bool run = alive;                  // this lane still decodes
-        bool dead = false;                 // voided by an error in a plane above
-        uint32_t done_px = 0;              // pixels this lane has (possibly) written
-
-        while (pos < px && __any_sync(0xffffffffu, run)) {
-            uint32_t limit = px;
-            if (j > 0) {
-                const uint32_t up = sl.prog[j - 1];
+        icer_core::DecLane<BT> ln(S.T, cnt + t, stlow + t, depthA + t, alive);
+        if (alive) ln.br.start(pay, fend, nbits);
+        const int sw = u.w, sh = u.h, sb = u.subband, cw = (int) u.cw;
+        const uint32_t nsl = (uint32_t) sh * (uint32_t) cw;
+        // field offsets (in words); -1: identically zero (nothing is known above the top coded plane)
+        const int oB = lsb * 32, oS = (P + lsb) * 32, oN = (2 * P + lsb) * 32;
+        const int oP = lsb + 1 < P ? (P + lsb + 1) * 32 : -1, o2 = lsb + 2 < P ? (P + lsb + 2) * 32 : -1, o3 = lsb + 3 < P ? (P + lsb + 3) * 32 : -1;
+        const int oNp = lsb + 1 < P ? (2 * P + lsb + 1) * 32 : -1;
+        const size_t row_words = slot_words * cw;
+        uint32_t *base = a.bs + ((size_t) g * a.nslots + u.slot0) * slot_words + lane;
+        uint32_t stored = 0;               // slots of this plane whose words are final (warp-uniform)
+        uint32_t tslot = 0;
+        for (int row = 0; row < sh; row++) {
+            const bool up = row > 0, dn = row + 1 < sh;
+            uint32_t carryB = 0, carryN = 0, pendS = 0, pendN = 0;
+            for (int jc = 0; jc < cw; jc++, tslot++) {
+                if (j > 0) {
+                    // the plane above must have stored the words of the row below this chunk (incl. their right halo)
+                    const uint32_t need = tslot + cw + 1 < nsl ? tslot + cw + 1 : nsl;
+                    while (sl.prog[j - 1] < need) __nanosleep(ICER_DEC_BACKOFF_NS);
+                    __threadfence_block();
+                }
+                uint32_t *p = base + (size_t) tslot * slot_words;
+                const int ncols = sw - jc * ICER_CHUNK < ICER_CHUNK ? sw - jc * ICER_CHUNK : ICER_CHUNK;
+                icer_core::DecChunk kc;
+                {
+                    const uint32_t *pa = p - row_words, *pc = p + row_words;
+                    const uint32_t bP = oP >= 0 ? p[oP] : 0u, bNp = oNp >= 0 ? p[oNp] : 0u;
+                    const uint32_t b2 = o2 >= 0 ? p[o2] : 0u, b3 = o3 >= 0 ? p[o3] : 0u;
+                    const uint32_t cP = (dn && oP >= 0) ? pc[oP] : 0u, cN = (dn && oNp >= 0) ? pc[oNp] : 0u;
+                    // row above: this plane's own words
+                    const uint32_t aS = up ? pa[oS] : 0u, aN = up ? pa[oN] : 0u;
+                    kc.set(aS, aN, bP, bNp, b2, b3, cP, cN, carryB, carryN, ncols);
+                }
+                ln.begin_chunk();
+                for (;;) {
+                    const bool busy = !ln.chunk_done(ncols);
+                    if (!__any_sync(0xffffffffu, busy)) break;
+                    if (busy) ln.step(kc, sb);
+                }
+                // this chunk's words; the right halo of the chunk before is patched now that this chunk's first column is known
+                p[oB] = kc.bB;
+                if (jc > 0) {
+                    uint32_t *pp = p - slot_words;
+                    pp[oS] = pendS | (((kc.bB >> 1) & 1u) << 31);
+                    pp[oN] = pendN | (((kc.bNn >> 1) & 1u) << 31);
+                }
+                pendS = kc.bP | kc.bB; pendN = kc.bNp | kc.bNn;
+                carryB = kc.bB >> ICER_CHUNK; carryN = kc.bNn >> ICER_CHUNK;
+                if (jc == cw - 1) {
+                    p[oS] = pendS;
+                    p[oN] = pendN;
+                    stored = tslot + 1;
+                } else stored = tslot;
                 __threadfence_block();
-                if (sl.anyerr) {     // an error above voids this plane for that frame
-                    if (run && (sl.deadf[j - 1][lane] | sl.errf[j - 1][lane])) { run = false; dead = true; sl.deadf[j][lane] = 1; }
-                }
-                if (up < px) limit = (a.debug_flags & 2u) ? 0u : (up > lag ? up - lag : 0u);
+                __syncwarp();
+                if (lane == 0) sl.prog[j] = stored;
             }
-            if (pos >= limit) { __nanosleep(ICER_DEC_BACKOFF_NS); continue; }   // the plane above is not far enough ahead yet
-            uint32_t stop = pos + ICER_DEC_RECHECK < limit ? pos + ICER_DEC_RECHECK : limit;      // re-check progress every ICER_DEC_RECHECK pixels
-            for (; pos < stop; pos++) {
-                uint16_t *p = seg + (size_t) row * RS + (size_t) col * 32;
-                const bool up_ = row > 0, dn = row + 1 < sh, rt = col + 1 < sw;
-                if (col == 0) {
-                    a0 = b0 = c0 = 0; a1 = up_ ? p[-RS] : 0; b1 = p[0]; c1 = dn ? p[RS] : 0;
-                    a2n = (up_ && rt) ? p[32 - RS] : 0; b2n = rt ? p[32] : 0; c2n = (dn && rt) ? p[32 + RS] : 0;
-                }
-                a2 = a2n; b2 = b2n; c2 = c2n;
-                {   // fetch the column after next one pixel early (overlaps the coding of this pixel)
-                    const bool rt2 = col + 2 < sw;
-                    a2n = (up_ && rt2) ? p[64 - RS] : 0;
-                    b2n = rt2 ? p[64] : 0;
-                    c2n = (dn && rt2) ? p[64 + RS] : 0;
-                }
-                if (run) {
-                    uint32_t v = b1;
-                    const bool quiet = ((((a0 | a1 | a2 | b0 | b1 | b2 | c0 | c1 | c2) & 0x7FFF) >> lsb) == 0);
-                    uint32_t todo;
-                    if (quiet && fz_left) { fz_run++; fz_left--; todo = 0; }
-                    else todo = (fz_run ? 1u : 0u) | 2u;
-                    int cat = 0;
-                    if (todo & 2u) {
-                        const int msb = 31 - __clz((v & 0x7FFF) | 1);
-                        cat = msb - lsb;
-                        cat = cat < 0 ? 0 : (cat > 3 ? 3 : cat);
-                    }
-                    bool changed = false;
-                    while (todo) {
-                        const int st = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        if (st == 0) {
-                            const int bin = fz_bin;
-                            const uint32_t zt = cnt[t];
-                            uint32_t z = CNT_Z(zt) + fz_run, tot = CNT_TOT(zt) + fz_run;
-                            if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
-                            cnt[t] = CNT_PACK(bin, z, tot);
-                            depthA[bin * BT + t] -= (int) fz_run;
-                            fz_run = 0; fz_left = 0;
-                            continue;
-                        }
-                        int bin, ctx = -1, si = 0;
-                        bool inv = false;
-                        uint32_t z = 0, tot = 0;
-                        if (st == 1 && cat == 3) {
-                            bin = 0;
-                        } else {
-                            if (st == 1) ctx = mag_context(S.T, cat, lsb, sb, a0, a1, a2, b0, b2, c0, c1, c2);
-                            else { si = sign_index(lsb, sb, a1, b0, b2, c1); ctx = S.T.ctx_sign[si]; }
-                            const uint32_t zt = cnt[ctx * BT + t];
-                            z = CNT_Z(zt); tot = CNT_TOT(zt);
-                            uint32_t zz = z;
-                            inv = zz < (tot >> 1);
-                            if (inv) zz = tot - zz;
-                            bin = bin_cached(S.T, zz, tot, CNT_BIN(zt));
-                        }
-                        // next decoded bit of `bin` (icer_decoding.c:127, :186-192)
-                        int depth = depthA[bin * BT + t];
-                        const uint32_t slw = stlow[bin * BT + t];
-                        uint32_t low = slw >> 24;
-                        bool refilled = false;
-                        if (depth <= 0 || dc.words - (slw & 0xFFFFFFu) >= ICER_RING) {
-                            const int rc = dc.refill(bin, depth, low);
-                            if (rc != ICER_RESULT_OK) { run = false; sl.errf[j][lane] = 1; sl.anyerr = 1; todo = 0; break; }
-                            refilled = true;
-                        }
-                        const uint32_t stamp = refilled ? (dc.words & 0xFFFFFFu) : (slw & 0xFFFFFFu);
-                        if (st == 1 && quiet && !inv && bin > 7 && fast_ok) {
-                            // quiet fast path: the run of pending zeros of this Golomb bin is taken without touching the stack
-                            const uint32_t zeros = (uint32_t) depth - (low & 1u);
-                            if (zeros > 0) {
-                                const uint32_t n2 = zeros_in_same_bin(S.T, bin, z, tot);
-                                const uint32_t n3 = 500u - tot;
-                                depthA[bin * BT + t] = (int16_t) depth;
-                                stlow[bin * BT + t] = stamp | (low << 24);
-                                fz_left = min(zeros, min(n2, n3)) - 1;
-                                fz_run = 1;
-                                fz_bin = bin;
-                                continue;
-                            }
-                        }
-                        const int top = depth - 1;
-                        uint32_t b = 0;
-                        if (top >= 0 && top < 8) { b = (low >> top) & 1u; low &= ~(1u << top); }
-                        depthA[bin * BT + t] = (int16_t) (depth - 1);
-                        stlow[bin * BT + t] = stamp | (low << 24);
-                        const uint32_t bit = inv ? (b ^ 1u) : b;
-                        if (ctx >= 0) {
-                            tot++;
-                            z += bit ^ 1u;
-                            if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }
-                            cnt[ctx * BT + t] = CNT_PACK(bin, z, tot);
-                        }
-                        if (st == 1) {
-                            if (bit) { v |= 1u << lsb; changed = true; if (cat == 0) todo |= 4u; }
-                        } else {
-                            if ((bit ^ S.T.sign_pred[si]) & 1u) { v |= 0x8000u; changed = true; }
-                        }
-                    }
-                    if (changed) { *p = (uint16_t) v; b1 = v; }      // also stores the magnitude bit when the sign read failed
-                    done_px = pos + 1;
-                }
-                a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
-                if (++col == sw) { col = 0; row++; }
-            }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) sl.prog[j] = pos;
         }
         // ---- task finished -------------------------------------------------------------------------------
-        sl.posd[j][lane] = done_px;
+        if (frame >= 0) a.pstat[((size_t) frame * a.nunits + ui) * P + lsb] = (uint8_t) (ln.err != icer_core::ST_OK ? PST_ERROR : (alive ? PST_OK : PST_ABSENT));
         __threadfence_block();
         __syncwarp();
         uint32_t old = 0;
@@ -1014,36 +460,9 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
             sl.prog[j] = 0xFFFFFFFFu;                 // never hold the planes below
             __threadfence_block();
             old = atomicAdd((uint32_t *) &sl.done, 1u);
+            if (old == (uint32_t) P - 1) { __threadfence_block(); sl.freed = 1; }
         }
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old == (uint32_t) P - 1) {
-            // last plane of the chain to finish.  A decode error voids every plane below it (lib_icer stops the chain
-            // there and never decodes them, icer_partition.c:441); those planes ran ahead in the pipeline: take their
-            // bits back, then clear the sign of coefficients whose magnitude is now zero.  Lane = frame.
-            __threadfence_block();
-            if (sl.anyerr) {
-                bool voided = false, any_void = false;
-                for (int q = 0; q < P; q++) {
-                    if (q > 0 && (voided || sl.errf[q - 1][lane])) voided = true;     // everything below an error
-                    if (!voided) continue;
-                    const uint32_t npx = sl.posd[q][lane];
-                    if (npx) any_void = true;
-                    const uint32_t bitm = ~(1u << (P - 1 - q));
-                    for (uint32_t n = 0; n < npx; n++) {
-                        uint16_t *qq = seg + (size_t) (n / (uint32_t) sw) * RS + (size_t) (n % (uint32_t) sw) * 32;
-                        *qq = (uint16_t) (*qq & bitm);
-                    }
-                }
-                if (any_void)
-                    for (uint32_t n = 0; n < px; n++) {
-                        uint16_t *qq = seg + (size_t) (n / (uint32_t) sw) * RS + (size_t) (n % (uint32_t) sw) * 32;
-                        if ((*qq & 0x7FFF) == 0 && *qq != 0) *qq = 0;
-                    }
-            }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) sl.freed = 1;
-        }
+        __syncwarp();
     }
 }
 
@@ -1207,9 +626,8 @@ __global__ void __launch_bounds__(256) k_gather(AssembleArgs a) {
 
 }  // namespace
 
-bool frames_to_T_fuses_signmag(const uint16_t *frames, const uint16_t *T, uint32_t w, uint32_t h) {
-    return (((size_t) w * h) % 8) == 0 && ((uintptr_t) frames % 16) == 0 && ((uintptr_t) T % 16) == 0;
-}
+size_t enc_slice_words(uint32_t planes, uint32_t nslots) { return (size_t) enc_geom((int) planes).F * 32 * nslots; }
+size_t dec_slice_words(uint32_t planes, uint32_t nslots) { return (size_t) dec_fields((int) planes) * 32 * nslots; }
 
 uint32_t encode_resident_threads(int device) {
     int sms = 148;
@@ -1221,56 +639,36 @@ uint32_t encode_resident_threads(int device) {
     return (uint32_t) (sms * bps * NT);
 }
 
-int launch_frames_to_T(const uint16_t *frames, uint16_t *T, uint32_t nframes, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h,
-                       cudaStream_t st, LaunchStats &ls, bool signmag) {
-    const size_t plane_px = (size_t) w * h;
-    if ((plane_px % 8) == 0 && ((uintptr_t) frames % 16) == 0 && ((uintptr_t) T % 16) == 0) {
-        for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
-            const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
-            dim3 grid((unsigned) ((plane_px + TT_PX - 1) / TT_PX), chan, cnt);
-            const uint32_t f0 = g0 * 32;
-            const uint16_t *src = frames + (size_t) f0 * chan * plane_px;
-            uint16_t *dstT = T + (size_t) g0 * chan * plane_px * 32;
-            if (signmag) k_frames_to_T_v<true><<<grid, 256, 0, st>>>(src, dstT, nframes - f0, chan, (uint32_t) plane_px);
-            else k_frames_to_T_v<false><<<grid, 256, 0, st>>>(src, dstT, nframes - f0, chan, (uint32_t) plane_px);
-            ls.launches++;
-        }
-        CUDA_TRY(cudaGetLastError());
-        return ICER_RESULT_OK;
-    }
-    if (signmag) return ICER_INVALID_INPUT;      // the scalar kernel expects sign-magnitude input (callers check frames_to_T_fuses_signmag)
+static unsigned slice_grid_x(uint32_t nslots, uint32_t ngroups) {
+    // 1024-thread blocks, two per SM: a few waves over all groups
+    unsigned gx = (unsigned) ((8u * 296u + ngroups - 1) / ngroups);
+    if (gx > nslots) gx = nslots;
+    return gx < 1 ? 1 : gx;
+}
+
+int launch_bitslice(const uint16_t *coefs, uint32_t *bs, const SlotDesc *slots, const Unit *units, uint32_t nslots, uint32_t nframes,
+                    uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h, uint32_t planes, bool twos_complement, cudaStream_t st, LaunchStats &ls) {
+    if (!nslots || !ngroups) return ICER_RESULT_OK;
     for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
         const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
-        dim3 grid((unsigned) ((plane_px + 31) / 32), chan, cnt);
-        const uint32_t f0 = g0 * 32;
-        k_frames_to_T<<<grid, 256, 0, st>>>(frames + (size_t) f0 * chan * plane_px, T + (size_t) g0 * chan * plane_px * 32,
-                                            nframes - f0, chan, (uint32_t) plane_px);
+        dim3 grid(slice_grid_x(nslots, cnt), cnt);
+        k_bitslice<<<grid, 1024, 0, st>>>(coefs + (size_t) g0 * 32 * chan * w * h, bs + (size_t) g0 * enc_slice_words(planes, nslots), slots, units, nslots,
+                                          nframes - g0 * 32, chan, w, h, (int) planes, twos_complement ? 1 : 0);
         ls.launches++;
     }
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;
 }
 
-int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame_of, const uint16_t *mean, uint32_t ngroups,
-                       uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, uint32_t llw, uint32_t llh, cudaStream_t st,
-                       LaunchStats &ls, bool bits8) {
-    const size_t plane_px = (size_t) w * h;
-    if (!bits8 && (plane_px % 8) == 0 && (cap_px % 8) == 0 && (w % 8) == 0 && ((uintptr_t) frames % 16) == 0 && ((uintptr_t) T % 16) == 0) {
-        for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
-            const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
-            dim3 grid((unsigned) ((plane_px + TT_PX - 1) / TT_PX), chan, cnt);
-            k_T_to_frames_v<<<grid, 256, 0, st>>>(T + (size_t) g0 * chan * plane_px * 32, frames, frame_of + (size_t) g0 * 32, mean, chan,
-                                                  (uint32_t) plane_px, cap_px, (int) w, (int) llw, (int) llh);
-            ls.launches++;
-        }
-        CUDA_TRY(cudaGetLastError());
-        return ICER_RESULT_OK;
-    }
+int launch_unslice(const uint32_t *bs, uint16_t *frames, const SlotDesc *slots, const Unit *units, const uint8_t *pstat, const int32_t *frame_of,
+                   const uint16_t *mean, uint32_t nslots, uint32_t nunits, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px,
+                   uint32_t planes, uint32_t llw, uint32_t llh, cudaStream_t st, LaunchStats &ls, bool bits8) {
+    if (!nslots || !ngroups) return ICER_RESULT_OK;
     for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
         const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
-        dim3 grid((unsigned) ((plane_px + 31) / 32), chan, cnt);
-        k_T_to_frames<<<grid, 256, 0, st>>>(T + (size_t) g0 * chan * plane_px * 32, frames, frame_of + (size_t) g0 * 32, mean, chan,
-                                            (uint32_t) plane_px, cap_px, (int) w, (int) llw, (int) llh, bits8 ? 1 : 0);
+        dim3 grid(slice_grid_x(nslots, cnt), cnt);
+        k_unslice<<<grid, 1024, 0, st>>>(bs + (size_t) g0 * dec_slice_words(planes, nslots), frames, slots, units, pstat, frame_of + (size_t) g0 * 32, mean,
+                                         nslots, nunits, chan, w, h, cap_px, (int) planes, (int) llw, (int) llh, bits8 ? 1 : 0);
         ls.launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1280,6 +678,7 @@ int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame
 int launch_encode(const EncodeArgs &a, cudaStream_t st, LaunchStats &ls) {
     int rc = upload_tables();
     if (rc) return rc;
+    if (a.planes < 1 || a.planes > 15) return ICER_BITPLANE_OUT_OF_RANGE;
     CUDA_TRY(cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EncSmem)));
     const unsigned long long total = (unsigned long long) a.ngroups * (a.list ? a.nlist : a.nunits * a.planes);   // warps of work
     unsigned blocks = a.nring_threads / NT;

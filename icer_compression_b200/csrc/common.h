@@ -36,13 +36,20 @@ struct Unit {
     int32_t x, y, w, h;        // rectangle inside the channel plane
     uint8_t chan, level, subband, seg;
     uint32_t px;
+    uint32_t slot0, cw;        // bit-slice slots: first slot of the unit, chunks (slots) per row; the unit owns h * cw slots, row-major
 };
+// One bit-slice slot = one chunk of ICER_CHUNK pixels of one row of one unit (coder.cu).  flags bit 0 / 1: the pixel left / right of
+// the chunk belongs to the same unit (else that halo bit is zero).
+struct SlotDesc { uint16_t x0, y, unit; uint8_t ncols, flags; };
 
 struct Plan {
     uint32_t w, h, chan, stages, segments, planes, max_stages;
     int status;                          // ICER_RESULT_OK or the error every frame of this shape gets
     int enc_status;                      // errors only the encoder reports (ICER_PACKET_COUNT_EXCEEDED)
     std::vector<Unit> units;
+    std::vector<SlotDesc> slots;         // bit-slice slots of all units (unit after unit, row-major inside a unit)
+    uint32_t nslots = 0;
+    SlotDesc *d_slots = nullptr;
     uint32_t nstreams;                   // units.size() * planes
     std::vector<uint32_t> prio_order;    // stream ids in (priority packet, segment) order
     std::vector<uint32_t> rearr_order;   // stream ids in the rearranged output order
@@ -91,8 +98,9 @@ int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_
                            uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8 = false, bool skip_signmag = false);
 
 struct EncodeArgs {
-    const uint16_t *coefsT;    // [ngroups][chan][h][w][32] sign-magnitude, frame-interleaved (32 frames per group)
-    uint32_t nframes, ngroups, w, h, chan, planes;
+    const uint32_t *bs;        // encoder bit slices [ngroups][nslots][F][32] (coder.cu), 32 frames per group
+    uint32_t nslots;
+    uint32_t nframes, ngroups, planes;
     const Unit *units; uint32_t nunits;
     const uint32_t *soff, *scap;   // per stream
     uint64_t scratch_words;        // per frame
@@ -134,28 +142,28 @@ struct AssembleArgs {
 int launch_assemble(const AssembleArgs &a, cudaStream_t st, LaunchStats &ls);
 
 struct DecodeArgs {
-    uint16_t *coefsT;              // [ngroups][chan][h][w][32] zero-initialised, receives sign-magnitude (frame-interleaved)
-    uint32_t ngroups, chan, planes;
+    uint32_t *bs;                  // decoder bit slices [ngroups][nslots][3 * planes][32]: written and read by the planes of a chain
+    uint32_t nslots;
+    uint8_t *pstat;                // [batch frames][nunits][planes] status of every plane (coder.cu PST_*), read by the un-slicing kernel
+    uint32_t ngroups, planes;
     const Unit *units; uint32_t nunits;
-    uint32_t plan_w, plan_h;
     const int32_t *frame_of;       // [ngroups*32] batch index of each lane's frame, -1 = padding
     const uint8_t *streams; uint64_t stream_stride;
     const uint64_t *stream_len;    // [batch frames] bytes of each frame's stream; the bit readers of a frame see zeros behind it
     const uint32_t *seg_off;       // [batch frames][nstreams] 1 + byte offset of the segment header inside the frame's stream, 0 = absent
     unsigned long long *work_counter;
-    uint32_t debug_flags;          // bit0: no quiet fast path, bit1: planes strictly one after the other
 };
 int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls);
-// planar frames [n][chan][h][w]  <->  frame-interleaved T layout [ngroups][chan][h][w][32]
-// signmag: the planes hold two's-complement coefficients and the kernel applies the sign-magnitude mapping on the way (only
-// when frames_to_T_fuses_signmag() says the vector kernel applies)
-int launch_frames_to_T(const uint16_t *frames, uint16_t *T, uint32_t nframes, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h,
-                       cudaStream_t st, LaunchStats &ls, bool signmag = false);
-bool frames_to_T_fuses_signmag(const uint16_t *frames, const uint16_t *T, uint32_t w, uint32_t h);
-// also undoes sign-magnitude and adds the header LL mean; frame_of maps (group, lane) to the batch index (-1 = none)
-int launch_T_to_frames(const uint16_t *T, uint16_t *frames, const int32_t *frame_of, const uint16_t *mean, uint32_t ngroups,
-                       uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, uint32_t llw, uint32_t llh, cudaStream_t st,
-                       LaunchStats &ls, bool bits8 = false);
+// planar coefficients [n][chan][h][w] -> encoder bit slices (twos_complement: apply the sign-magnitude mapping on the way), and the
+// decoder's bit slices -> planar coefficients (undoes sign-magnitude, adds the header LL mean; frame_of maps (group, lane) to the
+// batch index, -1 = none)
+size_t enc_slice_words(uint32_t planes, uint32_t nslots);      // 32-bit words per group
+size_t dec_slice_words(uint32_t planes, uint32_t nslots);
+int launch_bitslice(const uint16_t *coefs, uint32_t *bs, const SlotDesc *slots, const Unit *units, uint32_t nslots, uint32_t nframes,
+                    uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h, uint32_t planes, bool twos_complement, cudaStream_t st, LaunchStats &ls);
+int launch_unslice(const uint32_t *bs, uint16_t *frames, const SlotDesc *slots, const Unit *units, const uint8_t *pstat, const int32_t *frame_of,
+                   const uint16_t *mean, uint32_t nslots, uint32_t nunits, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px,
+                   uint32_t planes, uint32_t llw, uint32_t llh, cudaStream_t st, LaunchStats &ls, bool bits8 = false);
 
 // ---- K6: device stream scanner (parse.cu) ------------------------------------------------------------
 struct ParseInfo {               // per frame, what lib_icer's scan loop leaves behind (icer_compress.c:443-459)

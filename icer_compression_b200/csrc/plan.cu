@@ -96,7 +96,7 @@ int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages,
     pl.w = w; pl.h = h; pl.chan = chan; pl.stages = stages; pl.segments = segments; pl.planes = planes;
     pl.max_stages = max_stages; pl.scratch_bits = scratch_bits;
     pl.status = ICER_RESULT_OK; pl.enc_status = ICER_RESULT_OK;
-    pl.units.clear(); pl.prio_order.clear(); pl.rearr_order.clear(); pl.unit_of.clear();
+    pl.units.clear(); pl.slots.clear(); pl.nslots = 0; pl.prio_order.clear(); pl.rearr_order.clear(); pl.unit_of.clear();
     pl.nstreams = 0; pl.scratch_words = 0;
     if (stages < 1 || stages > max_stages) { pl.status = ICER_TOO_MANY_STAGES; return pl.status; }
     if (dim_low(w, stages) < 3 || dim_low(h, stages) < 3) { pl.status = ICER_TOO_MANY_STAGES; return pl.status; }
@@ -122,6 +122,23 @@ int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages,
                 }
             }
     pl.nstreams = (uint32_t) pl.units.size() * planes;
+    // bit-slice slots (coder.cu): per unit row, chunks of ICER_CHUNK columns
+    pl.slots.clear();
+    for (size_t k = 0; k < pl.units.size(); k++) {
+        Unit &q = pl.units[k];
+        q.cw = (uint32_t) ((q.w + ICER_CHUNK - 1) / ICER_CHUNK);
+        q.slot0 = (uint32_t) pl.slots.size();
+        for (int r = 0; r < q.h; r++)
+            for (uint32_t j = 0; j < q.cw; j++) {
+                SlotDesc d;
+                d.x0 = (uint16_t) (q.x + (int) j * ICER_CHUNK); d.y = (uint16_t) (q.y + r); d.unit = (uint16_t) k;
+                const int left = q.w - (int) j * ICER_CHUNK;
+                d.ncols = (uint8_t) (left < ICER_CHUNK ? left : ICER_CHUNK);
+                d.flags = (uint8_t) ((j > 0 ? 1 : 0) | (j + 1 < q.cw ? 2 : 0));
+                pl.slots.push_back(d);
+            }
+    }
+    pl.nslots = (uint32_t) pl.slots.size();
     pl.unit_lut.assign((size_t) chan * (max_stages + 1) * 4 * (ICER_MAX_SEGMENTS + 1), 0xFFFFFFFFu);
     for (size_t k = 0; k < pl.units.size(); k++) {
         const Unit &q = pl.units[k];
@@ -252,6 +269,7 @@ void u8_interleave_dst(uint32_t len, std::vector<uint32_t> &dst) {
 }
 
 void free_plan_device(Plan &pl) {
+    cudaFree(pl.d_slots); pl.d_slots = nullptr;
     cudaFree(pl.d_units); cudaFree(pl.d_prio); cudaFree(pl.d_rearr); cudaFree(pl.d_soff); cudaFree(pl.d_scap); cudaFree(pl.d_unit_lut);
     pl.d_unit_lut = nullptr;
     cudaFree(pl.d_list); pl.d_list = nullptr; pl.list_prefix = 0;
@@ -271,6 +289,8 @@ int upload_plan(Plan &pl) {
     CUDA_TRY(cudaMemcpy(pl.d_rearr, pl.rearr_order.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(pl.d_soff, pl.scratch_off.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(pl.d_scap, pl.scratch_cap.data(), pl.nstreams * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&pl.d_slots, pl.slots.size() * sizeof(SlotDesc)));
+    CUDA_TRY(cudaMemcpy(pl.d_slots, pl.slots.data(), pl.slots.size() * sizeof(SlotDesc), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&pl.d_unit_lut, pl.unit_lut.size() * 4));
     CUDA_TRY(cudaMemcpy(pl.d_unit_lut, pl.unit_lut.data(), pl.unit_lut.size() * 4, cudaMemcpyHostToDevice));
     return ICER_RESULT_OK;
