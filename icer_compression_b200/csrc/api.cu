@@ -42,7 +42,7 @@ struct icer_b200_ctx {
     std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int, int>, Plan *> plans;
     LaunchStats ls;
     DevBuf coefs, tmp, scratch, bits, crc, rings, out, out_prio, size_used, rc, keep, offp, offr, mean, ovf, misc,
-        streams, segoff, dims, frame_ok, cand, ncand, pinfo, list, pix, fin, tmp2, slices, pstat;
+        streams, segoff, dims, frame_ok, cand, ncand, pinfo, list, pix, fin, tmp2, slices, pstat, vplanes;
     uint32_t ring_threads = 0;
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -147,7 +147,7 @@ void icer_b200_destroy(icer_b200_ctx *c) {
     for (auto &kv : c->perms8) cudaFree((void *) kv.second);
     DevBuf *all[] = {&c->coefs, &c->tmp, &c->scratch, &c->bits, &c->crc, &c->rings, &c->out, &c->out_prio, &c->size_used, &c->rc,
                      &c->keep, &c->offp, &c->offr, &c->mean, &c->ovf, &c->misc, &c->streams, &c->segoff, &c->dims, &c->frame_ok,
-                     &c->cand, &c->ncand, &c->pinfo, &c->list, &c->pix, &c->fin, &c->tmp2, &c->slices, &c->pstat};
+                     &c->cand, &c->ncand, &c->pinfo, &c->list, &c->pix, &c->fin, &c->tmp2, &c->slices, &c->pstat, &c->vplanes};
     for (auto b : all) b->release();
     for (int k = 0; k < 2; k++) {
         c->p_in[k].release(); c->p_out[k].release(); c->p_used[k].release(); c->p_rc[k].release(); c->p_dims[k].release();
@@ -460,7 +460,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
         }
         // bit slices of the coefficients for the coder (lane = frame of a group of 32)
         uint32_t *d_bs = c->slices.as<uint32_t>();
-        if ((e = launch_bitslice(d_coefs, d_bs, pl->d_slots, pl->d_units, pl->nslots, (uint32_t) nb, ngroups, chan, w, h, pl->planes, fuse_sm, st, c->ls))) return e;
+        if ((e = launch_bitslice(d_coefs, d_bs, pl->d_slots, pl->nslots, (uint32_t) nb, ngroups, chan, w, h, pl->planes, fuse_sm, st, c->ls))) return e;
         ev_record(c, 2, st);
         // entropy coder + segment assembly.
         //  * a stream that outgrows its payload slot (rare) restarts the coder with a larger scratch budget;
@@ -784,6 +784,7 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         if ((e = c->tmp.ensure(n * chan * plane_px * 2))) return e;
         if ((e = c->slices.ensure((size_t) ngroups * dec_slice_words(pl->planes, pl->nslots) * 4))) return e;
         if ((e = c->pstat.ensure(n * pl->units.size() * pl->planes + 16))) return e;
+        if ((e = c->vplanes.ensure(n * pl->units.size() + 16))) return e;
         if ((e = c->segoff.ensure(n * (size_t) pl->nstreams * 4))) return e;
         if ((e = c->frame_ok.ensure(frame_of.size() * 4))) return e;
         if ((e = c->list.ensure(list.size() * 4 + 4))) return e;
@@ -837,7 +838,7 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         }
         uint16_t *d_planar = fused ? c->tmp2.as<uint16_t>() : d_frames;
         // every pixel of the frames of this group is written (icer_compress.c:470: the image starts at zero)
-        if ((e = launch_unslice(c->slices.as<uint32_t>(), d_planar, pl->d_slots, pl->d_units, c->pstat.as<uint8_t>(), c->frame_ok.as<int32_t>(),
+        if ((e = launch_unslice(c->slices.as<uint32_t>(), d_planar, pl->d_slots, c->pstat.as<uint8_t>(), c->vplanes.as<uint8_t>(), n, c->frame_ok.as<int32_t>(),
                                 c->mean.as<uint16_t>(), pl->nslots, (uint32_t) pl->units.size(), ngroups, chan, w, h, cap_px, pl->planes, llw, llh,
                                 st, c->ls, native8))) return e;
         if (native8 && (e = ensure_perms8(c, w, h, p->stages))) return e;

@@ -30,6 +30,9 @@ constexpr int NT = 128;   // threads per encoder block
 #ifndef ICER_ENC_MINI
 #define ICER_ENC_MINI 8
 #endif
+#ifndef ICER_ENC_PUMPS
+#define ICER_ENC_PUMPS 1
+#endif
 #ifndef ICER_ENC_MINBLOCKS
 #define ICER_ENC_MINBLOCKS 8
 #endif
@@ -96,87 +99,101 @@ __device__ __forceinline__ uint32_t to_signmag16(uint32_t v) {          // icer_
     return s < 0 ? (uint32_t) ((-s) & (B8 ? 0x7F : 0x7FFF)) | 0x8000u : (uint32_t) s;
 }
 
-// K3: planar coefficients -> encoder slices.  Block = 32 warps = the 32 frames of a group; a warp reads the 32 window columns of its
-// frame (one 64-byte access) and turns every field into a word with one ballot; the block then writes the slot's F x 32 words as
-// F contiguous 128-byte lines.
+// K3: planar coefficients -> encoder slices.  Warp = (frame, slot): the lanes read the 32 window columns of their frame (one 64-byte
+// access), every field becomes a word with one ballot, and lane 0 stores it; the 32 frames of a group (the 32 warps of a block) fill
+// each 128-byte line of the slice buffer together (merged in L2).
+template <int P>
 __global__ void __launch_bounds__(1024) k_bitslice(const uint16_t *__restrict__ coefs, uint32_t *__restrict__ bs, const SlotDesc *__restrict__ slots,
-                                                   const Unit *__restrict__ units, uint32_t nslots, uint32_t nframes, uint32_t chan, uint32_t W, uint32_t H,
-                                                   int P, int twos) {
-    __shared__ uint32_t tile[32][33];
+                                                   uint32_t nslots, uint32_t nframes, uint32_t chan, uint32_t W, uint32_t H, int twos) {
     const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;
     const uint32_t g = blockIdx.y;
     const uint32_t frame = g * 32 + f;
-    const SliceGeom G = enc_geom(P);
+    constexpr int PS = P + 2 < 14 ? P + 2 : 14, F = P + PS + 1;
+    const bool writer = lane == 0;
+    const size_t plane_px = (size_t) W * H;
+    const uint16_t *src = coefs + (size_t) frame * chan * plane_px - 1 + lane;
+    uint32_t *dstg = bs + (size_t) g * nslots * F * 32 + f;
     for (uint32_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
         const SlotDesc d = slots[slot];
-        const uint32_t ch = units[d.unit].chan;
+        const uint32_t ch = (d.flags >> 2) & 3u;
         const bool inwin = (lane >= 1 && lane <= (int) d.ncols) || (lane == 0 && (d.flags & 1)) || (lane == (int) d.ncols + 1 && (d.flags & 2));
         uint32_t v = 0;
-        if (inwin && frame < nframes) v = coefs[(((size_t) frame * chan + ch) * H + d.y) * W + d.x0 - 1 + lane];
+        if (inwin && frame < nframes) v = src[ch * plane_px + (size_t) d.y * W + d.x0];
         if (twos) v = to_signmag16<false>(v);
         const uint32_t mag = v & 0x7FFFu;
-        uint32_t mine = 0;
+        uint32_t *dst = dstg + (size_t) slot * F * 32;
+#pragma unroll
         for (int p = 0; p < P; p++) {
-            const uint32_t w = __ballot_sync(0xffffffffu, (mag >> p) & 1u);
-            if (lane == p) mine = w;
+            const uint32_t w = __ballot_sync(0xffffffffu, (mag & (1u << p)) != 0u);
+            if (writer) dst[p * 32] = w;
         }
-        for (int p = 1; p <= G.PS; p++) {
-            const uint32_t w = __ballot_sync(0xffffffffu, (mag >> p) != 0u);
-            if (lane == P + p - 1) mine = w;
+#pragma unroll
+        for (int p = 1; p <= PS; p++) {
+            const uint32_t w = __ballot_sync(0xffffffffu, mag >= (1u << p));
+            if (writer) dst[(P + p - 1) * 32] = w;
         }
         {
-            const uint32_t w = __ballot_sync(0xffffffffu, (v >> 15) & 1u);
-            if (lane == P + G.PS) mine = w;
+            const uint32_t w = __ballot_sync(0xffffffffu, (v & 0x8000u) != 0u);
+            if (writer) dst[(P + PS) * 32] = w;
         }
-        tile[lane][f] = mine;
-        __syncthreads();
-        uint32_t *dst = bs + ((size_t) g * nslots + slot) * G.F * 32;
-        if ((int) threadIdx.x < G.F * 32) dst[threadIdx.x] = tile[threadIdx.x >> 5][threadIdx.x & 31];
-        __syncthreads();
     }
 }
 
-// K8: decoder slices -> planar coefficients.  Warp = frame, lane = window column.  Which planes of a (frame, unit) count is decided
-// by their status bytes: a plane is decoded only if it and every plane above it are present (icer_partition.c:431), and lib_icer
-// stops a chain at the first plane that fails (:441) -- that plane keeps the bits it decoded before the error, the planes below
-// were decoded ahead of time by the pipeline and are ignored here.  Also undoes sign-magnitude (icer_wavelet.c:880-886) and adds the
-// header LL mean (icer_compress.c:520-531).
+// K8a: which planes of a (frame, unit) count.  A plane is decoded only if it and every plane above it are present
+// (icer_partition.c:431), and lib_icer stops a chain at the first plane that fails (:441) -- that plane keeps the bits it decoded
+// before the error; the planes below were decoded ahead of time by the pipeline and are ignored.  vp = lowest plane that counts.
 enum { PST_OK = 0, PST_ERROR = 1, PST_ABSENT = 2 };
+__global__ void __launch_bounds__(256) k_valid_planes(const uint8_t *__restrict__ pstat, uint8_t *__restrict__ vp, size_t count, int P) {
+    const size_t i = (size_t) blockIdx.x * 256 + threadIdx.x;
+    if (i >= count) return;
+    int v = 0;
+    for (int p = P - 1; p >= 0; p--) {
+        const uint32_t st = pstat[i * P + p];
+        if (st == PST_ABSENT) { v = p + 1; break; }
+        if (st == PST_ERROR) { v = p; break; }
+    }
+    vp[i] = (uint8_t) v;
+}
+
+// K8: decoder slices -> planar coefficients.  Warp = (frame, slot), lane = window column.  Also undoes sign-magnitude
+// (icer_wavelet.c:880-886) and adds the header LL mean (icer_compress.c:520-531).
+template <int P>
 __global__ void __launch_bounds__(1024) k_unslice(const uint32_t *__restrict__ bs, uint16_t *__restrict__ dst, const SlotDesc *__restrict__ slots,
-                                                  const Unit *__restrict__ units, const uint8_t *__restrict__ pstat, const int32_t *__restrict__ frame_of,
+                                                  const uint8_t *__restrict__ vpmap, const int32_t *__restrict__ frame_of,
                                                   const uint16_t *__restrict__ mean, uint32_t nslots, uint32_t nunits, uint32_t chan, uint32_t W, uint32_t H,
-                                                  uint64_t cap_px, int P, int llw, int llh, int bits8) {
+                                                  uint64_t cap_px, int llw, int llh, int bits8) {
     const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;
     const uint32_t g = blockIdx.y;
     const int32_t frame = frame_of[g * 32 + f];
     if (frame < 0) return;
-    const int F = dec_fields(P);
+    constexpr int F = 3 * P;
+    const uint8_t *vpf = vpmap + (size_t) frame * nunits;
+    const uint32_t *srcg = bs + (size_t) g * nslots * F * 32 + f;
+    uint16_t *dstf = dst + (size_t) frame * chan * cap_px - 1 + lane;
     for (uint32_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
         const SlotDesc d = slots[slot];
-        const Unit u = units[d.unit];
-        // lowest plane that counts
-        uint32_t st = PST_OK;
-        if (lane < P) st = pstat[((size_t) frame * nunits + d.unit) * P + lane];
-        const uint32_t flagged = __ballot_sync(0xffffffffu, st != PST_OK), absent = __ballot_sync(0xffffffffu, st == PST_ABSENT);
-        int vp = 0;
-        if (flagged) { const int hp = 31 - __clz((int) flagged); vp = ((absent >> hp) & 1u) ? hp + 1 : hp; }
-        const uint32_t *src = bs + ((size_t) g * nslots + slot) * F * 32 + f;
-        uint32_t wB = 0;
-        if (lane < P && lane >= vp) wB = src[lane * 32];
-        const uint32_t wN = vp < P ? src[(2 * P + vp) * 32] : 0u;        // same address in every lane: one broadcast load
+        const int vp = vpf[d.unit];
+        const uint32_t *src = srcg + (size_t) slot * F * 32;
+        // every lane reads the same words (broadcast loads) and keeps its own column's bit
         uint32_t mag = 0;
-        for (int p = 0; p < P; p++) mag |= ((__shfl_sync(0xffffffffu, wB, p) >> lane) & 1u) << p;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const uint32_t w = p >= vp ? src[p * 32] : 0u;
+            mag |= ((w >> lane) & 1u) << p;
+        }
+        const uint32_t wN = vp < P ? src[(2 * P + vp) * 32] : 0u;
         if (lane < 1 || lane > (int) d.ncols) continue;
         uint32_t v = mag ? (mag | (((wN >> lane) & 1u) << 15)) : 0u;
         v = (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;                      // icer_wavelet.c:880-886
+        const uint32_t ch = (d.flags >> 2) & 3u;
         const int x = (int) d.x0 - 1 + lane, y = (int) d.y;
         if (y < llh && x < llw) {
-            const int m = (int) mean[(size_t) frame * chan + u.chan];
+            const int m = (int) mean[(size_t) frame * chan + ch];
             // uint16 API: int16 add (icer_compress.c:524-531); native uint8 API: int8 add of the header value's low byte (:258-265)
             v = bits8 ? (uint32_t) (uint16_t) (int16_t) (int8_t) ((int) (int16_t) v + (int) (int8_t) m)
                       : (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + (int) (int16_t) m);
         }
-        dst[((size_t) frame * chan + u.chan) * cap_px + (size_t) y * W + x] = (uint16_t) v;
+        dstf[ch * cap_px + (size_t) y * W + d.x0] = (uint16_t) v;
     }
 }
 
@@ -243,9 +260,13 @@ __global__ void __launch_bounds__(NT, ICER_ENC_MINBLOCKS) k_encode(EncodeArgs a)
                 ln.begin_chunk();
                 for (;;) {
                     const bool busy = !ln.chunk_done(ncols);
-                    if (!__any_sync(0xffffffffu, busy)) break;
-                    if (busy) ln.step(k, sb);
+                    const unsigned lanes = __ballot_sync(0xffffffffu, busy);
+                    if (!lanes) break;
+                    if (busy) ln.step(k, sb, lanes);
+                    ln.pump();       // a completion can release several parked codewords: more than one emission per step keeps the backlog short
+#if ICER_ENC_PUMPS > 1
                     ln.pump();
+#endif
                 }
             }
         }
@@ -282,11 +303,14 @@ __global__ void __launch_bounds__(NT, ICER_ENC_MINBLOCKS) k_encode(EncodeArgs a)
 #ifndef ICER_DEC_BACKOFF_NS
 #define ICER_DEC_BACKOFF_NS 2000     /* sleep when the plane above is not far enough ahead */
 #endif
+#ifndef ICER_DEC_SLACK
+#define ICER_DEC_SLACK 0            /* extra chunks a blocked plane lets the plane above get ahead before it continues */
+#endif
 #ifndef ICER_DEC_SLOTWAIT_NS
 #define ICER_DEC_SLOTWAIT_NS 20000   /* poll interval while a chain waits for a free slot (chains last milliseconds) */
 #endif
 #ifndef ICER_DEC_CHAINWAIT_NS
-#define ICER_DEC_CHAINWAIT_NS 5000   /* poll interval while a plane waits for its chain's slot to be published */
+#define ICER_DEC_CHAINWAIT_NS 4000   /* poll interval while a plane waits for its chain's slot to be published */
 #endif
 constexpr int DEC_WARPS = ICER_DEC_WARPS;
 constexpr int DEC_BT = DEC_WARPS * 32;
@@ -351,8 +375,10 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
             wid = __shfl_sync(0xffffffffu, wid, 0);
             if (wid >= total) break;
             if (lane == 0) {
-                if (k >= (uint32_t) DEC_SLOTS)
-                    while (!(sl.chain == k - DEC_SLOTS && sl.freed)) __nanosleep(ICER_DEC_SLOTWAIT_NS);     // that chain is live: it will finish
+                if (k >= (uint32_t) DEC_SLOTS) {
+                    uint32_t ns = ICER_DEC_SLOTWAIT_NS;
+                    while (!(sl.chain == k - DEC_SLOTS && sl.freed)) { __nanosleep(ns); if (ns < 8 * ICER_DEC_SLOTWAIT_NS) ns += ns; }     // that chain is live: it will finish
+                }
                 __threadfence_block();
                 for (int q = 0; q < 15; q++) sl.prog[q] = 0;
                 sl.done = 0; sl.freed = 0; sl.wid = wid;
@@ -362,7 +388,10 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
             __syncwarp();
         } else {
             bool gone = false;
-            if (lane == 0) while (sl.chain != k) { if (S.k_end <= k) { gone = true; break; } __nanosleep(ICER_DEC_CHAINWAIT_NS); }
+            if (lane == 0) {
+                uint32_t ns = ICER_DEC_CHAINWAIT_NS;
+                while (sl.chain != k) { if (S.k_end <= k) { gone = true; break; } __nanosleep(ns); if (ns < 16 * ICER_DEC_CHAINWAIT_NS) ns += ns; }
+            }
             gone = __shfl_sync(0xffffffffu, gone ? 1 : 0, 0) != 0;
             if (gone) break;
         }
@@ -403,6 +432,7 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
         const size_t row_words = slot_words * cw;
         uint32_t *base = a.bs + ((size_t) g * a.nslots + u.slot0) * slot_words + lane;
         uint32_t stored = 0;               // slots of this plane whose words are final (warp-uniform)
+        uint32_t avail = 0;                // slots the plane above is known to have stored
         uint32_t tslot = 0;
         for (int row = 0; row < sh; row++) {
             const bool up = row > 0, dn = row + 1 < sh;
@@ -411,8 +441,17 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
                 if (j > 0) {
                     // the plane above must have stored the words of the row below this chunk (incl. their right halo)
                     const uint32_t need = tslot + cw + 1 < nsl ? tslot + cw + 1 : nsl;
-                    while (sl.prog[j - 1] < need) __nanosleep(ICER_DEC_BACKOFF_NS);
-                    __threadfence_block();
+                    if (avail < need) {                      // warp-uniform: `avail` is what lane 0 saw last
+                        // wait until the plane above is a few chunks further than needed: this plane then runs that many chunks without
+                        // looking again (planes of similar density would otherwise block and poll at every chunk)
+                        const uint32_t want = need + ICER_DEC_SLACK < nsl ? need + ICER_DEC_SLACK : nsl;
+                        if (lane == 0) {
+                            uint32_t ns = ICER_DEC_BACKOFF_NS;
+                            while ((avail = sl.prog[j - 1]) < want) { __nanosleep(ns); if (ns < 8 * ICER_DEC_BACKOFF_NS) ns += ns; }
+                        }
+                        avail = __shfl_sync(0xffffffffu, avail, 0);
+                        __threadfence_block();
+                    }
                 }
                 uint32_t *p = base + (size_t) tslot * slot_words;
                 const int ncols = sw - jc * ICER_CHUNK < ICER_CHUNK ? sw - jc * ICER_CHUNK : ICER_CHUNK;
@@ -429,8 +468,9 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
                 ln.begin_chunk();
                 for (;;) {
                     const bool busy = !ln.chunk_done(ncols);
-                    if (!__any_sync(0xffffffffu, busy)) break;
-                    if (busy) ln.step(kc, sb);
+                    const unsigned lanes = __ballot_sync(0xffffffffu, busy);
+                    if (!lanes) break;
+                    if (busy) ln.step(kc, sb, lanes);
                 }
                 // this chunk's words; the right halo of the chunk before is patched now that this chunk's first column is known
                 p[oB] = kc.bB;
@@ -646,29 +686,54 @@ static unsigned slice_grid_x(uint32_t nslots, uint32_t ngroups) {
     return gx < 1 ? 1 : gx;
 }
 
-int launch_bitslice(const uint16_t *coefs, uint32_t *bs, const SlotDesc *slots, const Unit *units, uint32_t nslots, uint32_t nframes,
-                    uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h, uint32_t planes, bool twos_complement, cudaStream_t st, LaunchStats &ls) {
+template <int P> struct SliceLaunch {
+    static void enc(dim3 grid, cudaStream_t st, const uint16_t *coefs, uint32_t *bs, const SlotDesc *slots, uint32_t nslots, uint32_t nframes,
+                    uint32_t chan, uint32_t w, uint32_t h, int twos) {
+        k_bitslice<P><<<grid, 1024, 0, st>>>(coefs, bs, slots, nslots, nframes, chan, w, h, twos);
+    }
+    static void dec(dim3 grid, cudaStream_t st, const uint32_t *bs, uint16_t *frames, const SlotDesc *slots, const uint8_t *vp, const int32_t *frame_of,
+                    const uint16_t *mean, uint32_t nslots, uint32_t nunits, uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, int llw, int llh, int bits8) {
+        k_unslice<P><<<grid, 1024, 0, st>>>(bs, frames, slots, vp, frame_of, mean, nslots, nunits, chan, w, h, cap_px, llw, llh, bits8);
+    }
+};
+#define ICER_FOR_PLANES(P, CALL)                                                                                              \
+    switch (P) {                                                                                                              \
+        case 1: SliceLaunch<1>::CALL; break; case 2: SliceLaunch<2>::CALL; break; case 3: SliceLaunch<3>::CALL; break;        \
+        case 4: SliceLaunch<4>::CALL; break; case 5: SliceLaunch<5>::CALL; break; case 6: SliceLaunch<6>::CALL; break;        \
+        case 7: SliceLaunch<7>::CALL; break; case 8: SliceLaunch<8>::CALL; break; case 9: SliceLaunch<9>::CALL; break;        \
+        case 10: SliceLaunch<10>::CALL; break; case 11: SliceLaunch<11>::CALL; break; case 12: SliceLaunch<12>::CALL; break;  \
+        case 13: SliceLaunch<13>::CALL; break; case 14: SliceLaunch<14>::CALL; break; case 15: SliceLaunch<15>::CALL; break;  \
+        default: return ICER_BITPLANE_OUT_OF_RANGE;                                                                           \
+    }
+
+int launch_bitslice(const uint16_t *coefs, uint32_t *bs, const SlotDesc *slots, uint32_t nslots, uint32_t nframes, uint32_t ngroups, uint32_t chan,
+                    uint32_t w, uint32_t h, uint32_t planes, bool twos_complement, cudaStream_t st, LaunchStats &ls) {
     if (!nslots || !ngroups) return ICER_RESULT_OK;
     for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
         const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
         dim3 grid(slice_grid_x(nslots, cnt), cnt);
-        k_bitslice<<<grid, 1024, 0, st>>>(coefs + (size_t) g0 * 32 * chan * w * h, bs + (size_t) g0 * enc_slice_words(planes, nslots), slots, units, nslots,
-                                          nframes - g0 * 32, chan, w, h, (int) planes, twos_complement ? 1 : 0);
+        const uint16_t *src = coefs + (size_t) g0 * 32 * chan * w * h;
+        uint32_t *dst = bs + (size_t) g0 * enc_slice_words(planes, nslots);
+        ICER_FOR_PLANES((int) planes, enc(grid, st, src, dst, slots, nslots, nframes - g0 * 32, chan, w, h, twos_complement ? 1 : 0))
         ls.launches++;
     }
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;
 }
 
-int launch_unslice(const uint32_t *bs, uint16_t *frames, const SlotDesc *slots, const Unit *units, const uint8_t *pstat, const int32_t *frame_of,
+int launch_unslice(const uint32_t *bs, uint16_t *frames, const SlotDesc *slots, const uint8_t *pstat, uint8_t *vp, size_t nbatch, const int32_t *frame_of,
                    const uint16_t *mean, uint32_t nslots, uint32_t nunits, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px,
                    uint32_t planes, uint32_t llw, uint32_t llh, cudaStream_t st, LaunchStats &ls, bool bits8) {
     if (!nslots || !ngroups) return ICER_RESULT_OK;
+    const size_t count = nbatch * nunits;
+    k_valid_planes<<<(unsigned) ((count + 255) / 256), 256, 0, st>>>(pstat, vp, count, (int) planes);
+    ls.launches++;
     for (uint32_t g0 = 0; g0 < ngroups; g0 += 32768) {
         const uint32_t cnt = ngroups - g0 < 32768 ? ngroups - g0 : 32768;
         dim3 grid(slice_grid_x(nslots, cnt), cnt);
-        k_unslice<<<grid, 1024, 0, st>>>(bs + (size_t) g0 * dec_slice_words(planes, nslots), frames, slots, units, pstat, frame_of + (size_t) g0 * 32, mean,
-                                         nslots, nunits, chan, w, h, cap_px, (int) planes, (int) llw, (int) llh, bits8 ? 1 : 0);
+        const uint32_t *src = bs + (size_t) g0 * dec_slice_words(planes, nslots);
+        ICER_FOR_PLANES((int) planes, dec(grid, st, src, frames, slots, vp, frame_of + (size_t) g0 * 32, mean, nslots, nunits, chan, w, h, cap_px,
+                                          (int) llw, (int) llh, bits8 ? 1 : 0))
         ls.launches++;
     }
     CUDA_TRY(cudaGetLastError());

@@ -25,6 +25,13 @@
 #else
 #define ICER_HD inline
 #endif
+// Re-convergence point of the lanes `mask` of a warp that all call the same step(): without it the compiler threads the jumps of
+// the set-up branches straight into the common tail and the tail runs once per branch (measured: 13 of 32 lanes active there).
+#if defined(__CUDA_ARCH__)
+#define ICER_CONVERGE(mask) __syncwarp(mask)
+#else
+#define ICER_CONVERGE(mask) ((void) (mask))
+#endif
 
 #ifndef ICER_RING
 #define ICER_RING 2048
@@ -64,7 +71,7 @@ ICER_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 // Tables every lane needs with divergent indices (shared memory on the device).
 struct CoreTables {
-    uint32_t cutlo[17], cuthi[17];   // per bin: cut-off below it / above it, sentinels 0 / 65537 -- validates a cached bin
+    struct alignas(8) Cut { uint32_t lo, hi; } cut[17];   // per bin: cut-off below it / above it, sentinels 0 / 65537 -- one 64-bit load validates a cached bin
     uint32_t cutoff[16];
     uint16_t v2v[8][32];             // encoder: keyed by the gathered input word: in_bits | out_bits << 4 | out << 8
                                      // decoder: keyed by the NEXT 5 stream bits: codeword length | out_bits << 4 | out << 8
@@ -91,7 +98,8 @@ ICER_HD int bin_of(const CoreTables &T, uint32_t zz, uint32_t tot) {
 // cut[guess-1] * tot <= zz * 65536 < cut[guess] * tot.
 ICER_HD int bin_cached(const CoreTables &T, uint32_t zz, uint32_t tot, int guess) {
     const uint32_t lhs = zz << 16;
-    if (lhs >= tot * T.cutlo[guess] && lhs < tot * T.cuthi[guess]) return guess;
+    const CoreTables::Cut c = T.cut[guess];
+    if (lhs >= tot * c.lo && lhs < tot * c.hi) return guess;
     return bin_of(T, zz, tot);
 }
 #define ICER_CNT_Z(zt) (((zt) >> 16) & 0x7FFu)
@@ -246,24 +254,22 @@ struct EncLane {
     ICER_HD void begin_chunk() { col = 1; }
     ICER_HD bool chunk_done(int ncols) const { return col > ncols; }
 
-    // One micro-operation: skip a run of quiet pixels, apply a pending run, or code one magnitude / sign decision.
-    ICER_HD void step(const EncChunk &k, int sb) {
-        int bin;
-        uint32_t bit;
-        int ctx = -1;
-        uint32_t z = 0, tot = 0;
+    // One micro-operation: skip a run of quiet pixels, apply a pending run, or code one magnitude / sign decision.  The three kinds
+    // set up an operation and meet again before the common coding tail (no early returns: lanes that took different branches
+    // re-converge there, so the tail and the completion site run once per step for the whole warp).
+    ICER_HD void step(const EncChunk &k, int sb, unsigned lanes) {
+        enum { OP_NONE = 0, OP_CODE = 1, OP_FORCE = 2, OP_DONE = 3 };
+        int op = OP_NONE;
+        int bin = 0, ctx = -1;
+        uint32_t bit = 0, z = 0, tot = 0, code = 0, nb = 0;
         bool inv = false;
         if (phase == 0) {
             const uint32_t nqs = k.nq >> col;               // bit 0: this column; never zero (the bits above the chunk are set)
-            if (fz_left) {
-                const uint32_t r = (uint32_t) ctz32(nqs);
-                if (r) {                                    // r quiet pixels ahead: they only bump counters
-                    const uint32_t n = umin32(r, fz_left);
-                    fz_run += n; fz_left -= n; col += (int) n;
-                    return;
-                }
-            }
-            if (fz_run) {
+            const uint32_t r = fz_left ? (uint32_t) ctz32(nqs) : 0u;
+            if (r) {                                        // r quiet pixels ahead: they only bump counters
+                const uint32_t n = umin32(r, fz_left);
+                fz_run += n; fz_left -= n; col += (int) n;
+            } else if (fz_run) {
                 // apply `fz_run` (context 0, bit 0) decisions at once
                 bin = fz_bin;
                 const uint32_t zt = cnt[0];
@@ -272,28 +278,29 @@ struct EncLane {
                 cnt[0] = ICER_CNT_PACK(bin, zz, tt);
                 const uint32_t kk = bst[bin * STRIDE] + fz_run;
                 fz_run = 0; fz_left = 0;
-                if (kk >= T.gol_m[bin]) complete(bin, 1, 1);
+                if (kk >= T.gol_m[bin]) { op = OP_DONE; code = 1; nb = 1; }
                 else bst[bin * STRIDE] = kk;
-                return;
-            }
-            const int selfp = (int) ((k.bP >> col) & 1u);
-            const int cat = selfp ? 1 + (int) ((k.b2 >> col) & 1u) + (int) ((k.b3 >> col) & 1u) : 0;     // icer_context_modeller.c:631-634
-            bit = (k.bB >> col) & 1u;
-            if (cat == 3) {
-                bin = 0;                                    // p(0) = 1/2 -> uncoded bin
-                if (window_full_for(0)) { force_oldest(); return; }
             } else {
-                const int s = col - 1;
-                const uint32_t nm = ((k.aS >> s) & 7u) | (((k.bSc >> s) & 1u) << 3) | (((k.bP >> s) & 4u) << 2) | (((k.cP >> s) & 7u) << 5);
-                ctx = mag_ctx(T, sb, cat, nm);
-                const uint32_t zt = cnt[ctx * STRIDE];
-                z = ICER_CNT_Z(zt); tot = ICER_CNT_TOT(zt);
-                uint32_t zz = z;
-                inv = zz < (tot >> 1);
-                if (inv) zz = tot - zz;
-                bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
-                if (window_full_for(bin)) { force_oldest(); return; }      // then redo this decision
-                if (!(nqs & 1u) && !inv && bin > 7) {
+                const int selfp = (int) ((k.bP >> col) & 1u);
+                const int cat = selfp ? 1 + (int) ((k.b2 >> col) & 1u) + (int) ((k.b3 >> col) & 1u) : 0;     // icer_context_modeller.c:631-634
+                bit = (k.bB >> col) & 1u;
+                op = OP_CODE;
+                if (cat == 3) {
+                    bin = 0;                                // p(0) = 1/2 -> uncoded bin
+                } else {
+                    const int s = col - 1;
+                    const uint32_t nm = ((k.aS >> s) & 7u) | (((k.bSc >> s) & 1u) << 3) | (((k.bP >> s) & 4u) << 2) | (((k.cP >> s) & 7u) << 5);
+                    ctx = mag_ctx(T, sb, cat, nm);
+                    const uint32_t zt = cnt[ctx * STRIDE];
+                    z = ICER_CNT_Z(zt); tot = ICER_CNT_TOT(zt);
+                    uint32_t zz = z;
+                    inv = zz < (tot >> 1);
+                    if (inv) zz = tot - zz;
+                    bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
+                }
+                if (window_full_for(bin)) {
+                    op = OP_FORCE;                          // force the oldest codeword out first, then redo this decision
+                } else if (ctx >= 0 && !(nqs & 1u) && !inv && bin > 7) {
                     // enter the quiet fast path: this and the following quiet pixels only bump counters
                     open_bin(bin);
                     const uint32_t n1 = (uint32_t) T.gol_m[bin] - bst[bin * STRIDE];
@@ -303,10 +310,10 @@ struct EncLane {
                     fz_run = 1;
                     fz_bin = bin;
                     col++;
-                    return;
-                }
+                    op = OP_NONE;
+                } else if (cat == 0 && bit) phase = 1;      // first 1 of this coefficient: its sign follows
+                else col++;
             }
-            if (cat == 0 && bit) phase = 1; else col++;     // first 1 of this coefficient: its sign follows
         } else {
             const uint32_t m = ((k.nsA >> col) & 1u) | (((k.nsBc >> (col - 1)) & 1u) << 1) | (((k.nsBp >> (col + 1)) & 1u) << 2) |
                                (((k.nsC >> col) & 1u) << 3);
@@ -319,42 +326,49 @@ struct EncLane {
             inv = zz < (tot >> 1);
             if (inv) zz = tot - zz;
             bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
-            if (window_full_for(bin)) { force_oldest(); return; }
-            phase = 0; col++;
+            if (window_full_for(bin)) op = OP_FORCE;
+            else { op = OP_CODE; phase = 0; col++; }
         }
-        if (ctx >= 0) {
-            tot++;
-            z += bit ^ 1u;
-            if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }   // icer_context_modeller.c:396-402
-            cnt[ctx * STRIDE] = ICER_CNT_PACK(bin, z, tot);
-            bit ^= inv ? 1u : 0u;
-        }
-        open_bin(bin);
-        bool done = false;
-        uint32_t code = 0, nb = 0;
-        if (bin > 7) {                                        // Golomb run-length bins
-            if (bit) {
-                code = golomb_word(bin, bst[bin * STRIDE], nb);
-                done = true;
-            } else {
-                const uint32_t kk = bst[bin * STRIDE] + 1;
-                bst[bin * STRIDE] = kk;
-                if (kk >= T.gol_m[bin]) { code = 1; nb = 1; done = true; }
+        ICER_CONVERGE(lanes);       // ---- all lanes meet here ----
+        if (op == OP_CODE) {
+            if (ctx >= 0) {
+                tot++;
+                z += bit ^ 1u;
+                if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }   // icer_context_modeller.c:396-402
+                cnt[ctx * STRIDE] = ICER_CNT_PACK(bin, z, tot);
+                bit ^= inv ? 1u : 0u;
             }
-        } else if (bin != 0) {                                // variable-to-variable bins
-            const uint32_t stt = bst[bin * STRIDE];
-            const uint32_t fill = stt >> 16;
-            const uint32_t word = (stt & 0xFFFF) | (bit << fill);
-            const uint32_t e = T.v2v[bin][word & 31];
-            if ((e & 0xF) == fill + 1) { code = e >> 8; nb = (e >> 4) & 0xF; done = true; }
-            else bst[bin * STRIDE] = word | ((fill + 1) << 16);
-        } else {                                              // uncoded bin
-            code = bit & 1; nb = 1; done = true;
+            open_bin(bin);
+            if (bin > 7) {                                        // Golomb run-length bins
+                if (bit) {
+                    code = golomb_word(bin, bst[bin * STRIDE], nb);
+                    op = OP_DONE;
+                } else {
+                    const uint32_t kk = bst[bin * STRIDE] + 1;
+                    bst[bin * STRIDE] = kk;
+                    if (kk >= T.gol_m[bin]) { code = 1; nb = 1; op = OP_DONE; }
+                }
+            } else if (bin != 0) {                                // variable-to-variable bins
+                const uint32_t stt = bst[bin * STRIDE];
+                const uint32_t fill = stt >> 16;
+                const uint32_t word = (stt & 0xFFFF) | (bit << fill);
+                const uint32_t e = T.v2v[bin][word & 31];
+                if ((e & 0xF) == fill + 1) { code = e >> 8; nb = (e >> 4) & 0xF; op = OP_DONE; }
+                else bst[bin * STRIDE] = word | ((fill + 1) << 16);
+            } else {                                              // uncoded bin
+                code = bit & 1; nb = 1; op = OP_DONE;
+            }
+        } else if (op == OP_FORCE) {
+            // window full: force-complete the oldest codeword (icer_encoding.c:59-64); the decision is retried in the next step
+            bin = oldest;
+            code = forced_word(bin, nb);
+            op = OP_DONE;
         }
-        if (done) complete(bin, code, nb);
+        ICER_CONVERGE(lanes);
+        if (op == OP_DONE) complete(bin, code, nb);
     }
 
-    // window full: force-complete the oldest codeword (icer_encoding.c:59-64); the caller retries its decision
+    // force-complete the oldest codeword (end of stream)
     ICER_HD void force_oldest() {
         uint32_t nb;
         const int b = oldest;
@@ -511,82 +525,84 @@ struct DecLane {
     ICER_HD void begin_chunk() { col = 1; }
     ICER_HD bool chunk_done(int ncols) const { return !run || col > ncols; }
 
-    ICER_HD void step(DecChunk &k, int sb) {
-        int bin, ctx = -1;
-        int kind = 0;                                           // 0: sign decision, 2: magnitude decision of a category-0 pixel (a one starts the sign decision), 3: other magnitude decision
+    // One micro-operation (see EncLane::step): the set-up branches meet before the common decoding tail.
+    ICER_HD void step(DecChunk &k, int sb, unsigned lanes) {
+        int bin = 0, ctx = -1;
+        int kind = -1;                                          // -1: nothing to decode in this step, 0: sign decision, 2: magnitude decision of a category-0 pixel (a one starts the sign decision), 3: other magnitude decision
         uint32_t z = 0, tot = 0, e = 0;
         bool inv = false, quiet = false;
         if (phase == 0) {
             const uint32_t nqs = (k.nq | (k.bB << 1)) >> col;
-            if (fz_left) {
-                const uint32_t r = (uint32_t) ctz32(nqs);
-                if (r) {
-                    const uint32_t n = umin32(r, fz_left);
-                    fz_run += n; fz_left -= n; col += (int) n;
-                    return;
-                }
-            }
-            if (fz_run) {                                       // apply the pending run (no stream access), then go on with this pixel
-                const int fb = fz_bin;
-                const uint32_t zt = cnt[0];
-                uint32_t zz = ICER_CNT_Z(zt) + fz_run, tt = ICER_CNT_TOT(zt) + fz_run;
-                if (tt >= 500) { tt >>= 1; if (zz > tt) zz >>= 1; }
-                cnt[0] = ICER_CNT_PACK(fb, zz, tt);
-                depth[fb * STRIDE] = (int16_t) (depth[fb * STRIDE] - (int) fz_run);
-                fz_run = 0; fz_left = 0;
-            }
-            quiet = !(nqs & 1u);
-            const int selfp = (int) ((k.bP >> col) & 1u);
-            const int cat = selfp ? 1 + (int) ((k.b2 >> col) & 1u) + (int) ((k.b3 >> col) & 1u) : 0;
-            if (cat == 3) {
-                bin = 0;
+            const uint32_t r = fz_left ? (uint32_t) ctz32(nqs) : 0u;
+            if (r) {
+                const uint32_t n = umin32(r, fz_left);
+                fz_run += n; fz_left -= n; col += (int) n;
             } else {
-                const int s = col - 1;
-                const uint32_t bSc = k.bP | k.bB;
-                const uint32_t nm = ((k.aS >> s) & 7u) | (((bSc >> s) & 1u) << 3) | (((k.bP >> s) & 4u) << 2) | (((k.cP >> s) & 7u) << 5);
-                ctx = mag_ctx(T, sb, cat, nm);
+                if (fz_run) {                                   // apply the pending run (no stream access), then go on with this pixel
+                    const int fb = fz_bin;
+                    const uint32_t zt = cnt[0];
+                    uint32_t zz = ICER_CNT_Z(zt) + fz_run, tt = ICER_CNT_TOT(zt) + fz_run;
+                    if (tt >= 500) { tt >>= 1; if (zz > tt) zz >>= 1; }
+                    cnt[0] = ICER_CNT_PACK(fb, zz, tt);
+                    depth[fb * STRIDE] = (int16_t) (depth[fb * STRIDE] - (int) fz_run);
+                    fz_run = 0; fz_left = 0;
+                }
+                quiet = !(nqs & 1u);
+                const int selfp = (int) ((k.bP >> col) & 1u);
+                const int cat = selfp ? 1 + (int) ((k.b2 >> col) & 1u) + (int) ((k.b3 >> col) & 1u) : 0;
+                if (cat != 3) {
+                    const int s = col - 1;
+                    const uint32_t bSc = k.bP | k.bB;
+                    const uint32_t nm = ((k.aS >> s) & 7u) | (((bSc >> s) & 1u) << 3) | (((k.bP >> s) & 4u) << 2) | (((k.cP >> s) & 7u) << 5);
+                    ctx = mag_ctx(T, sb, cat, nm);
+                }
+                kind = (cat == 0) ? 2 : 3;
             }
-            kind = (cat == 0) ? 2 : 3;
         } else {
             const uint32_t nsBc = (k.bNp | k.bNn) & (k.bP | k.bB), nsBp = k.bNp & k.bP;
             const uint32_t m = ((k.nsA >> col) & 1u) | (((nsBc >> (col - 1)) & 1u) << 1) | (((nsBp >> (col + 1)) & 1u) << 2) |
                                (((k.nsC >> col) & 1u) << 3);
             e = T.lut_sign[sb == 1][m];
             ctx = (int) (e & 0x7Fu);
+            kind = 0;
         }
-        if (ctx >= 0) {
-            const uint32_t zt = cnt[ctx * STRIDE];
-            z = ICER_CNT_Z(zt); tot = ICER_CNT_TOT(zt);
-            uint32_t zz = z;
-            inv = zz < (tot >> 1);
-            if (inv) zz = tot - zz;
-            bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
-        } else bin = 0;
-        // next decoded bit of `bin` (icer_decoding.c:127, :186-192)
-        int dep = depth[bin * STRIDE];
-        const uint32_t slw = stlow[bin * STRIDE];
-        uint32_t low = slw >> 24;
-        bool refilled = false;
-        if (dep <= 0 || br.words - (slw & 0xFFFFFFu) >= ICER_RING) {
-            const int rc = br.refill(T, bin, dep, low);
-            if (rc != ST_OK) { run = false; err = rc; return; }
-            refilled = true;
+        ICER_CONVERGE(lanes);       // ---- all lanes meet here ----
+        int dep = 0;
+        uint32_t low = 0, stamp = 0;
+        if (kind >= 0) {
+            if (ctx >= 0) {
+                const uint32_t zt = cnt[ctx * STRIDE];
+                z = ICER_CNT_Z(zt); tot = ICER_CNT_TOT(zt);
+                uint32_t zz = z;
+                inv = zz < (tot >> 1);
+                if (inv) zz = tot - zz;
+                bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
+            }
+            // next decoded bit of `bin` (icer_decoding.c:127, :186-192)
+            dep = depth[bin * STRIDE];
+            const uint32_t slw = stlow[bin * STRIDE];
+            low = slw >> 24;
+            stamp = slw & 0xFFFFFFu;
+            if (dep <= 0 || br.words - stamp >= ICER_RING) {
+                const int rc = br.refill(T, bin, dep, low);
+                if (rc != ST_OK) { run = false; err = rc; kind = -1; }
+                stamp = br.words & 0xFFFFFFu;
+            }
         }
-        const uint32_t stamp = refilled ? (br.words & 0xFFFFFFu) : (slw & 0xFFFFFFu);
-        if (kind && quiet && !inv && bin > 7) {
+        ICER_CONVERGE(lanes);       // the lanes that had to fetch a codeword are back
+        if (kind < 0) return;
+        if (kind && quiet && !inv && bin > 7 && (uint32_t) dep > (low & 1u)) {
             // quiet fast path: the run of pending zeros of this Golomb bin is taken without touching the stack
             const uint32_t zeros = (uint32_t) dep - (low & 1u);
-            if (zeros > 0) {
-                const uint32_t n2 = zeros_in_same_bin(T, bin, z, tot);
-                const uint32_t n3 = 500u - tot;
-                depth[bin * STRIDE] = (int16_t) dep;
-                stlow[bin * STRIDE] = stamp | (low << 24);
-                fz_left = umin32(zeros, umin32(n2, n3)) - 1;
-                fz_run = 1;
-                fz_bin = bin;
-                phase = 0; col++;
-                return;
-            }
+            const uint32_t n2 = zeros_in_same_bin(T, bin, z, tot);
+            const uint32_t n3 = 500u - tot;
+            depth[bin * STRIDE] = (int16_t) dep;
+            stlow[bin * STRIDE] = stamp | (low << 24);
+            fz_left = umin32(zeros, umin32(n2, n3)) - 1;
+            fz_run = 1;
+            fz_bin = bin;
+            col++;
+            return;
         }
         const int top = dep - 1;
         uint32_t b = 0;
@@ -601,10 +617,10 @@ struct DecLane {
             cnt[ctx * STRIDE] = ICER_CNT_PACK(bin, z, tot);
         }
         if (kind) {
-            if (bit) k.bB |= 1u << col;
+            k.bB |= bit << col;
             if (bit && kind == 2) phase = 1; else col++;
         } else {
-            if ((bit ^ (e >> 7)) & 1u) k.bNn |= 1u << col;
+            k.bNn |= ((bit ^ (e >> 7)) & 1u) << col;
             phase = 0; col++;
         }
     }

@@ -80,8 +80,8 @@ inline void fill_core_tables(icer_core::CoreTables &d, const HostTables &h, bool
     memset(&d, 0, sizeof d);
     for (int b = 0; b < 16; b++) d.cutoff[b] = h.cutoff[b];
     for (int b = 0; b < 17; b++) {
-        d.cutlo[b] = b ? h.cutoff[b - 1] : 0u;
-        d.cuthi[b] = b < 16 ? h.cutoff[b] : 65537u;
+        d.cut[b].lo = b ? h.cutoff[b - 1] : 0u;
+        d.cut[b].hi = b < 16 ? h.cutoff[b] : 65537u;
         d.gol_m[b] = h.gol_m[b]; d.gol_l[b] = h.gol_l[b]; d.gol_i[b] = h.gol_i[b];
     }
     for (int b = 0; b < 8; b++)

@@ -159,9 +159,10 @@ int launch_decode(const DecodeArgs &a, cudaStream_t st, LaunchStats &ls);
 // batch index, -1 = none)
 size_t enc_slice_words(uint32_t planes, uint32_t nslots);      // 32-bit words per group
 size_t dec_slice_words(uint32_t planes, uint32_t nslots);
-int launch_bitslice(const uint16_t *coefs, uint32_t *bs, const SlotDesc *slots, const Unit *units, uint32_t nslots, uint32_t nframes,
-                    uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h, uint32_t planes, bool twos_complement, cudaStream_t st, LaunchStats &ls);
-int launch_unslice(const uint32_t *bs, uint16_t *frames, const SlotDesc *slots, const Unit *units, const uint8_t *pstat, const int32_t *frame_of,
+int launch_bitslice(const uint16_t *coefs, uint32_t *bs, const SlotDesc *slots, uint32_t nslots, uint32_t nframes, uint32_t ngroups, uint32_t chan,
+                    uint32_t w, uint32_t h, uint32_t planes, bool twos_complement, cudaStream_t st, LaunchStats &ls);
+// pstat: [nbatch][nunits][planes] plane status written by the decoder; vp: [nbatch][nunits] scratch (lowest plane that counts)
+int launch_unslice(const uint32_t *bs, uint16_t *frames, const SlotDesc *slots, const uint8_t *pstat, uint8_t *vp, size_t nbatch, const int32_t *frame_of,
                    const uint16_t *mean, uint32_t nslots, uint32_t nunits, uint32_t ngroups, uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px,
                    uint32_t planes, uint32_t llw, uint32_t llh, cudaStream_t st, LaunchStats &ls, bool bits8 = false);
 

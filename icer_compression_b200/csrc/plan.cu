@@ -134,7 +134,7 @@ int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages,
                 d.x0 = (uint16_t) (q.x + (int) j * ICER_CHUNK); d.y = (uint16_t) (q.y + r); d.unit = (uint16_t) k;
                 const int left = q.w - (int) j * ICER_CHUNK;
                 d.ncols = (uint8_t) (left < ICER_CHUNK ? left : ICER_CHUNK);
-                d.flags = (uint8_t) ((j > 0 ? 1 : 0) | (j + 1 < q.cw ? 2 : 0));
+                d.flags = (uint8_t) ((j > 0 ? 1 : 0) | (j + 1 < q.cw ? 2 : 0) | (q.chan << 2));
                 pl.slots.push_back(d);
             }
     }

@@ -23,8 +23,18 @@ for r in body:
     key=off2line.get(off)
     v=float(r[ix['Instructions Executed']]); t=float(r[ix['Thread Instructions Executed']]); s=float(r[ix['# Samples']])
     agg[key]+=v; aggt[key]+=t; smp[key]+=s; tot+=v
-src=open(srcfile).read().split('\n'); ts=sum(smp.values())
+import os
+srcdir=os.path.dirname(srcfile); srcs={}
+def line_of(k):
+    if not k: return str(k)
+    f=os.path.join(srcdir,k[0])
+    if f not in srcs:
+        try: srcs[f]=open(f).read().split('\n')
+        except OSError: srcs[f]=None
+    if srcs[f] is None or k[1]-1>=len(srcs[f]): return str(k)
+    return (k[0][:12]+': '+srcs[f][k[1]-1].strip())[:110]
+ts=sum(smp.values())
 print("total warp inst %.3g, mapped %d offsets"%(tot,len(off2line)))
 for k,v in agg.most_common(int(sys.argv[5]) if len(sys.argv)>5 else 45):
-    txt_ = src[k[1]-1].strip()[:95] if k and k[0]==srcfile.split('/')[-1] else str(k)
+    txt_ = line_of(k)
     print(f"{100*v/tot:5.1f}% inst {100*smp[k]/ts:5.1f}% smp thr/inst {aggt[k]/max(v,1):5.1f} {k[1] if k else '?':>4} {txt_}")

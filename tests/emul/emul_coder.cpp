@@ -55,7 +55,7 @@ extern "C" long emul_encode_segment_plane(const uint16_t *seg, size_t w, size_t 
             k.set(s.S(ra, j, lsb + 1), s.B(ra, j, lsb), s.N(ra, j), s.S(r, j, lsb + 1), s.B(r, j, lsb), s.N(r, j), s.S(r, j, lsb + 2), s.S(r, j, lsb + 3),
                   s.S(rc, j, lsb + 1), s.N(rc, j), ncols);
             ln.begin_chunk();
-            while (!ln.chunk_done(ncols)) { ln.step(k, subband); ln.pump(); steps++; }
+            while (!ln.chunk_done(ncols)) { ln.step(k, subband, 1u); ln.pump(); steps++; }
         }
     uint32_t bits = 0;
     ln.finish(bits);
@@ -87,7 +87,7 @@ extern "C" int emul_decode_segment_plane(uint16_t *seg, size_t w, size_t h, size
             const long rc = (long) r + 1;
             k.set(aS, aN, s.S(r, j, lsb + 1), s.N(r, j), s.S(r, j, lsb + 2), s.S(r, j, lsb + 3), s.S(rc, j, lsb + 1), s.N(rc, j), carryB, carryN, ncols);
             ln.begin_chunk();
-            while (!ln.chunk_done(ncols)) ln.step(k, subband);
+            while (!ln.chunk_done(ncols)) ln.step(k, subband, 1u);
             // this chunk's words; the right halo is patched when the next chunk's first column is known
             const uint32_t sw = k.bP | k.bB, nw = k.bNp | k.bNn;
             if (j > 0) {
