@@ -30,9 +30,6 @@ constexpr int NT = 128;   // threads per encoder block
 #ifndef ICER_ENC_MINI
 #define ICER_ENC_MINI 8
 #endif
-#ifndef ICER_ENC_PUMPS
-#define ICER_ENC_PUMPS 1
-#endif
 #ifndef ICER_ENC_MINBLOCKS
 #define ICER_ENC_MINBLOCKS 8
 #endif
@@ -204,7 +201,7 @@ struct EncSmem {
     CoreTables T;
     uint32_t cnt[17][NT];      // cached bin << 27 | zero << 16 | total, per context
     uint16_t bseq[17][NT];     // sequence number (low 16 bits; the window spans 2048) of the codeword each bin is building
-    uint32_t bst[17][NT];      // Golomb: zeros counted; variable-to-variable: input word (first bit = bit 0) | bits gathered << 16
+    uint16_t bst[17][NT];      // Golomb: zeros counted; variable-to-variable: input word (first bit = bit 0) | bits gathered << 8
     uint16_t mini[ICER_ENC_MINI > 0 ? ICER_ENC_MINI : 1][NT];   // parked codewords close to the emission point
 };
 
@@ -263,10 +260,7 @@ __global__ void __launch_bounds__(NT, ICER_ENC_MINBLOCKS) k_encode(EncodeArgs a)
                     const unsigned lanes = __ballot_sync(0xffffffffu, busy);
                     if (!lanes) break;
                     if (busy) ln.step(k, sb, lanes);
-                    ln.pump();       // a completion can release several parked codewords: more than one emission per step keeps the backlog short
-#if ICER_ENC_PUMPS > 1
-                    ln.pump();
-#endif
+                    ln.pump();       // one emission per step keeps pace: a step starts at most one codeword
                 }
             }
         }

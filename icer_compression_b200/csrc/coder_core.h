@@ -152,7 +152,7 @@ struct EncLane {
     const CoreTables &T;
     uint32_t *cnt;      // [17] (stride STRIDE): cached bin << 27 | zero count << 16 | total count, per context
     uint16_t *bseq;     // [17] sequence number (low 16 bits; the window spans 2048) of the codeword each bin is building
-    uint32_t *bst;      // [17] Golomb: zeros counted; variable-to-variable: input word (first bit = bit 0) | bits gathered << 16
+    uint16_t *bst;      // [17] Golomb: zeros counted; variable-to-variable: input word (first bit = bit 0) | bits gathered << 8
     uint16_t *mini;     // [MINI] parked codewords close to the emission point (see complete())
     uint16_t *ring;     // [ICER_RING] parked codewords further away (global memory)
     uint32_t *out;
@@ -161,7 +161,8 @@ struct EncLane {
     int nacc = 0;
     // Interleave-window bookkeeping.  A codeword gets a sequence number when its first bit arrives (lib_icer: a ring slot,
     // icer_encoding.c:59-67); `head` = first sequence number that is not complete; everything in [emit_pos, head) is ready.
-    uint32_t head = 0, tail = 0, open_mask = 0;   // bits 24.. of open_mask: which slots of `mini` hold a parked codeword
+    uint32_t head = 0, tail = 0, open_mask = 0;
+    uint32_t mini_mask = 0;       // which slots of `mini` hold a parked codeword
     uint32_t emit_pos = 0;
     int oldest = 0;
     bool overflow = false;
@@ -172,7 +173,7 @@ struct EncLane {
     int col = 1;        // 1..ncols; > ncols: chunk finished
     int phase = 0;      // 0: magnitude decision next, 1: sign decision of this pixel next
 
-    ICER_HD EncLane(const CoreTables &t, uint32_t *c, uint16_t *bs, uint32_t *st, uint16_t *mn, uint16_t *r, uint32_t *o, uint32_t cp)
+    ICER_HD EncLane(const CoreTables &t, uint32_t *c, uint16_t *bs, uint16_t *st, uint16_t *mn, uint16_t *r, uint32_t *o, uint32_t cp)
         : T(t), cnt(c), bseq(bs), bst(st), mini(mn), ring(r), out(o), cap(cp) {
         for (int k = 0; k < 17; k++) cnt[k * STRIDE] = ICER_CNT_INIT;
     }
@@ -192,14 +193,14 @@ struct EncLane {
         // number in [emit_pos, emit_pos + MINI), so slot = seq mod MINI is unambiguous
         if (MINI > 0 && ((seq - emit_pos) & 0xFFFFu) < (uint32_t) MINI) {
             mini[(seq & (MINI - 1)) * STRIDE] = (uint16_t) ((nb << 11) | code);
-            open_mask |= 0x1000000u << (seq & (MINI - 1));
+            mini_mask |= 1u << (seq & (MINI - 1));
         } else {
             ring[seq & (ICER_RING - 1)] = (uint16_t) ((nb << 11) | code);
         }
         if (seq != (head & 0xFFFFu)) return;
         const uint32_t h1 = head + 1;
         uint32_t dist = tail - h1;                       // every other open codeword lies in [head + 1, tail)
-        for (uint32_t m = open_mask & 0x1FFFFu; m; m &= m - 1) {
+        for (uint32_t m = open_mask; m; m &= m - 1) {
             const int b = ctz32(m);
             const uint32_t d = ((uint32_t) bseq[b * STRIDE] - h1) & 0xFFFFu;
             if (d < dist) { dist = d; oldest = b; }
@@ -212,7 +213,7 @@ struct EncLane {
         if (emit_pos == head) return;
         uint32_t v;
         const uint32_t slot = emit_pos & (uint32_t) ((MINI > 0 ? MINI : 1) - 1);
-        if (MINI > 0 && ((open_mask >> (24 + slot)) & 1u)) { v = mini[slot * STRIDE]; open_mask &= ~(0x1000000u << slot); }
+        if (MINI > 0 && ((mini_mask >> slot) & 1u)) { v = mini[slot * STRIDE]; mini_mask &= ~(1u << slot); }
         else v = ring[emit_pos & (ICER_RING - 1)];
         emit_pos++;
         acc |= (unsigned long long) (v & 0x7FF) << nacc;
@@ -232,7 +233,7 @@ struct EncLane {
             if (st == (uint32_t) T.gol_m[bin] - 1) { nb = 1; return 1; }
             return golomb_word(bin, st, nb);
         }
-        const uint32_t pre = st & 0xFFFF, fill = st >> 16;
+        const uint32_t pre = st & 0xFF, fill = st >> 8;
         const uint32_t fl = T.flush[bin][pre][fill];
         const uint32_t word = (pre | ((fl & 0xF) << fill)) & 0x3FF;
         const uint32_t e = T.v2v[bin][word & 31];
@@ -245,7 +246,7 @@ struct EncLane {
     ICER_HD void open_bin(int bin) {
         if (open_mask & (1u << bin)) return;
         while (tail - emit_pos >= ICER_RING) pump();       // physical ring space (emission may lag behind `head`)
-        if ((open_mask & 0x1FFFFu) == 0) oldest = bin;
+        if ((open_mask) == 0) oldest = bin;
         bseq[bin * STRIDE] = (uint16_t) tail++;
         bst[bin * STRIDE] = 0;
         open_mask |= 1u << bin;
@@ -254,15 +255,15 @@ struct EncLane {
     ICER_HD void begin_chunk() { col = 1; }
     ICER_HD bool chunk_done(int ncols) const { return col > ncols; }
 
-    // One micro-operation: skip a run of quiet pixels, apply a pending run, or code one magnitude / sign decision.  The three kinds
-    // set up an operation and meet again before the common coding tail (no early returns: lanes that took different branches
-    // re-converge there, so the tail and the completion site run once per step for the whole warp).
+    // One micro-operation: skip a run of quiet pixels, apply a pending run, or code one magnitude / sign decision.  The set-up
+    // branches only derive (context, bit); the lanes meet again before the common part -- adaptive counts, bin, interleave window,
+    // codeword building, completion -- which therefore runs once per step for the whole warp.
     ICER_HD void step(const EncChunk &k, int sb, unsigned lanes) {
-        enum { OP_NONE = 0, OP_CODE = 1, OP_FORCE = 2, OP_DONE = 3 };
+        enum { OP_NONE = 0, OP_CODE = 1, OP_DONE = 3 };
         int op = OP_NONE;
+        int kind = 0;                                       // 1: magnitude decision, 2: ... of a quiet pixel, 4: ... whose one starts the sign decision; 8: sign decision
         int bin = 0, ctx = -1;
-        uint32_t bit = 0, z = 0, tot = 0, code = 0, nb = 0;
-        bool inv = false;
+        uint32_t bit = 0, code = 0, nb = 0;
         if (phase == 0) {
             const uint32_t nqs = k.nq >> col;               // bit 0: this column; never zero (the bits above the chunk are set)
             const uint32_t r = fz_left ? (uint32_t) ctz32(nqs) : 0u;
@@ -279,40 +280,17 @@ struct EncLane {
                 const uint32_t kk = bst[bin * STRIDE] + fz_run;
                 fz_run = 0; fz_left = 0;
                 if (kk >= T.gol_m[bin]) { op = OP_DONE; code = 1; nb = 1; }
-                else bst[bin * STRIDE] = kk;
+                else bst[bin * STRIDE] = (uint16_t) kk;
             } else {
                 const int selfp = (int) ((k.bP >> col) & 1u);
                 const int cat = selfp ? 1 + (int) ((k.b2 >> col) & 1u) + (int) ((k.b3 >> col) & 1u) : 0;     // icer_context_modeller.c:631-634
                 bit = (k.bB >> col) & 1u;
-                op = OP_CODE;
-                if (cat == 3) {
-                    bin = 0;                                // p(0) = 1/2 -> uncoded bin
-                } else {
+                kind = 1 | ((nqs & 1u) ? 0 : 2) | ((cat == 0 && bit) ? 4 : 0);
+                if (cat != 3) {                             // category 3: p(0) = 1/2 -> uncoded bin, no context
                     const int s = col - 1;
                     const uint32_t nm = ((k.aS >> s) & 7u) | (((k.bSc >> s) & 1u) << 3) | (((k.bP >> s) & 4u) << 2) | (((k.cP >> s) & 7u) << 5);
                     ctx = mag_ctx(T, sb, cat, nm);
-                    const uint32_t zt = cnt[ctx * STRIDE];
-                    z = ICER_CNT_Z(zt); tot = ICER_CNT_TOT(zt);
-                    uint32_t zz = z;
-                    inv = zz < (tot >> 1);
-                    if (inv) zz = tot - zz;
-                    bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
                 }
-                if (window_full_for(bin)) {
-                    op = OP_FORCE;                          // force the oldest codeword out first, then redo this decision
-                } else if (ctx >= 0 && !(nqs & 1u) && !inv && bin > 7) {
-                    // enter the quiet fast path: this and the following quiet pixels only bump counters
-                    open_bin(bin);
-                    const uint32_t n1 = (uint32_t) T.gol_m[bin] - bst[bin * STRIDE];
-                    const uint32_t n2 = zeros_in_same_bin(T, bin, z, tot);
-                    const uint32_t n3 = 500u - tot;
-                    fz_left = umin32(n1, umin32(n2, n3)) - 1;
-                    fz_run = 1;
-                    fz_bin = bin;
-                    col++;
-                    op = OP_NONE;
-                } else if (cat == 0 && bit) phase = 1;      // first 1 of this coefficient: its sign follows
-                else col++;
             }
         } else {
             const uint32_t m = ((k.nsA >> col) & 1u) | (((k.nsBc >> (col - 1)) & 1u) << 1) | (((k.nsBp >> (col + 1)) & 1u) << 2) |
@@ -320,49 +298,63 @@ struct EncLane {
             const uint32_t e = T.lut_sign[sb == 1][m];
             ctx = (int) (e & 0x7Fu);
             bit = ((e >> 7) ^ (k.bN >> col)) & 1u;
-            const uint32_t zt = cnt[ctx * STRIDE];
-            z = ICER_CNT_Z(zt); tot = ICER_CNT_TOT(zt);
-            uint32_t zz = z;
-            inv = zz < (tot >> 1);
-            if (inv) zz = tot - zz;
-            bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
-            if (window_full_for(bin)) op = OP_FORCE;
-            else { op = OP_CODE; phase = 0; col++; }
+            kind = 8;
         }
         ICER_CONVERGE(lanes);       // ---- all lanes meet here ----
-        if (op == OP_CODE) {
+        if (kind) {
+            uint32_t z = 0, tot = 0;
+            bool inv = false;
             if (ctx >= 0) {
-                tot++;
-                z += bit ^ 1u;
-                if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }   // icer_context_modeller.c:396-402
-                cnt[ctx * STRIDE] = ICER_CNT_PACK(bin, z, tot);
-                bit ^= inv ? 1u : 0u;
+                const uint32_t zt = cnt[ctx * STRIDE];
+                z = ICER_CNT_Z(zt); tot = ICER_CNT_TOT(zt);
+                uint32_t zz = z;
+                inv = zz < (tot >> 1);
+                if (inv) zz = tot - zz;
+                bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
             }
-            open_bin(bin);
-            if (bin > 7) {                                        // Golomb run-length bins
-                if (bit) {
-                    code = golomb_word(bin, bst[bin * STRIDE], nb);
-                    op = OP_DONE;
-                } else {
-                    const uint32_t kk = bst[bin * STRIDE] + 1;
-                    bst[bin * STRIDE] = kk;
-                    if (kk >= T.gol_m[bin]) { code = 1; nb = 1; op = OP_DONE; }
+            if (window_full_for(bin)) {
+                // window full: force-complete the oldest codeword (icer_encoding.c:59-64); the decision is retried in the next step
+                bin = oldest;
+                code = forced_word(bin, nb);
+                op = OP_DONE;
+            } else if ((kind & 2) && ctx >= 0 && !inv && bin > 7) {
+                // enter the quiet fast path: this and the following quiet pixels only bump counters
+                open_bin(bin);
+                const uint32_t n1 = (uint32_t) T.gol_m[bin] - bst[bin * STRIDE];
+                const uint32_t n2 = zeros_in_same_bin(T, bin, z, tot);
+                const uint32_t n3 = 500u - tot;
+                fz_left = umin32(n1, umin32(n2, n3)) - 1;
+                fz_run = 1;
+                fz_bin = bin;
+                col++;
+            } else {
+                if (kind & 4) phase = 1;                    // first 1 of this coefficient: its sign follows
+                else { phase = 0; col++; }
+                if (ctx >= 0) {
+                    tot++;
+                    z += bit ^ 1u;
+                    if (tot >= 500) { tot >>= 1; if (z > tot) z >>= 1; }   // icer_context_modeller.c:396-402
+                    cnt[ctx * STRIDE] = ICER_CNT_PACK(bin, z, tot);
+                    bit ^= inv ? 1u : 0u;
                 }
-            } else if (bin != 0) {                                // variable-to-variable bins
+                open_bin(bin);
                 const uint32_t stt = bst[bin * STRIDE];
-                const uint32_t fill = stt >> 16;
-                const uint32_t word = (stt & 0xFFFF) | (bit << fill);
-                const uint32_t e = T.v2v[bin][word & 31];
-                if ((e & 0xF) == fill + 1) { code = e >> 8; nb = (e >> 4) & 0xF; op = OP_DONE; }
-                else bst[bin * STRIDE] = word | ((fill + 1) << 16);
-            } else {                                              // uncoded bin
-                code = bit & 1; nb = 1; op = OP_DONE;
+                if (bin > 7) {                                        // Golomb run-length bins
+                    if (bit) {
+                        code = golomb_word(bin, stt, nb);
+                        op = OP_DONE;
+                    } else {
+                        bst[bin * STRIDE] = (uint16_t) (stt + 1);
+                        if (stt + 1 >= T.gol_m[bin]) { code = 1; nb = 1; op = OP_DONE; }
+                    }
+                } else {                                              // variable-to-variable bins; bin 0 (uncoded) is the identity code
+                    const uint32_t fill = stt >> 8;
+                    const uint32_t word = (stt & 0xFF) | (bit << fill);
+                    const uint32_t e = T.v2v[bin][word & 31];
+                    if ((e & 0xF) == fill + 1) { code = e >> 8; nb = (e >> 4) & 0xF; op = OP_DONE; }
+                    else bst[bin * STRIDE] = (uint16_t) (word | ((fill + 1) << 8));
+                }
             }
-        } else if (op == OP_FORCE) {
-            // window full: force-complete the oldest codeword (icer_encoding.c:59-64); the decision is retried in the next step
-            bin = oldest;
-            code = forced_word(bin, nb);
-            op = OP_DONE;
         }
         ICER_CONVERGE(lanes);
         if (op == OP_DONE) complete(bin, code, nb);
@@ -381,10 +373,10 @@ struct EncLane {
             const int bin = fz_bin;
             const uint32_t kk = bst[bin * STRIDE] + fz_run;
             if (kk >= T.gol_m[bin]) complete(bin, 1, 1);
-            else bst[bin * STRIDE] = kk;
+            else bst[bin * STRIDE] = (uint16_t) kk;
             fz_run = 0;
         }
-        while (open_mask & 0x1FFFFu) force_oldest();           // icer_context_modeller.c:452-455
+        while (open_mask) force_oldest();           // icer_context_modeller.c:452-455
         while (emit_pos != head) pump();
         bits_out = nwords * 32u + (uint32_t) nacc;
         if (nacc > 0) { if (nwords < cap) out[nwords] = (uint32_t) acc; else overflow = true; }

@@ -88,6 +88,7 @@ inline void fill_core_tables(icer_core::CoreTables &d, const HostTables &h, bool
         for (int x = 0; x < 32; x++) {
             if (!decoder) {
                 d.v2v[b][x] = (uint16_t) (h.enc[b][x].in_bits | (h.enc[b][x].out_bits << 4) | (h.enc[b][x].out << 8));
+                if (b == 0) d.v2v[b][x] = (uint16_t) (1 | (1 << 4) | ((x & 1) << 8));      // the uncoded bin as a one-bit identity code
             } else {
                 // the variable-to-variable codes are complete prefix codes of at most 5 bits: the next 5 stream bits select the
                 // codeword directly (same first-match order as the bit-by-bit loop of icer_decoding.c:155-177)

@@ -41,7 +41,7 @@ extern "C" long emul_encode_segment_plane(const uint16_t *seg, size_t w, size_t 
                                           size_t max_bytes, uint32_t *steps_out) {
     ready();
     Seg s{seg, w, h, rowstride};
-    uint32_t cnt[17]; uint16_t bseq[17]; uint32_t bst[17]; uint16_t mini[8];
+    uint32_t cnt[17]; uint16_t bseq[17]; uint16_t bst[17]; uint16_t mini[8];
     std::vector<uint16_t> ring(ICER_RING);
     std::vector<uint32_t> words(max_bytes / 4 + 2);
     EncLane<1, 8> ln(g_enc, cnt, bseq, bst, mini, ring.data(), words.data(), (uint32_t) (max_bytes / 4));
