@@ -437,7 +437,7 @@ class Bench:
         n, chan, h, w = frames.shape
         quota = wl["quota"]
         big = n * chan * h * w * 2 > (3 << 30)
-        nworkers = 1 if (big or len(self.devices) > 1 or self.args.e2e_workers < 2) else 2
+        nworkers = 1 if (big or len(self.devices) > 1 or self.args.e2e_workers < 2) else min(self.args.e2e_workers, 4)
         old_aff = os.sched_getaffinity(0)
         cpus = gpu_numa_cpus(self.devices[0]) if len(self.devices) == 1 else None
         if cpus:
@@ -519,7 +519,7 @@ def main():
     ap.add_argument("--workload", default=None, help="one of %s, or 'all'; default: c2 as the headline + the other BASELINE configs under `configs`" % ", ".join(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="override frames per GPU of the headline workload")
     ap.add_argument("--single-process", action="store_true", help="drive all --gpus devices from this one process through icer_b200_*_batch_multi")
-    ap.add_argument("--e2e-workers", type=int, default=2)
+    ap.add_argument("--e2e-workers", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--watchdog", type=float, default=1500.0, help="dump every Python stack and exit if the run takes longer than this many seconds")

@@ -96,43 +96,85 @@ __device__ __forceinline__ uint32_t to_signmag16(uint32_t v) {          // icer_
     return s < 0 ? (uint32_t) ((-s) & (B8 ? 0x7F : 0x7FFF)) | 0x8000u : (uint32_t) s;
 }
 
-// K3: planar coefficients -> encoder slices.  Warp = (frame, slot): the lanes read the 32 window columns of their frame (one 64-byte
-// access), every field becomes a word with one ballot, and lane 0 stores it; the 32 frames of a group (the 32 warps of a block) fill
-// each 128-byte line of the slice buffer together (merged in L2).
+// 16 x 16 bit-matrix transpose, done in BOTH 16-bit halves of 16 registers at once: afterwards bit i of half h of r[p] is what
+// bit p of half h of r[i] was.  With r[i] = pixel i | pixel (i + 16) << 16 of a 32-pixel window this turns 16-bit samples into
+// bit planes (word p = bit p of the 32 pixels) and back -- the operation is its own inverse.
+template <int J>
+__device__ __forceinline__ void transpose_stage(uint32_t (&r)[16]) {
+    constexpr uint32_t m = J == 8 ? 0x00FF00FFu : (J == 4 ? 0x0F0F0F0Fu : (J == 2 ? 0x33333333u : 0x55555555u));
+#pragma unroll
+    for (int idx = 0; idx < 8; idx++) {
+        const int k = ((idx & ~(J - 1)) << 1) | (idx & (J - 1));       // the rows whose bit J is clear
+        const uint32_t t = ((r[k] >> J) ^ r[k + J]) & m;
+        r[k + J] ^= t;
+        r[k] ^= t << J;
+    }
+}
+__device__ __forceinline__ void transpose16x16_halves(uint32_t (&r)[16]) {
+    transpose_stage<8>(r); transpose_stage<4>(r); transpose_stage<2>(r); transpose_stage<1>(r);
+}
+
+// K3: planar coefficients -> encoder slices.  Warp = (group, slot), LANE = FRAME: a lane reads the 32 window samples of its frame
+// (17 aligned 32-bit words), turns them into bit planes with the register transpose above, derives the S_p words as running ORs and
+// stores every field as one coalesced 128-byte line of the slice buffer.
 template <int P>
-__global__ void __launch_bounds__(1024) k_bitslice(const uint16_t *__restrict__ coefs, uint32_t *__restrict__ bs, const SlotDesc *__restrict__ slots,
-                                                   uint32_t nslots, uint32_t nframes, uint32_t chan, uint32_t W, uint32_t H, int twos) {
-    const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;
+__global__ void __launch_bounds__(128) k_bitslice(const uint16_t *__restrict__ coefs, uint32_t *__restrict__ bs, const SlotDesc *__restrict__ slots,
+                                                  uint32_t nslots, uint32_t nframes, uint32_t chan, uint32_t W, uint32_t H, int twos) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t g = blockIdx.y;
-    const uint32_t frame = g * 32 + f;
+    const uint32_t frame = g * 32 + lane;
     constexpr int PS = P + 2 < 14 ? P + 2 : 14, F = P + PS + 1;
-    const bool writer = lane == 0;
     const size_t plane_px = (size_t) W * H;
-    const uint16_t *src = coefs + (size_t) frame * chan * plane_px - 1 + lane;
-    uint32_t *dstg = bs + (size_t) g * nslots * F * 32 + f;
-    for (uint32_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+    const long long total = (long long) nframes * chan * (long long) plane_px;       // samples in the buffer
+    const uint32_t *src32 = reinterpret_cast<const uint32_t *>(coefs);
+    uint32_t *dstg = bs + (size_t) g * nslots * F * 32 + lane;
+    for (uint32_t slot = blockIdx.x * 4 + warp; slot < nslots; slot += gridDim.x * 4) {
         const SlotDesc d = slots[slot];
         const uint32_t ch = (d.flags >> 2) & 3u;
-        const bool inwin = (lane >= 1 && lane <= (int) d.ncols) || (lane == 0 && (d.flags & 1)) || (lane == (int) d.ncols + 1 && (d.flags & 2));
-        uint32_t v = 0;
-        if (inwin && frame < nframes) v = src[ch * plane_px + (size_t) d.y * W + d.x0];
-        if (twos) v = to_signmag16<false>(v);
-        const uint32_t mag = v & 0x7FFFu;
+        uint32_t r[16];
+        if (frame < nframes) {
+            const long long e0 = ((long long) frame * chan + ch) * (long long) plane_px + (long long) d.y * W + d.x0 - 1;     // first window sample (may lie one before / after the buffer)
+            const long long w0 = e0 >> 1;
+            const uint32_t sh = (uint32_t) (e0 & 1) * 16u;
+            uint32_t w[17];
+#pragma unroll
+            for (int k = 0; k < 17; k++) {
+                const long long wi = w0 + k;
+                uint32_t v = 0;
+                if (wi >= 0 && 2 * wi + 1 < total) v = src32[wi];
+                else if (wi >= 0 && 2 * wi < total) v = coefs[2 * wi];
+                w[k] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                // window sample i -> low half, sample i + 16 -> high half
+                const uint32_t va = __funnelshift_r(w[i >> 1], w[(i >> 1) + 1], sh), vb = __funnelshift_r(w[(i >> 1) + 8], w[(i >> 1) + 9], sh);
+                r[i] = __byte_perm(va, vb, (i & 1) ? 0x7632 : 0x5410);
+            }
+            if (twos) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {        // two's complement -> sign-magnitude in both halves (icer_wavelet.c:871-877)
+                    const uint32_t sg = (r[i] >> 15) & 0x00010001u;
+                    const uint32_t t = (r[i] ^ (sg * 0xFFFFu)) + sg;
+                    r[i] = (t & 0x7FFF7FFFu) | (sg << 15);
+                }
+            }
+            transpose16x16_halves(r);              // r[p] = bit p of the 32 window samples (p = 15: the sign)
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) r[i] = 0;
+        }
+        // window columns that belong to the unit: 1..ncols, the left / right neighbour when it exists
+        uint32_t vmask = ((2u << d.ncols) - 2u) | ((d.flags & 1u) ? 1u : 0u) | ((d.flags & 2u) ? (2u << d.ncols) : 0u);
         uint32_t *dst = dstg + (size_t) slot * F * 32;
+        uint32_t sig = 0;
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            const uint32_t w = __ballot_sync(0xffffffffu, (mag & (1u << p)) != 0u);
-            if (writer) dst[p * 32] = w;
+        for (int p = 14; p >= 0; p--) {
+            sig |= r[p];                            // S_p = S_{p+1} | B_p
+            if (p < P) dst[p * 32] = r[p] & vmask;
+            if (p >= 1 && p <= PS) dst[(P + p - 1) * 32] = sig & vmask;
         }
-#pragma unroll
-        for (int p = 1; p <= PS; p++) {
-            const uint32_t w = __ballot_sync(0xffffffffu, mag >= (1u << p));
-            if (writer) dst[(P + p - 1) * 32] = w;
-        }
-        {
-            const uint32_t w = __ballot_sync(0xffffffffu, (v & 0x8000u) != 0u);
-            if (writer) dst[(P + PS) * 32] = w;
-        }
+        dst[(P + PS) * 32] = r[15] & vmask;
     }
 }
 
@@ -152,45 +194,46 @@ __global__ void __launch_bounds__(256) k_valid_planes(const uint8_t *__restrict_
     vp[i] = (uint8_t) v;
 }
 
-// K8: decoder slices -> planar coefficients.  Warp = (frame, slot), lane = window column.  Also undoes sign-magnitude
-// (icer_wavelet.c:880-886) and adds the header LL mean (icer_compress.c:520-531).
+// K8: decoder slices -> planar coefficients.  Warp = (group, slot), lane = frame: the lane loads its B words (coalesced), the register
+// transpose turns them back into 32 sign-magnitude samples, which are converted (icer_wavelet.c:880-886), get the header LL mean
+// (icer_compress.c:520-531) and are stored.
 template <int P>
-__global__ void __launch_bounds__(1024) k_unslice(const uint32_t *__restrict__ bs, uint16_t *__restrict__ dst, const SlotDesc *__restrict__ slots,
-                                                  const uint8_t *__restrict__ vpmap, const int32_t *__restrict__ frame_of,
-                                                  const uint16_t *__restrict__ mean, uint32_t nslots, uint32_t nunits, uint32_t chan, uint32_t W, uint32_t H,
-                                                  uint64_t cap_px, int llw, int llh, int bits8) {
-    const int lane = threadIdx.x & 31, f = threadIdx.x >> 5;
+__global__ void __launch_bounds__(128) k_unslice(const uint32_t *__restrict__ bs, uint16_t *__restrict__ dst, const SlotDesc *__restrict__ slots,
+                                                 const uint8_t *__restrict__ vpmap, const int32_t *__restrict__ frame_of,
+                                                 const uint16_t *__restrict__ mean, uint32_t nslots, uint32_t nunits, uint32_t chan, uint32_t W, uint32_t H,
+                                                 uint64_t cap_px, int llw, int llh, int bits8) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t g = blockIdx.y;
-    const int32_t frame = frame_of[g * 32 + f];
-    if (frame < 0) return;
+    const int32_t frame = frame_of[g * 32 + lane];
     constexpr int F = 3 * P;
-    const uint8_t *vpf = vpmap + (size_t) frame * nunits;
-    const uint32_t *srcg = bs + (size_t) g * nslots * F * 32 + f;
-    uint16_t *dstf = dst + (size_t) frame * chan * cap_px - 1 + lane;
-    for (uint32_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+    const uint32_t *srcg = bs + (size_t) g * nslots * F * 32 + lane;
+    for (uint32_t slot = blockIdx.x * 4 + warp; slot < nslots; slot += gridDim.x * 4) {
+        if (frame < 0) continue;
         const SlotDesc d = slots[slot];
-        const int vp = vpf[d.unit];
+        const int vp = vpmap[(size_t) frame * nunits + d.unit];
         const uint32_t *src = srcg + (size_t) slot * F * 32;
-        // every lane reads the same words (broadcast loads) and keeps its own column's bit
-        uint32_t mag = 0;
+        uint32_t r[16];
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            const uint32_t w = p >= vp ? src[p * 32] : 0u;
-            mag |= ((w >> lane) & 1u) << p;
-        }
-        const uint32_t wN = vp < P ? src[(2 * P + vp) * 32] : 0u;
-        if (lane < 1 || lane > (int) d.ncols) continue;
-        uint32_t v = mag ? (mag | (((wN >> lane) & 1u) << 15)) : 0u;
-        v = (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;                      // icer_wavelet.c:880-886
+        for (int p = 0; p < 15; p++) r[p] = (p < P && p >= vp) ? src[p * 32] : 0u;
+        r[15] = vp < P ? src[(2 * P + vp) * 32] : 0u;
+        transpose16x16_halves(r);                  // r[i] = sample i | sample (i + 16) << 16, sign-magnitude
         const uint32_t ch = (d.flags >> 2) & 3u;
-        const int x = (int) d.x0 - 1 + lane, y = (int) d.y;
-        if (y < llh && x < llw) {
-            const int m = (int) mean[(size_t) frame * chan + ch];
-            // uint16 API: int16 add (icer_compress.c:524-531); native uint8 API: int8 add of the header value's low byte (:258-265)
-            v = bits8 ? (uint32_t) (uint16_t) (int16_t) (int8_t) ((int) (int16_t) v + (int) (int8_t) m)
-                      : (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + (int) (int16_t) m);
+        const int m = (int) mean[(size_t) frame * chan + ch];
+        const int y = (int) d.y;
+        uint16_t *o = dst + ((size_t) frame * chan + ch) * cap_px + (size_t) y * W + d.x0 - 1;
+#pragma unroll
+        for (int c = 1; c <= ICER_CHUNK; c++) {
+            if (c > (int) d.ncols) break;
+            uint32_t v = (r[c & 15] >> ((c >> 4) * 16)) & 0xFFFFu;
+            if (!(v & 0x7FFFu)) v = 0;                                              // a sign without magnitude cannot occur; be safe
+            v = (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;                      // icer_wavelet.c:880-886
+            if (y < llh && (int) d.x0 - 1 + c < llw) {
+                // uint16 API: int16 add (icer_compress.c:524-531); native uint8 API: int8 add of the header value's low byte (:258-265)
+                v = bits8 ? (uint32_t) (uint16_t) (int16_t) (int8_t) ((int) (int16_t) v + (int) (int8_t) m)
+                          : (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + (int) (int16_t) m);
+            }
+            o[c] = (uint16_t) v;
         }
-        dstf[ch * cap_px + (size_t) y * W + d.x0] = (uint16_t) v;
     }
 }
 
@@ -674,20 +717,21 @@ uint32_t encode_resident_threads(int device) {
 }
 
 static unsigned slice_grid_x(uint32_t nslots, uint32_t ngroups) {
-    // 1024-thread blocks, two per SM: a few waves over all groups
-    unsigned gx = (unsigned) ((8u * 296u + ngroups - 1) / ngroups);
-    if (gx > nslots) gx = nslots;
+    // blocks of 4 warps (one slot per warp and iteration); a few waves of 148 SMs x 8 blocks over all groups
+    unsigned gx = (unsigned) ((8u * 1184u + ngroups - 1) / ngroups);
+    const unsigned need = (nslots + 3) / 4;
+    if (gx > need) gx = need;
     return gx < 1 ? 1 : gx;
 }
 
 template <int P> struct SliceLaunch {
     static void enc(dim3 grid, cudaStream_t st, const uint16_t *coefs, uint32_t *bs, const SlotDesc *slots, uint32_t nslots, uint32_t nframes,
                     uint32_t chan, uint32_t w, uint32_t h, int twos) {
-        k_bitslice<P><<<grid, 1024, 0, st>>>(coefs, bs, slots, nslots, nframes, chan, w, h, twos);
+        k_bitslice<P><<<grid, 128, 0, st>>>(coefs, bs, slots, nslots, nframes, chan, w, h, twos);
     }
     static void dec(dim3 grid, cudaStream_t st, const uint32_t *bs, uint16_t *frames, const SlotDesc *slots, const uint8_t *vp, const int32_t *frame_of,
                     const uint16_t *mean, uint32_t nslots, uint32_t nunits, uint32_t chan, uint32_t w, uint32_t h, uint64_t cap_px, int llw, int llh, int bits8) {
-        k_unslice<P><<<grid, 1024, 0, st>>>(bs, frames, slots, vp, frame_of, mean, nslots, nunits, chan, w, h, cap_px, llw, llh, bits8);
+        k_unslice<P><<<grid, 128, 0, st>>>(bs, frames, slots, vp, frame_of, mean, nslots, nunits, chan, w, h, cap_px, llw, llh, bits8);
     }
 };
 #define ICER_FOR_PLANES(P, CALL)                                                                                              \
