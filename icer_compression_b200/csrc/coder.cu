@@ -194,46 +194,60 @@ __global__ void __launch_bounds__(256) k_valid_planes(const uint8_t *__restrict_
     vp[i] = (uint8_t) v;
 }
 
-// K8: decoder slices -> planar coefficients.  Warp = (group, slot), lane = frame: the lane loads its B words (coalesced), the register
-// transpose turns them back into 32 sign-magnitude samples, which are converted (icer_wavelet.c:880-886), get the header LL mean
-// (icer_compress.c:520-531) and are stored.
+// K8: decoder slices -> planar coefficients.  Warp = (group, slot).  Load phase, lane = frame: the lane loads its B words (coalesced)
+// and the register transpose turns them back into 32 sign-magnitude samples.  Store phase, lane = window column: the samples cross a
+// shared-memory tile so that every store instruction writes the 60 contiguous bytes of ONE frame's row segment; on the way they
+// are converted (icer_wavelet.c:880-886) and get the header LL mean (icer_compress.c:520-531).
 template <int P>
 __global__ void __launch_bounds__(128) k_unslice(const uint32_t *__restrict__ bs, uint16_t *__restrict__ dst, const SlotDesc *__restrict__ slots,
                                                  const uint8_t *__restrict__ vpmap, const int32_t *__restrict__ frame_of,
                                                  const uint16_t *__restrict__ mean, uint32_t nslots, uint32_t nunits, uint32_t chan, uint32_t W, uint32_t H,
                                                  uint64_t cap_px, int llw, int llh, int bits8) {
+    __shared__ uint32_t tile_s[4][32][17];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t (*tile)[17] = tile_s[warp];
     const uint32_t g = blockIdx.y;
     const int32_t frame = frame_of[g * 32 + lane];
     constexpr int F = 3 * P;
     const uint32_t *srcg = bs + (size_t) g * nslots * F * 32 + lane;
     for (uint32_t slot = blockIdx.x * 4 + warp; slot < nslots; slot += gridDim.x * 4) {
-        if (frame < 0) continue;
         const SlotDesc d = slots[slot];
-        const int vp = vpmap[(size_t) frame * nunits + d.unit];
-        const uint32_t *src = srcg + (size_t) slot * F * 32;
-        uint32_t r[16];
-#pragma unroll
-        for (int p = 0; p < 15; p++) r[p] = (p < P && p >= vp) ? src[p * 32] : 0u;
-        r[15] = vp < P ? src[(2 * P + vp) * 32] : 0u;
-        transpose16x16_halves(r);                  // r[i] = sample i | sample (i + 16) << 16, sign-magnitude
         const uint32_t ch = (d.flags >> 2) & 3u;
-        const int m = (int) mean[(size_t) frame * chan + ch];
-        const int y = (int) d.y;
-        uint16_t *o = dst + ((size_t) frame * chan + ch) * cap_px + (size_t) y * W + d.x0 - 1;
+        {
+            uint32_t r[16];
+            if (frame >= 0) {
+                const int vp = vpmap[(size_t) frame * nunits + d.unit];
+                const uint32_t *src = srcg + (size_t) slot * F * 32;
 #pragma unroll
-        for (int c = 1; c <= ICER_CHUNK; c++) {
-            if (c > (int) d.ncols) break;
-            uint32_t v = (r[c & 15] >> ((c >> 4) * 16)) & 0xFFFFu;
+                for (int p = 0; p < 15; p++) r[p] = (p < P && p >= vp) ? src[p * 32] : 0u;
+                r[15] = vp < P ? src[(2 * P + vp) * 32] : 0u;
+                transpose16x16_halves(r);              // r[i] = sample i | sample (i + 16) << 16, sign-magnitude
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) r[i] = 0;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) tile[lane][i] = r[i];
+        }
+        __syncwarp();
+        const int y = (int) d.y, x = (int) d.x0 - 1 + lane;
+        const bool col_ok = lane >= 1 && lane <= (int) d.ncols;
+        const bool in_ll = y < llh && x < llw;
+        for (int f = 0; f < 32; f++) {
+            const int32_t fr = __shfl_sync(0xffffffffu, frame, f);
+            if (fr < 0 || !col_ok) continue;
+            uint32_t v = (tile[f][lane & 15] >> ((lane >> 4) * 16)) & 0xFFFFu;
             if (!(v & 0x7FFFu)) v = 0;                                              // a sign without magnitude cannot occur; be safe
             v = (v & 0x8000u) ? ((0x8000u - v) & 0xFFFFu) : v;                      // icer_wavelet.c:880-886
-            if (y < llh && (int) d.x0 - 1 + c < llw) {
+            if (in_ll) {
+                const int m = (int) mean[(size_t) fr * chan + ch];
                 // uint16 API: int16 add (icer_compress.c:524-531); native uint8 API: int8 add of the header value's low byte (:258-265)
                 v = bits8 ? (uint32_t) (uint16_t) (int16_t) (int8_t) ((int) (int16_t) v + (int) (int8_t) m)
                           : (uint32_t) (uint16_t) (int16_t) ((int) (int16_t) v + (int) (int16_t) m);
             }
-            o[c] = (uint16_t) v;
+            dst[((size_t) fr * chan + ch) * cap_px + (size_t) y * W + x] = (uint16_t) v;
         }
+        __syncwarp();
     }
 }
 
@@ -332,13 +346,13 @@ __global__ void __launch_bounds__(NT, ICER_ENC_MINBLOCKS) k_encode(EncodeArgs a)
 #define ICER_DEC_WARPS 32
 #endif
 #ifndef ICER_DEC_SLOTS
-#define ICER_DEC_SLOTS 12
+#define ICER_DEC_SLOTS 48
 #endif
 #ifndef ICER_DEC_MINBLOCKS
 #define ICER_DEC_MINBLOCKS 1
 #endif
 #ifndef ICER_DEC_BACKOFF_NS
-#define ICER_DEC_BACKOFF_NS 2000     /* sleep when the plane above is not far enough ahead */
+#define ICER_DEC_BACKOFF_NS 500      /* sleep when the plane above is not far enough ahead */
 #endif
 #ifndef ICER_DEC_SLACK
 #define ICER_DEC_SLACK 0            /* extra chunks a blocked plane lets the plane above get ahead before it continues */
