@@ -492,6 +492,74 @@ class Bench:
             os.sched_setaffinity(0, old_aff)
 
 
+def latency_section(args):
+    """BASELINE config 1 (ONE 512x512 image through the reference's own single-image calls, host buffers) and small batches of the
+    largest frames: what a caller without a big batch sees.  lane = frame needs 32 frames per warp; a single image runs with one lane
+    per warp and its latency is the longest stream's (lib_icer needs 84 + 95 ms for the same image on one core)."""
+    import statistics
+    import numpy as np
+    import torch
+    import icer_compression_b200 as icer
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness
+    out = {}
+    boat = harness.load_boat()
+    leg = icer.LegacyAPI()
+    enc_ms, dec_ms = [], []
+    stream = None
+    for k in range(8):
+        t0 = time.perf_counter()
+        r = leg.compress([boat], 6, 0, 10, 512 * 512)
+        t1 = time.perf_counter()
+        d = leg.decompress(r["stream"], 1, 512 * 512, 6, 0, 10)
+        t2 = time.perf_counter()
+        if k >= 2:
+            enc_ms.append((t1 - t0) * 1e3); dec_ms.append((t2 - t1) * 1e3)
+        stream = r["stream"]
+    c1 = {"workload": "single 512x512 uint8 grayscale (boat.512), 6 stages, 10 segments, 9 bit planes, icer_compress_image_uint16 / icer_decompress_image_uint16 "
+                      "with host buffers, wall clock incl. the Python wrapper's buffer copies, median of 6 calls",
+          "encode_ms": round(statistics.median(enc_ms), 3), "decode_ms": round(statistics.median(dec_ms), 3),
+          "lossless": bool(d["rc"] == 0 and (d["images"][0] == boat).all()), "stream_bytes": len(stream)}
+    if not args.no_cpu and harness.have_ref():
+        ref = harness.Ref()
+        t0 = time.perf_counter(); rr = ref.compress([boat], 6, 0, 10, 512 * 512); t1 = time.perf_counter()
+        ref.decompress(rr["stream"], 1, 512 * 512, 6, 0, 10); t2 = time.perf_counter()
+        c1["reference_encode_ms"] = round((t1 - t0) * 1e3, 3); c1["reference_decode_ms"] = round((t2 - t1) * 1e3, 3)
+        c1["same_stream_as_reference"] = bool(rr["stream"] == stream)
+    out["c1_single_image"] = c1
+    # small batches of config 4's frames, device-resident
+    wl = WORKLOADS["c4"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    w, h, quota = wl["w"], wl["h"], wl["quota"]
+    for nb in (8, 32):
+        ctx = icer.IcerB200(device=torch.cuda.current_device(), planes=wl["planes"], max_stages=wl["max_stages"])
+        st = torch.cuda.current_stream().cuda_stream
+        frames = torch.empty((nb, 1, h, w), dtype=torch.int16, device=dev)
+        ctx.synth_frames(frames, nb, w, h, 0, wl["seed"], wl["kind"], st)
+        o = torch.empty((nb, quota), dtype=torch.uint8, device=dev)
+        used = torch.zeros(nb, dtype=torch.int64, device=dev); rc = torch.zeros(nb, dtype=torch.int32, device=dev)
+        dec = torch.empty((nb, 1, h * w), dtype=torch.int16, device=dev)
+        dims = torch.zeros((nb, 2), dtype=torch.int32, device=dev); drc = torch.zeros(nb, dtype=torch.int32, device=dev)
+        params = (w, h, 1, wl["stages"], 0, wl["segments"], quota)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for k in range(2):
+            ev[0].record()
+            ctx.compress_batch_raw(params, frames, nb, o, quota, None, None, used, rc, icer.MEM_DEVICE)
+            ev[1].record()
+            ctx.decompress_batch_raw(params, o, quota, used, nb, dec, dims, drc, icer.MEM_DEVICE)
+            ev[2].record()
+            torch.cuda.synchronize()
+        e_ms, d_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        out["c4_batch%d" % nb] = {"workload": "batch=%d 4096x4096 12-bit-in-uint16, 7 stages, 15 bit planes, device-resident" % nb,
+                                  "encode_ms": round(e_ms, 2), "decode_ms": round(d_ms, 2),
+                                  "value": round(nb * w * h / ((e_ms + d_ms) * 1e-3) / 1e6, 2), "unit": "Mpixels/s",
+                                  "rc_ok": int(((rc == 0) | (rc == -5)).sum().item())}
+        del frames, o, dec
+        ctx.close()
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, names, rank, world, local_rank):
     b = Bench(args, rank, world, local_rank)
     head = dict(WORKLOADS[names[0]], **batch_override(args, names[0]))
@@ -505,6 +573,11 @@ def run_ours(args, names, rank, world, local_rank):
     if rank == 0:
         if rest:
             line["configs"] = rest
+        if args.workload in (None, "all") and world == 1 and not args.single_process:
+            try:
+                line["latency"] = latency_section(args)
+            except Exception as e:      # the headline must not depend on the extra measurements
+                line["latency"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if b.dist is not None:
         b.dist.destroy_process_group()

@@ -23,13 +23,6 @@ namespace {
 using icer_core::CoreTables;
 
 constexpr int NT = 128;   // threads per encoder block
-// Codewords that complete behind an older open one wait in the interleave window (lib_icer's 2048-slot circular buffer).  The
-// window of every resident thread lives in global memory (2048 x 2 B x ~150 k threads); most codewords, however, complete within
-// a few sequence numbers of the emission point: those are parked in a small per-thread shared-memory window instead and never
-// touch global memory.  Must be a power of two (0 = everything goes through the global ring).
-#ifndef ICER_ENC_MINI
-#define ICER_ENC_MINI 8
-#endif
 #ifndef ICER_ENC_MINBLOCKS
 #define ICER_ENC_MINBLOCKS 8
 #endif
@@ -259,7 +252,6 @@ struct EncSmem {
     uint32_t cnt[17][NT];      // cached bin << 27 | zero << 16 | total, per context
     uint16_t bseq[17][NT];     // sequence number (low 16 bits; the window spans 2048) of the codeword each bin is building
     uint16_t bst[17][NT];      // Golomb: zeros counted; variable-to-variable: input word (first bit = bit 0) | bits gathered << 8
-    uint16_t mini[ICER_ENC_MINI > 0 ? ICER_ENC_MINI : 1][NT];   // parked codewords close to the emission point
 };
 
 // One warp per (frame group, stream); lane = frame of the group.
@@ -289,7 +281,7 @@ __global__ void __launch_bounds__(NT, ICER_ENC_MINBLOCKS) k_encode(EncodeArgs a)
         const int lsb = (int) (s % a.planes);
         const uint32_t frame = g * 32 + lane;
         const bool valid = frame < a.nframes;
-        icer_core::EncLane<NT, ICER_ENC_MINI> ln(S.T, &S.cnt[0][t], &S.bseq[0][t], &S.bst[0][t], &S.mini[0][t], ring,
+        icer_core::EncLane<NT> ln(S.T, &S.cnt[0][t], &S.bseq[0][t], &S.bst[0][t], ring,
                                                  valid ? a.scratch + (size_t) frame * a.scratch_words + a.soff[s] : nullptr, valid ? a.scap[s] : 0);
         const int sw = u.w, sh = u.h, sb = u.subband, cw = (int) u.cw;
         // field offsets (in words) inside a slot; -1: the field is identically zero

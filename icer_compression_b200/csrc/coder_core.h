@@ -147,14 +147,13 @@ struct EncChunk {
     }
 };
 
-template <int STRIDE, int MINI>
+template <int STRIDE>
 struct EncLane {
     const CoreTables &T;
     uint32_t *cnt;      // [17] (stride STRIDE): cached bin << 27 | zero count << 16 | total count, per context
     uint16_t *bseq;     // [17] sequence number (low 16 bits; the window spans 2048) of the codeword each bin is building
     uint16_t *bst;      // [17] Golomb: zeros counted; variable-to-variable: input word (first bit = bit 0) | bits gathered << 8
-    uint16_t *mini;     // [MINI] parked codewords close to the emission point (see complete())
-    uint16_t *ring;     // [ICER_RING] parked codewords further away (global memory)
+    uint16_t *ring;     // [ICER_RING] the interleave window: codewords wait here for the older ones still open (global memory)
     uint32_t *out;
     uint32_t cap, nwords = 0;
     unsigned long long acc = 0;
@@ -162,7 +161,6 @@ struct EncLane {
     // Interleave-window bookkeeping.  A codeword gets a sequence number when its first bit arrives (lib_icer: a ring slot,
     // icer_encoding.c:59-67); `head` = first sequence number that is not complete; everything in [emit_pos, head) is ready.
     uint32_t head = 0, tail = 0, open_mask = 0;
-    uint32_t mini_mask = 0;       // which slots of `mini` hold a parked codeword
     uint32_t emit_pos = 0;
     int oldest = 0;
     bool overflow = false;
@@ -173,8 +171,8 @@ struct EncLane {
     int col = 1;        // 1..ncols; > ncols: chunk finished
     int phase = 0;      // 0: magnitude decision next, 1: sign decision of this pixel next
 
-    ICER_HD EncLane(const CoreTables &t, uint32_t *c, uint16_t *bs, uint16_t *st, uint16_t *mn, uint16_t *r, uint32_t *o, uint32_t cp)
-        : T(t), cnt(c), bseq(bs), bst(st), mini(mn), ring(r), out(o), cap(cp) {
+    ICER_HD EncLane(const CoreTables &t, uint32_t *c, uint16_t *bs, uint16_t *st, uint16_t *r, uint32_t *o, uint32_t cp)
+        : T(t), cnt(c), bseq(bs), bst(st), ring(r), out(o), cap(cp) {
         for (int k = 0; k < 17; k++) cnt[k * STRIDE] = ICER_CNT_INIT;
     }
 
@@ -189,14 +187,7 @@ struct EncLane {
     ICER_HD void complete(int bin, uint32_t code, uint32_t nb) {
         const uint32_t seq = bseq[bin * STRIDE];
         open_mask &= ~(1u << bin);
-        // a parked entry is live until emitted, and emit_pos only grows: every live entry of the small window has a sequence
-        // number in [emit_pos, emit_pos + MINI), so slot = seq mod MINI is unambiguous
-        if (MINI > 0 && ((seq - emit_pos) & 0xFFFFu) < (uint32_t) MINI) {
-            mini[(seq & (MINI - 1)) * STRIDE] = (uint16_t) ((nb << 11) | code);
-            mini_mask |= 1u << (seq & (MINI - 1));
-        } else {
-            ring[seq & (ICER_RING - 1)] = (uint16_t) ((nb << 11) | code);
-        }
+        ring[seq & (ICER_RING - 1)] = (uint16_t) ((nb << 11) | code);
         if (seq != (head & 0xFFFFu)) return;
         const uint32_t h1 = head + 1;
         uint32_t dist = tail - h1;                       // every other open codeword lies in [head + 1, tail)
@@ -211,10 +202,7 @@ struct EncLane {
     // pack one ready codeword into the payload, LSB first (icer_encoding.c:114-139)
     ICER_HD void pump() {
         if (emit_pos == head) return;
-        uint32_t v;
-        const uint32_t slot = emit_pos & (uint32_t) ((MINI > 0 ? MINI : 1) - 1);
-        if (MINI > 0 && ((mini_mask >> slot) & 1u)) { v = mini[slot * STRIDE]; mini_mask &= ~(1u << slot); }
-        else v = ring[emit_pos & (ICER_RING - 1)];
+        const uint32_t v = ring[emit_pos & (ICER_RING - 1)];
         emit_pos++;
         acc |= (unsigned long long) (v & 0x7FF) << nacc;
         nacc += (int) (v >> 11);

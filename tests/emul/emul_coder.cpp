@@ -41,10 +41,10 @@ extern "C" long emul_encode_segment_plane(const uint16_t *seg, size_t w, size_t 
                                           size_t max_bytes, uint32_t *steps_out) {
     ready();
     Seg s{seg, w, h, rowstride};
-    uint32_t cnt[17]; uint16_t bseq[17]; uint16_t bst[17]; uint16_t mini[8];
+    uint32_t cnt[17]; uint16_t bseq[17]; uint16_t bst[17];
     std::vector<uint16_t> ring(ICER_RING);
     std::vector<uint32_t> words(max_bytes / 4 + 2);
-    EncLane<1, 8> ln(g_enc, cnt, bseq, bst, mini, ring.data(), words.data(), (uint32_t) (max_bytes / 4));
+    EncLane<1> ln(g_enc, cnt, bseq, bst, ring.data(), words.data(), (uint32_t) (max_bytes / 4));
     const size_t cw = (w + ICER_CHUNK - 1) / ICER_CHUNK;
     uint32_t steps = 0;
     for (size_t r = 0; r < h; r++)
