@@ -6,6 +6,7 @@
 // Host-side work is limited to planning (plan.cu), the byte-stream scanner that locates CRC-valid segments
 // (lib_icer does this on the host too: icer_compress.c:443-459,:569-588) and buffer management.
 #include "common.h"
+#include <chrono>
 #include <algorithm>
 #include <string.h>
 #include <string>
@@ -97,6 +98,14 @@ int ensure_perms8(icer_b200_ctx *c, uint32_t w, uint32_t h, uint32_t stages) {
     return ICER_RESULT_OK;
 }
 
+// ICER_B200_TRACE=1: host timestamps (ms since the first call) at the synchronisation points of the batch calls, on stderr
+void trace(icer_b200_ctx *c, const char *what) {
+    static const bool on = getenv("ICER_B200_TRACE") != nullptr;
+    if (!on) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[trace] %p %-18s %10.3f\n", (void *) c, what, ms);
+}
 void ev_record(icer_b200_ctx *c, int i, cudaStream_t st) {
     if (!c->timing) return;
     if (!c->ev[i]) cudaEventCreate(&c->ev[i]);
@@ -364,7 +373,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
     }
 
     ev_record(c, 0, st);
-    float ms_dwt = 0, ms_enc = 0, ms_asm = 0;
+    float ms_dwt = 0, ms_enc = 0, ms_asm = 0; trace(c, "enc:enter");
     size_t done = 0;
     while (done < n) {
         // chunk size under the workspace budget: every per-frame buffer counts (coefs, tmp rounded up to 32-frame groups, tmp2
@@ -493,7 +502,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
             ea.list = list; ea.nlist = nlist;
             if ((e = launch_encode(ea, st, c->ls))) return e;
             CUDA_TRY(cudaMemcpyAsync(ovf, c->misc.as<int>() + 4, 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaStreamSynchronize(st)); trace(c, "enc:coded");
             return ICER_RESULT_OK;
         };
         static const bool no_prefix = getenv("ICER_B200_NO_PREFIX") != nullptr;
@@ -545,7 +554,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
         if (host) {
             CUDA_TRY(cudaMemcpyAsync(size_used + done, d_used, nb * 8, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaMemcpyAsync(rc + done, d_rc, nb * 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaStreamSynchronize(st)); trace(c, "enc:assembled");
             // only the used part of every slot travels back
             size_t maxlen = 0;
             for (size_t i = 0; i < nb; i++) maxlen = std::max<size_t>(maxlen, (size_t) size_used[done + i]);
@@ -558,7 +567,7 @@ static int compress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, const
                 if (len) CUDA_TRY(cudaMemcpyAsync(out + (done + i) * out_stride, d_out + i * out_stride, len, cudaMemcpyDeviceToHost, st));
                 if (len && out_prio) CUDA_TRY(cudaMemcpyAsync(out_prio + (done + i) * out_stride, d_prio + i * out_stride, len, cudaMemcpyDeviceToHost, st));
             }
-            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaStreamSynchronize(st)); trace(c, "enc:copied");
         }
         if (c->timing) {
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -686,7 +695,7 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         return decompress_host_pipelined(c, p, streams, stream_stride, stream_len, n, frames_any, pixfmt, dims, rc, st);
     const uint32_t chan = p->channels;
     const size_t cap_px = (size_t) p->width * p->height;
-    ev_record(c, 0, st);
+    ev_record(c, 0, st); trace(c, "dec:enter");
 
     // 1. the streams and their lengths on the device
     int e;
@@ -722,7 +731,7 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
     if ((e = launch_parse(pa, st, c->ls))) return e;
     std::vector<ParseInfo> info(n);
     CUDA_TRY(cudaMemcpyAsync(info.data(), c->pinfo.p, n * sizeof(ParseInfo), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(st)); trace(c, "dec:parsed");
     // frames with more candidates than the device path holds are scanned on the host (never seen with real streams)
     std::map<size_t, Parsed> host_parsed;
     for (size_t i = 0; i < n; i++) {
@@ -905,6 +914,7 @@ static int decompress_batch_any(icer_b200_ctx *c, const icer_b200_params *p, con
         if (dims) CUDA_TRY(cudaMemcpyAsync(dims, hdims.data(), n * 8, cudaMemcpyHostToDevice, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));   // host vectors above must outlive the copies
+    trace(c, "dec:done");
     if (c->timing) {
         ev_record(c, 4, st);
         CUDA_TRY(cudaStreamSynchronize(st));
