@@ -44,6 +44,8 @@ WORKLOADS = {
                batch=1024, w=512, h=512, chan=1, stages=6, segments=10, planes=9, max_stages=6, quota=512 * 512, kind=0, seed=20260922 + 2),
     "c2noise": dict(desc="batch=1024 512x512 uint8 noise in uint16 gray, 6 stages, 10 segments, 9 bit planes, filter A, quota=2*W*H",
                     batch=1024, w=512, h=512, chan=1, stages=6, segments=10, planes=9, max_stages=6, quota=2 * 512 * 512, kind=1, seed=20260922 + 2),
+    "c2filtB": dict(desc="batch=1024 512x512 uint8-in-uint16 gray, 6 stages, 10 segments, 9 bit planes, filter B, quota=W*H",
+                    batch=1024, w=512, h=512, chan=1, stages=6, segments=10, planes=9, max_stages=6, quota=512 * 512, kind=0, seed=20260922 + 2, filt=1),
     "c3": dict(desc="batch=1024 512x512 YUV planar uint16, 4 stages, 10 segments, 9 bit planes, filter A, quota=70000 B",
                batch=1024, w=512, h=512, chan=3, stages=4, segments=10, planes=9, max_stages=6, quota=70000, kind=0, seed=20260922 + 3),
     "c4": dict(desc="batch=256 4096x4096 12-bit-in-uint16 gray, 7 stages, 10 segments, 15 bit planes, filter A, quota=2*W*H",
@@ -164,9 +166,9 @@ def _cpu_worker(args):
     out = []
     for f, im in zip(frames_idx, imgs):
         t0 = time.perf_counter()
-        enc = ref.compress(im, wl["stages"], 0, wl["segments"], wl["quota"])
+        enc = ref.compress(im, wl["stages"], wl.get("filt", 0), wl["segments"], wl["quota"])
         t1 = time.perf_counter()
-        dec = ref.decompress(enc["stream"], wl["chan"], wl["w"] * wl["h"], wl["stages"], 0, wl["segments"])
+        dec = ref.decompress(enc["stream"], wl["chan"], wl["w"] * wl["h"], wl["stages"], wl.get("filt", 0), wl["segments"])
         t2 = time.perf_counter()
         t_enc += t1 - t0; t_dec += t2 - t1
         out.append((f, enc["rc"], enc["stream"], dec["rc"], b"".join(i.tobytes() for i in dec["images"]) if dec["images"] is not None else None))
@@ -279,7 +281,7 @@ class Bench:
         G = len(self.devices)
         n_gpu, w, h, chan, quota = wl["batch"], wl["w"], wl["h"], wl["chan"], wl["quota"]
         n = n_gpu * G                                   # frames this process codes per step
-        params = (w, h, chan, wl["stages"], 0, wl["segments"], quota)
+        params = (w, h, chan, wl["stages"], wl.get("filt", 0), wl["segments"], quota)
         multi = icer.IcerMulti(self.devices, planes=wl["planes"], max_stages=wl["max_stages"])
         ctx = multi.ctxs[0]
         dev = self.dev

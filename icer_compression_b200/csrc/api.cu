@@ -143,6 +143,12 @@ int icer_b200_create(icer_b200_ctx **out, int device) {
     { const char *pc = getenv("ICER_B200_PIPE_CHUNK"); if (pc) c->pipe_chunk = (size_t) atol(pc); }
     { const char *bc = getenv("ICER_B200_BULK_COPY"); if (bc) c->bulk_copy = atoi(bc) != 0; }
     { const char *fp = getenv("ICER_B200_FORCE_PREFIX"); if (fp) c->force_prefix = (uint32_t) atoi(fp); }
+    {   // encoder workspace per chunk: 55 % of the device memory by default (a B200 has 180 GB: a batch of 256 frames of 4096^2 -- ~300 MB of
+        // planes, bit slices and payload scratch each -- then runs as ONE chunk; two chunks would pay the coder's serial tail twice)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) c->workspace_budget = (size_t) ((double) total_b * 0.55);
+        else (void) cudaGetLastError();
+    }
     const char *gb = getenv("ICER_B200_WORKSPACE_GB");
     if (gb && atof(gb) > 0) c->workspace_budget = (size_t) (atof(gb) * (double) ((size_t) 1 << 30));
     *out = c;

@@ -269,12 +269,21 @@ __global__ void __launch_bounds__(NT, ICER_ENC_MINBLOCKS) k_encode(EncodeArgs a)
     const int lane = t & 31;
     uint16_t *ring = a.rings + (size_t) (blockIdx.x * NT + t) * ICER_RING;
 
+    // Work items in stream-major order: the largest streams of ALL groups first, so the tail of the kernel consists of small
+    // streams.  The FIRST item of every warp is dealt round-robin over the blocks (item i -> block i mod gridDim.x): neighbouring
+    // items are the bit planes of one segment -- dense low planes, nearly empty high planes -- and an SM that started with 32 dense
+    // planes of the largest segments would still be running when the rest of the chip has gone idle (4096^2 frames: 1.7 s instead
+    // of 0.9 s).  After that the warps fetch dynamically.
+    const unsigned long long dealt = (unsigned long long) gridDim.x * (NT / 32);
+    bool first = true;
     for (;;) {
         unsigned long long wid = 0;
-        if (lane == 0) wid = atomicAdd(a.work_counter, 1ull);
-        wid = __shfl_sync(0xffffffffu, wid, 0);
+        if (first) { wid = (unsigned long long) blockIdx.x + (unsigned long long) (t >> 5) * gridDim.x; first = false; }
+        else {
+            if (lane == 0) wid = atomicAdd(a.work_counter, 1ull) + dealt;
+            wid = __shfl_sync(0xffffffffu, wid, 0);
+        }
         if (wid >= total) break;
-        // stream-major order: the largest streams of ALL groups first, so the tail of the kernel consists of small streams
         const uint32_t g = (uint32_t) (wid % a.ngroups);
         const uint32_t s = a.list ? a.list[wid / a.ngroups] : (uint32_t) (wid / a.ngroups);
         const Unit u = a.units[s / a.planes];
@@ -296,11 +305,12 @@ __global__ void __launch_bounds__(NT, ICER_ENC_MINBLOCKS) k_encode(EncodeArgs a)
                 const int ncols = sw - j * ICER_CHUNK < ICER_CHUNK ? sw - j * ICER_CHUNK : ICER_CHUNK;
                 icer_core::EncChunk k;
                 {
+                    // the slice words are used once per stream: they bypass L1 (ld.global.cg), which is left to the codeword ring
                     const uint32_t *pa = p - row_words, *pc = p + row_words;
-                    const uint32_t bP = oP >= 0 ? p[oP] : 0u, bB = p[oB], bN = p[oN];
-                    const uint32_t b2 = o2 >= 0 ? p[o2] : 0u, b3 = o3 >= 0 ? p[o3] : 0u;
-                    const uint32_t aP = (up && oP >= 0) ? pa[oP] : 0u, aB = up ? pa[oB] : 0u, aN = up ? pa[oN] : 0u;
-                    const uint32_t cP = (dn && oP >= 0) ? pc[oP] : 0u, cN = dn ? pc[oN] : 0u;
+                    const uint32_t bP = oP >= 0 ? __ldcg(p + oP) : 0u, bB = __ldcg(p + oB), bN = __ldcg(p + oN);
+                    const uint32_t b2 = o2 >= 0 ? __ldcg(p + o2) : 0u, b3 = o3 >= 0 ? __ldcg(p + o3) : 0u;
+                    const uint32_t aP = (up && oP >= 0) ? __ldcg(pa + oP) : 0u, aB = up ? __ldcg(pa + oB) : 0u, aN = up ? __ldcg(pa + oN) : 0u;
+                    const uint32_t cP = (dn && oP >= 0) ? __ldcg(pc + oP) : 0u, cN = dn ? __ldcg(pc + oN) : 0u;
                     k.set(aP, aB, aN, bP, bB, bN, b2, b3, cP, cN, ncols);
                 }
                 ln.begin_chunk();
@@ -500,12 +510,14 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
                 const int ncols = sw - jc * ICER_CHUNK < ICER_CHUNK ? sw - jc * ICER_CHUNK : ICER_CHUNK;
                 icer_core::DecChunk kc;
                 {
+                    // slice words come from L2 (ld.global.cg): written by another warp of this block (the plane above) or by this
+                    // warp a row earlier, and used once
                     const uint32_t *pa = p - row_words, *pc = p + row_words;
-                    const uint32_t bP = oP >= 0 ? p[oP] : 0u, bNp = oNp >= 0 ? p[oNp] : 0u;
-                    const uint32_t b2 = o2 >= 0 ? p[o2] : 0u, b3 = o3 >= 0 ? p[o3] : 0u;
-                    const uint32_t cP = (dn && oP >= 0) ? pc[oP] : 0u, cN = (dn && oNp >= 0) ? pc[oNp] : 0u;
+                    const uint32_t bP = oP >= 0 ? __ldcg(p + oP) : 0u, bNp = oNp >= 0 ? __ldcg(p + oNp) : 0u;
+                    const uint32_t b2 = o2 >= 0 ? __ldcg(p + o2) : 0u, b3 = o3 >= 0 ? __ldcg(p + o3) : 0u;
+                    const uint32_t cP = (dn && oP >= 0) ? __ldcg(pc + oP) : 0u, cN = (dn && oNp >= 0) ? __ldcg(pc + oNp) : 0u;
                     // row above: this plane's own words
-                    const uint32_t aS = up ? pa[oS] : 0u, aN = up ? pa[oN] : 0u;
+                    const uint32_t aS = up ? __ldcg(pa + oS) : 0u, aN = up ? __ldcg(pa + oN) : 0u;
                     kc.set(aS, aN, bP, bNp, b2, b3, cP, cN, carryB, carryN, ncols);
                 }
                 ln.begin_chunk();

@@ -42,27 +42,38 @@ __device__ __forceinline__ void pair_ld(int a, int b, bool last_odd, int &lo, in
 
 // high output of pair k.  lm2, lm1, l0, lp1 = stored lows l[k-2], l[k-1], l[k], l[k+1]; d0 = unwrapped difference of pair k;
 // dp1 = stored (int16) difference of pair k+1.  Returns the stored high; ORs the overflow condition of the reference into ovf.
-__device__ __forceinline__ int lift_high(const Filt &F, int n, int k, int lm2, int lm1, int l0, int lp1, int d0, int dp1, bool &ovf) {
-    const int nl = (n + 1) >> 1, nh = n >> 1;
-    const bool odd = n & 1;
-    ovf |= d0 > 32767 || d0 < -32768;
+// INTERIOR: the caller guarantees 2 <= k < nh - 1 (and k + 1 < nl - 1), so none of the edge rules applies; F is a compile-time
+// filter (the multiplications fold into shifts and the unused taps disappear).
+__device__ __forceinline__ bool out_of_i16(int v) { return (unsigned) (v + 32768) > 65535u; }
+template <bool INTERIOR, typename FT>
+__device__ __forceinline__ int lift_high(const FT &F, int n, int k, int lm2, int lm1, int l0, int lp1, int d0, int dp1, bool &ovf) {
+    ovf |= out_of_i16(d0);
     const int dk = (int) (int16_t) d0;
     const int rk = (int) (int16_t) (lm1 - l0), rk1 = (int) (int16_t) (l0 - lp1);       // r[k], r[k+1] (get_r_int16 :206-208)
     int sub;
-    if (k == 0) sub = rk1 >> 2;
-    else if (k == 1 && F.f0 != 0) {                                                       // filter C quirk :436-440
-        const int x = (odd && nl - 1 == 2) ? 0 : dk;
-        sub = (2 * rk + 3 * rk1 - 2 * x + 4) >> 3;
-    } else if (!odd && k == nh - 1) sub = rk >> 2;
-    else {
-        const int rm1 = (F.f0 != 0) ? ((k - 1 > 0) ? (int) (int16_t) (lm2 - lm1) : 1) : 0;
-        const int dn = (odd && k + 1 == nl - 1) ? 0 : dp1;
-        sub = (F.f0 * rm1 + F.f1 * rk + F.f2 * rk1 - F.f3 * dn + 8) >> 4;
+    if (INTERIOR) {
+        const int rm1 = (F.f0 != 0) ? (int) (int16_t) (lm2 - lm1) : 0;
+        sub = (F.f0 * rm1 + F.f1 * rk + F.f2 * rk1 - F.f3 * dp1 + 8) >> 4;
+    } else {
+        const int nl = (n + 1) >> 1, nh = n >> 1;
+        const bool odd = n & 1;
+        if (k == 0) sub = rk1 >> 2;
+        else if (k == 1 && F.f0 != 0) {                                                       // filter C quirk :436-440
+            const int x = (odd && nl - 1 == 2) ? 0 : dk;
+            sub = (2 * rk + 3 * rk1 - 2 * x + 4) >> 3;
+        } else if (!odd && k == nh - 1) sub = rk >> 2;
+        else {
+            const int rm1 = (F.f0 != 0) ? ((k - 1 > 0) ? (int) (int16_t) (lm2 - lm1) : 1) : 0;
+            const int dn = (odd && k + 1 == nl - 1) ? 0 : dp1;
+            sub = (F.f0 * rm1 + F.f1 * rk + F.f2 * rk1 - F.f3 * dn + 8) >> 4;
+        }
     }
     const int hv = dk - sub;
-    ovf |= hv > 32767 || hv < -32768;
+    ovf |= out_of_i16(hv);
     return (int) (int16_t) hv;
 }
+// the same with the filter as compile-time constants: filter A (0, 4, 4, 0) is the default of every tool and benchmark
+struct FiltA { static constexpr int f0 = 0, f1 = 4, f2 = 4, f3 = 0; };
 
 struct StageArgs {
     int lw, lh, W;                 // region size, frame row stride (samples)
@@ -73,6 +84,80 @@ struct StageArgs {
     int *ovf;                      // per plane
 };
 
+// ---- row pass: one warp per tile row, lane = pair.  Each lane reads its two samples with ONE 32-bit load; three lanes also
+// evaluate the halo pairs k0-2, k0-1 and k0+TK; all neighbours then come from shuffles.
+template <bool INTERIOR, typename FT>
+__device__ __forceinline__ void fwd_row_pass(const FT &F, const int16_t (*in)[IN_W], int16_t (*rowl)[TK], int16_t (*rowh)[TK], int lw, int lh,
+                                             int k0, int y0, int lane, int warp, bool &ovf) {
+    const int nhx = lw >> 1;
+    const int k = k0 + lane;
+    const int ek = lane == 0 ? k0 - 2 : (lane == 1 ? k0 - 1 : k0 + TK);      // the halo pair of lanes 0, 1, 2
+    for (int yy = warp; yy < IN_H; yy += 8) {
+        const int gy = y0 + yy;
+        if (gy < 0 || gy >= lh) { rowl[yy][lane] = 0; rowh[yy][lane] = 0; continue; }    // warp-uniform; outside the region
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(&in[yy][0]);
+        const uint32_t v = rw[(HALO_X >> 1) + lane];
+        int l0, d0;
+        pair_ld((int) (int16_t) (v & 0xFFFF), (int) (int16_t) (v >> 16), !INTERIOR && (lw & 1) && k == nhx, l0, d0);
+        int le = 0, de = 0;
+        if (lane < 3) {
+            const uint32_t u = rw[(HALO_X >> 1) + (ek - k0)];
+            pair_ld((int) (int16_t) (u & 0xFFFF), (int) (int16_t) (u >> 16), !INTERIOR && (lw & 1) && ek == nhx, le, de);
+        }
+        const int lm2h = __shfl_sync(0xffffffffu, le, 0), lm1h = __shfl_sync(0xffffffffu, le, 1);
+        const int lph = __shfl_sync(0xffffffffu, le, 2), dph = __shfl_sync(0xffffffffu, de, 2);
+        int lm1 = __shfl_up_sync(0xffffffffu, l0, 1), lm2 = __shfl_up_sync(0xffffffffu, l0, 2);
+        int lp1 = __shfl_down_sync(0xffffffffu, l0, 1), dp1 = __shfl_down_sync(0xffffffffu, d0, 1);
+        if (lane == 0) { lm1 = lm1h; lm2 = lm2h; }
+        if (lane == 1) lm2 = lm1h;
+        if (lane == 31) { lp1 = lph; dp1 = dph; }
+        int hi = 0;
+        if (INTERIOR || k < nhx) hi = lift_high<INTERIOR>(F, lw, k, lm2, lm1, l0, lp1, d0, (int) (int16_t) dp1, ovf);
+        rowl[yy][lane] = (int16_t) l0;      // only read back for k < nlx
+        rowh[yy][lane] = (int16_t) hi;
+    }
+}
+
+// ---- column pass: warp = (half, strip of 8 output rows), lane = column; a thread walks down its column with the lows / differences
+// of four consecutive vertical pairs in registers
+template <bool INTERIOR, typename FT>
+__device__ __forceinline__ void fwd_col_pass(const FT &F, const int16_t (*rowl)[TK], const int16_t (*rowh)[TK], const StageArgs &a, int k0, int r0, int y0,
+                                             int plane, int lane, int warp, bool &ovf) {
+    const int nlx = (a.lw + 1) >> 1, nhx = a.lw >> 1, nly = (a.lh + 1) >> 1, nhy = a.lh >> 1;
+    const int half = warp & 1, strip = warp >> 1;
+    const int k = k0 + lane;
+    const bool col_ok = half == 0 ? k < nlx : k < nhx;
+    const int16_t (*col)[TK] = half == 0 ? rowl : rowh;
+    int16_t *hi_p = a.hi_dst + (size_t) plane * a.plane_stride;
+    int16_t *ll_p = a.ll_dst + (size_t) plane * a.plane_stride;
+    const int xo = half == 0 ? k : nlx + k;
+    const int rs = r0 + strip * 8;
+    if (!(col_ok && (INTERIOR || rs < nly))) return;
+    auto ld_pair = [&](int r, int &lo, int &d) {
+        // pairs outside [0, nly) are never used by lift_high (its edge rules only read in-range pairs)
+        const int yi = 2 * r - y0;
+        if (!INTERIOR && (r < 0 || r >= nly)) { lo = 0; d = 0; return; }
+        pair_ld((int) col[yi][lane], (int) col[yi + 1][lane], !INTERIOR && (a.lh & 1) && r == nhy, lo, d);
+    };
+    int lm2, lm1, l0, lp1, dm, d0, dp1;
+    ld_pair(rs - 2, lm2, dm);
+    ld_pair(rs - 1, lm1, dm);
+    ld_pair(rs, l0, d0);
+    int16_t *dst_lo = (half == 0 ? ll_p : hi_p) + (size_t) rs * a.W + xo;                       // LL  /  HL
+    int16_t *dst_hi = hi_p + (size_t) (nly + rs) * a.W + xo;                                    // LH  /  HH
+#pragma unroll
+    for (int i = 0; i < 8; i++, dst_lo += a.W, dst_hi += a.W) {
+        const int r = rs + i;
+        ld_pair(r + 1, lp1, dp1);
+        if (INTERIOR || r < nly) {
+            *dst_lo = (int16_t) l0;
+            if (INTERIOR || r < nhy) *dst_hi = (int16_t) lift_high<INTERIOR>(F, a.lh, r, lm2, lm1, l0, lp1, d0, (int) (int16_t) dp1, ovf);
+        }
+        lm2 = lm1; lm1 = l0; l0 = lp1; d0 = dp1;
+    }
+}
+
+template <bool FA>
 __global__ void __launch_bounds__(256) k_fwd_stage_tma(const __grid_constant__ CUtensorMap tmap, StageArgs a) {
     __shared__ __align__(128) int16_t in[IN_H][IN_W];          // TMA destination
     __shared__ __align__(16) int16_t rowl[IN_H][TK], rowh[IN_H][TK];   // row-pass result of every tile row
@@ -100,76 +185,27 @@ __global__ void __launch_bounds__(256) k_fwd_stage_tma(const __grid_constant__ C
     }
     Filt F;
     F.f0 = c_filt2[a.filt][0]; F.f1 = c_filt2[a.filt][1]; F.f2 = c_filt2[a.filt][2]; F.f3 = c_filt2[a.filt][3];
+    const FiltA FAc;
     bool ovf = false;
-    const int nlx = (a.lw + 1) >> 1, nhx = a.lw >> 1, nly = (a.lh + 1) >> 1, nhy = a.lh >> 1;
-    // ---- row pass: one warp per tile row, lane = pair.  Each lane reads its two samples with ONE 32-bit load; three lanes
-    // also evaluate the halo pairs k0-2, k0-1 and k0+TK; all neighbours then come from shuffles. -----------------------------
-    {
-        const int k = k0 + lane;
-        const int ek = lane == 0 ? k0 - 2 : (lane == 1 ? k0 - 1 : k0 + TK);      // the halo pair of lanes 0, 1, 2
-        for (int yy = warp; yy < IN_H; yy += 8) {
-            const int gy = y0 + yy;
-            if (gy < 0 || gy >= a.lh) { rowl[yy][lane] = 0; rowh[yy][lane] = 0; continue; }    // warp-uniform; outside the region
-            const uint32_t *rw = reinterpret_cast<const uint32_t *>(&in[yy][0]);
-            const uint32_t v = rw[(HALO_X >> 1) + lane];
-            int l0, d0;
-            pair_ld((int) (int16_t) (v & 0xFFFF), (int) (int16_t) (v >> 16), (a.lw & 1) && k == nhx, l0, d0);
-            int le = 0, de = 0;
-            if (lane < 3) {
-                const uint32_t u = rw[(HALO_X >> 1) + (ek - k0)];
-                pair_ld((int) (int16_t) (u & 0xFFFF), (int) (int16_t) (u >> 16), (a.lw & 1) && ek == nhx, le, de);
-            }
-            const int lm2h = __shfl_sync(0xffffffffu, le, 0), lm1h = __shfl_sync(0xffffffffu, le, 1);
-            const int lph = __shfl_sync(0xffffffffu, le, 2), dph = __shfl_sync(0xffffffffu, de, 2);
-            int lm1 = __shfl_up_sync(0xffffffffu, l0, 1), lm2 = __shfl_up_sync(0xffffffffu, l0, 2);
-            int lp1 = __shfl_down_sync(0xffffffffu, l0, 1), dp1 = __shfl_down_sync(0xffffffffu, d0, 1);
-            if (lane == 0) { lm1 = lm1h; lm2 = lm2h; }
-            if (lane == 1) lm2 = lm1h;
-            if (lane == 31) { lp1 = lph; dp1 = dph; }
-            int hi = 0;
-            if (k < nhx) hi = lift_high(F, a.lw, k, lm2, lm1, l0, lp1, d0, (int) (int16_t) dp1, ovf);
-            rowl[yy][lane] = (int16_t) l0;      // only read back for k < nlx
-            rowh[yy][lane] = (int16_t) hi;
-        }
+    const int nhx = a.lw >> 1, nhy = a.lh >> 1;
+    // a tile none of whose pairs meets an edge rule of the lifting step (first two / last pair of a line, the odd tail) takes the
+    // branch-free interior form of the predictor: 6 of 8 tile columns / rows of a 512-wide region
+    const bool int_x = k0 >= 2 && k0 + TK - 1 <= nhx - 2;
+    const bool int_y = r0 >= 2 && r0 + TR - 1 <= nhy - 2;
+    if (FA) {
+        if (int_x) fwd_row_pass<true>(FAc, in, rowl, rowh, a.lw, a.lh, k0, y0, lane, warp, ovf);
+        else fwd_row_pass<false>(FAc, in, rowl, rowh, a.lw, a.lh, k0, y0, lane, warp, ovf);
+    } else {
+        if (int_x) fwd_row_pass<true>(F, in, rowl, rowh, a.lw, a.lh, k0, y0, lane, warp, ovf);
+        else fwd_row_pass<false>(F, in, rowl, rowh, a.lw, a.lh, k0, y0, lane, warp, ovf);
     }
     __syncthreads();
-    // ---- column pass: warp = (half, strip of 8 output rows), lane = column; a thread walks down its column with the lows /
-    // differences of four consecutive vertical pairs in registers ---------------------------------------------------------------
-    {
-        const int half = warp & 1, strip = warp >> 1;
-        const int k = k0 + lane;
-        const bool col_ok = half == 0 ? k < nlx : k < nhx;
-        const int16_t (*col)[TK] = half == 0 ? rowl : rowh;
-        int16_t *hi_p = a.hi_dst + (size_t) plane * a.plane_stride;
-        int16_t *ll_p = a.ll_dst + (size_t) plane * a.plane_stride;
-        const int xo = half == 0 ? k : nlx + k;
-        const int rs = r0 + strip * 8;
-        if (col_ok && rs < nly) {
-            auto ld_pair = [&](int r, int &lo, int &d) {
-                // pairs outside [0, nly) are never used by lift_high (its edge rules only read in-range pairs)
-                const int yi = 2 * r - y0;
-                if (r < 0 || r >= nly) { lo = 0; d = 0; return; }
-                pair_ld((int) col[yi][lane], (int) col[yi + 1][lane], (a.lh & 1) && r == nhy, lo, d);
-            };
-            int lm2, lm1, l0, lp1, dm, d0, dp1;
-            ld_pair(rs - 2, lm2, dm);
-            ld_pair(rs - 1, lm1, dm);
-            ld_pair(rs, l0, d0);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int r = rs + i;
-                ld_pair(r + 1, lp1, dp1);
-                if (r < nly) {
-                    int16_t *dst_lo = half == 0 ? ll_p : hi_p;                       // LL  /  HL
-                    dst_lo[(size_t) r * a.W + xo] = (int16_t) l0;
-                    if (r < nhy) {
-                        const int hi = lift_high(F, a.lh, r, lm2, lm1, l0, lp1, d0, (int) (int16_t) dp1, ovf);
-                        hi_p[(size_t) (nly + r) * a.W + xo] = (int16_t) hi;          // LH  /  HH
-                    }
-                }
-                lm2 = lm1; lm1 = l0; l0 = lp1; d0 = dp1;
-            }
-        }
+    if (FA) {
+        if (int_y) fwd_col_pass<true>(FAc, rowl, rowh, a, k0, r0, y0, plane, lane, warp, ovf);
+        else fwd_col_pass<false>(FAc, rowl, rowh, a, k0, r0, y0, plane, lane, warp, ovf);
+    } else {
+        if (int_y) fwd_col_pass<true>(F, rowl, rowh, a, k0, r0, y0, plane, lane, warp, ovf);
+        else fwd_col_pass<false>(F, rowl, rowh, a, k0, r0, y0, plane, lane, warp, ovf);
     }
     if (ovf) atomicOr(&a.ovf[plane], 1);
 }
@@ -378,7 +414,8 @@ int launch_dwt_forward_fused(const uint16_t *src, size_t src_plane_stride, uint1
             a.ll_dst = reinterpret_cast<int16_t *>(ll) + p0 * ps;
             a.filt = (int) filt; a.ovf = d_ovf + p0;
             dim3 grid(((lw + 1) / 2 + TK - 1) / TK, ((lh + 1) / 2 + TR - 1) / TR, (unsigned) cnt);
-            k_fwd_stage_tma<<<grid, 256, 0, st>>>(tm, a);
+            if (filt == ICER_FILTER_A) k_fwd_stage_tma<true><<<grid, 256, 0, st>>>(tm, a);
+            else k_fwd_stage_tma<false><<<grid, 256, 0, st>>>(tm, a);
             ls.launches++;
         }
         cur = ll; cur_stride = ps;
