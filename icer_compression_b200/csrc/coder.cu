@@ -313,6 +313,12 @@ __global__ void __launch_bounds__(NT, ICER_ENC_MINBLOCKS) k_encode(EncodeArgs a)
                     const uint32_t cP = (dn && oP >= 0) ? __ldcg(pc + oP) : 0u, cN = dn ? __ldcg(pc + oN) : 0u;
                     k.set(aP, aB, aN, bP, bB, bN, b2, b3, cP, cN, ncols);
                 }
+                // a chunk that is quiet in every frame of the group and lies inside every lane's current run of (context 0, bit 0)
+                // decisions is absorbed without a single step (the empty upper planes consist of little else)
+                if (__all_sync(0xffffffffu, ln.fz_left >= (uint32_t) ncols && (k.nq & ((2u << ncols) - 2u)) == 0u)) {
+                    ln.fz_run += (uint32_t) ncols; ln.fz_left -= (uint32_t) ncols;
+                    continue;
+                }
                 ln.begin_chunk();
                 for (;;) {
                     const bool busy = !ln.chunk_done(ncols);
@@ -520,12 +526,18 @@ __global__ void __launch_bounds__(DEC_BT, ICER_DEC_MINBLOCKS) k_decode(DecodeArg
                     const uint32_t aS = up ? __ldcg(pa + oS) : 0u, aN = up ? __ldcg(pa + oN) : 0u;
                     kc.set(aS, aN, bP, bNp, b2, b3, cP, cN, carryB, carryN, ncols);
                 }
-                ln.begin_chunk();
-                for (;;) {
-                    const bool busy = !ln.chunk_done(ncols);
-                    const unsigned lanes = __ballot_sync(0xffffffffu, busy);
-                    if (!lanes) break;
-                    if (busy) ln.step(kc, sb, lanes);
+                // a chunk that is quiet in every frame and inside every lane's pending run of zeros needs no step (see k_encode)
+                const bool absorbed = __all_sync(0xffffffffu, !ln.run || (ln.fz_left >= (uint32_t) ncols && ((kc.nq | (kc.bB << 1)) & ((2u << ncols) - 2u)) == 0u));
+                if (absorbed) {
+                    if (ln.run) { ln.fz_run += (uint32_t) ncols; ln.fz_left -= (uint32_t) ncols; }
+                } else {
+                    ln.begin_chunk();
+                    for (;;) {
+                        const bool busy = !ln.chunk_done(ncols);
+                        const unsigned lanes = __ballot_sync(0xffffffffu, busy);
+                        if (!lanes) break;
+                        if (busy) ln.step(kc, sb, lanes);
+                    }
                 }
                 // this chunk's words; the right halo of the chunk before is patched now that this chunk's first column is known
                 p[oB] = kc.bB;

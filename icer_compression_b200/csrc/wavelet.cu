@@ -156,6 +156,66 @@ __global__ void __launch_bounds__(128) k_inv_pass_ser(const int16_t *__restrict_
     }
 }
 
+// ---- the same recurrence for the uint16 codec with a sliding window of lows in registers (two loads per restored pair instead of
+// eight) and, for the ROW pass, the restored samples collected in a shared-memory tile so that they leave as whole row segments (a
+// thread per row otherwise stores 2 bytes into 32 different sectors per instruction).  Used for filters B..Q (beta != 0). ----------
+template <bool COL, bool CLAMP>
+__global__ void __launch_bounds__(64) k_inv_pass_ser2(const int16_t *__restrict__ src, int16_t *__restrict__ dst, int n, int nlines, int W,
+                                                     size_t plane_stride, int filt, int plane0, int tile_stride /* samples, row pass only */) {
+    extern __shared__ __align__(16) int16_t tile[];          // row pass: [64][tile_stride]
+    const int line0 = blockIdx.x * 64, line = line0 + threadIdx.x;
+    const int plane = plane0 + blockIdx.z;
+    const int nl = (n + 1) >> 1, nh = n >> 1;
+    const bool odd = n & 1;
+    const bool live = line < nlines;
+    const int16_t *s = src + (size_t) plane * plane_stride + (COL ? (size_t) line : (size_t) line * W);
+    const size_t es = COL ? (size_t) W : 1;
+    int16_t *d = dst + (size_t) plane * plane_stride + (COL ? (size_t) line : (size_t) line * W);
+    int16_t *trow = tile + (size_t) threadIdx.x * tile_stride;
+    auto put = [&](int pos, int v) {
+        if (CLAMP && v < 0) v = 0;
+        if (COL) d[(size_t) pos * es] = (int16_t) v; else trow[pos] = (int16_t) v;
+    };
+    if (live) {
+        const int f0 = c_filt[filt][0], f1 = c_filt[filt][1], f2 = c_filt[filt][2], f3 = c_filt[filt][3];
+        auto L = [&](int j) -> int { return (j >= 0 && j < nl) ? (int) s[(size_t) j * es] : 0; };
+        if (odd) put(n - 1, L(nl - 1));
+        int lk1 = L(nh), lk = L(nh - 1), lkm1 = L(nh - 2), lkm2 = L(nh - 3);      // l[k+1], l[k], l[k-1], l[k-2] for k = nh - 1
+        int dnext = 0;
+        for (int k = nh - 1; k >= 0; k--) {
+            const int hk = (int) s[(size_t) (nl + k) * es];
+            const int rk = (int) (int16_t) (lkm1 - lk), rk1 = (int) (int16_t) (lk - lk1);       // R(k), R(k+1)
+            int add;
+            if (k == 0) add = rk1 >> 2;
+            else if (k == 1 && f0 != 0) {
+                const int x = (odd && nl - 1 == 2) ? 0 : hk;              // still the un-restored h[1] (:488-492)
+                add = (2 * rk + 3 * rk1 - 2 * x + 4) >> 3;
+            } else if (!odd && k == nh - 1) add = rk >> 2;
+            else {
+                const int rm1 = (f0 != 0) ? ((k - 1 > 0) ? (int) (int16_t) (lkm2 - lkm1) : 1) : 0;
+                const int dn = (odd && k + 1 == nl - 1) ? 0 : dnext;
+                add = (f0 * rm1 + f1 * rk + f2 * rk1 - f3 * dn + 8) >> 4;
+            }
+            const int dk = (int) (int16_t) (hk + add);
+            dnext = dk;
+            const int t = lk + ((dk + 1) >> 1);
+            put(2 * k, (int) (int16_t) t);
+            put(2 * k + 1, (int) (int16_t) (t - dk));
+            lk1 = lk; lk = lkm1; lkm1 = lkm2; lkm2 = L(k - 3);
+        }
+    }
+    if (!COL) {
+        __syncthreads();
+        // 64 rows x n samples leave as row segments: consecutive threads write consecutive samples of one row
+        const int rows = nlines - line0 < 64 ? nlines - line0 : 64;
+        for (int r = 0; r < rows; r++) {
+            int16_t *o = dst + (size_t) plane * plane_stride + (size_t) (line0 + r) * W;
+            const int16_t *tr = tile + (size_t) r * tile_stride;
+            for (int c = threadIdx.x; c < n; c += 64) o[c] = tr[c];
+        }
+    }
+}
+
 // ---- K3: LL mean (unsigned sum, icer_compress.c:289-302), subtract on LL, then sign-magnitude everywhere ----
 template <bool B8>
 __global__ void __launch_bounds__(256) k_ll_mean(uint16_t *__restrict__ planes, size_t plane_stride, int W, int llw,
@@ -257,6 +317,20 @@ void inverse_stage(int16_t *A, int16_t *B, int p0, unsigned cnt, uint32_t lw, ui
         dim3 g2(((lw + 1) / 2 + 63) / 64, (lh + 3) / 4, cnt);
         if (clamp) k_inv_pass_par<false, true, B8><<<g2, blk, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, perm_row);
         else k_inv_pass_par<false, false, B8><<<g2, blk, 0, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, perm_row);
+    } else if (!B8 && (size_t) 64 * ((((lw + 1) / 2) | 1) * 2) * 2 <= 200 * 1024) {
+        // uint16 codec: sliding-window recurrence; the row pass stages its output rows in shared memory (odd word stride: no bank conflicts)
+        dim3 g1((lw + 63) / 64, 1, cnt);
+        k_inv_pass_ser2<true, false><<<g1, 64, 0, st>>>(A, B, (int) lh, (int) lw, (int) w, ps, (int) filt, p0, 0);
+        const int ts = (int) ((((lw + 1) / 2) | 1) * 2);               // samples per tile row: an odd number of 32-bit words (>= lw)
+        const size_t smem = (size_t) 64 * ts * 2;
+        dim3 g2((lh + 63) / 64, 1, cnt);
+        if (clamp) {
+            cudaFuncSetAttribute(k_inv_pass_ser2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            k_inv_pass_ser2<false, true><<<g2, 64, smem, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, ts);
+        } else {
+            cudaFuncSetAttribute(k_inv_pass_ser2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            k_inv_pass_ser2<false, false><<<g2, 64, smem, st>>>(B, A, (int) lw, (int) lh, (int) w, ps, (int) filt, p0, ts);
+        }
     } else {
         dim3 g1((lw + 127) / 128, 1, cnt);
         k_inv_pass_ser<true, false, B8><<<g1, 128, 0, st>>>(A, B, (int) lh, (int) lw, (int) w, ps, (int) filt, p0, perm_col);

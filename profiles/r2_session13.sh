@@ -1,15 +1,15 @@
 #!/bin/bash
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 1500 python -m pytest tests -m gpu -q -rfEx --timeout 300 -x > $OUT/r2_s13_pytest.log 2>&1
-echo "pytest rc=$?" >> $OUT/r2_s13_pytest.log
-tail -4 $OUT/r2_s13_pytest.log
-for wl in c2 c2filtB c4; do
-    timeout 300 python bench.py --workload $wl --no-cpu --no-e2e --steps 3 --warmup 2 --watchdog 280 > $OUT/r2_s13_$wl.json 2>$OUT/r2_s13_$wl.err
+timeout 1500 python -m pytest tests -m gpu -q -rfEx --timeout 300 -x > $OUT/r2_s14_pytest.log 2>&1
+echo "pytest rc=$?" >> $OUT/r2_s14_pytest.log
+tail -4 $OUT/r2_s14_pytest.log
+for wl in c2 c2filtB c3 c5; do
+    timeout 300 python bench.py --workload $wl --no-cpu --no-e2e --steps 3 --warmup 2 --watchdog 280 > $OUT/r2_s14_$wl.json 2>$OUT/r2_s14_$wl.err
     python - <<PY
 import json
 try:
-    d=json.load(open("$OUT/r2_s13_$wl.json"))
+    d=json.load(open("$OUT/r2_s14_$wl.json"))
     r=d["roofline"]; o=d["roofline_other"]
     ke = r["kernel_ms"] if r["kernel"].startswith("k_encode") else o["kernel_ms"]
     kd = r["kernel_ms"] if r["kernel"].startswith("k_decode") else o["kernel_ms"]
@@ -17,4 +17,4 @@ try:
 except Exception as e: print("$wl failed", e)
 PY
 done
-bash profiles/r2_kernlist.sh r2_s13 c2
+
