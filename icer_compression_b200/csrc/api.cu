@@ -63,6 +63,8 @@ struct icer_b200_ctx {
     DevBuf p_in[2], p_out[2], p_used[2], p_rc[2], p_dims[2];
 };
 
+int ctx_device(const icer_b200_ctx *c) { return c->device; }
+
 namespace {
 
 Plan *get_plan(icer_b200_ctx *c, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages, uint32_t segments, bool native8 = false) {

@@ -84,6 +84,8 @@ static inline size_t dim_high(size_t d, unsigned s) { return dim_low(d, s - 1) /
 int partition_rects(size_t w, size_t h, int segments, int *xs, int *ys, int *ws, int *hs, partition_param_typdef *pp);
 uint32_t host_crc32(const uint8_t *buf, size_t len);
 
+int ctx_device(const icer_b200_ctx *c);      // api.cu
+
 // ---- kernel launchers (wavelet.cu / wavelet_tma.cu / coder.cu) -------------------------------------------
 struct LaunchStats { uint64_t launches = 0; };
 

@@ -38,8 +38,8 @@ __global__ void k_synth(uint16_t *dst, size_t n, uint32_t w, uint32_t h, uint32_
 
 extern "C" int icer_b200_synth_frames_u16(icer_b200_ctx *ctx, uint16_t *dst_device, size_t n, uint32_t w, uint32_t h,
                                           uint32_t first_frame, uint32_t seed, int kind, void *stream) {
-    (void) ctx;
     if (!dst_device || n == 0) return ICER_INVALID_INPUT;
+    if (ctx) CUDA_TRY(cudaSetDevice(ctx_device(ctx)));       // the stream belongs to the context's device (a process may hold several)
     k_synth<<<(unsigned) ((n + 31) / 32), 32, 0, (cudaStream_t) stream>>>(dst_device, n, w, h, first_frame, seed, kind);
     CUDA_TRY(cudaGetLastError());
     return ICER_RESULT_OK;
