@@ -32,6 +32,11 @@ struct DevTables {
     uint32_t crc[256];
 };
 __constant__ DevTables c_tab;
+// CRC-32 of the 24 header bytes without a serial loop: the register update is affine over GF(2), so
+//     crc = ~(K ^ XOR_i P[i][byte_i])        with P[i][b] = A^(23-i)(tab[b]),  A(r) = tab[r & 0xFF] ^ (r >> 8),  K = A^24(0xFFFFFFFF)
+// -- one table look-up per byte position (24 lanes) and a warp XOR reduction.  Global memory: the index differs in every lane.
+__device__ uint32_t g_hdr_crc_pos[24][256];
+__device__ uint32_t g_hdr_crc_k;
 // __constant__ memory has one instance PER DEVICE: the upload is tracked per device ordinal (a process may hold contexts on
 // several GPUs, e.g. icer_b200_*_batch_multi)
 std::mutex g_tab_mu;
@@ -53,6 +58,20 @@ int upload_tables() {
         d.crc[n] = c;
     }
     CUDA_TRY(cudaMemcpyToSymbol(c_tab, &d, sizeof d));      // synchronous: complete before any later launch on any stream
+    {
+        static uint32_t pos[24][256];
+        auto A = [&](uint32_t r) { return d.crc[r & 0xFF] ^ (r >> 8); };
+        for (int i = 0; i < 24; i++)
+            for (uint32_t b = 0; b < 256; b++) {
+                uint32_t r = d.crc[b];
+                for (int k = 0; k < 23 - i; k++) r = A(r);
+                pos[i][b] = r;
+            }
+        uint32_t kk = 0xFFFFFFFFu;
+        for (int k = 0; k < 24; k++) kk = A(kk);
+        CUDA_TRY(cudaMemcpyToSymbol(g_hdr_crc_pos, pos, sizeof pos));
+        CUDA_TRY(cudaMemcpyToSymbol(g_hdr_crc_k, &kk, sizeof kk));
+    }
     g_tables_uploaded[dev] = true;
     return ICER_RESULT_OK;
 }
@@ -705,28 +724,26 @@ __global__ void __launch_bounds__(256) k_gather(AssembleArgs a) {
     const uint32_t nbytes = (nb + 7) >> 3;
     const Unit u = a.units[s / a.planes];
     const uint32_t lsb = s % a.planes;
-    __shared__ uint8_t hdr_s[8][ICER_HDR_BYTES + 4];
-    uint8_t *hdr = hdr_s[threadIdx.x >> 5];
-    if (lane == 0) {
-        const uint32_t mean = a.mean[(size_t) f * a.chan + u.chan] & 0xFF;    // passes through a uint8_t (icer.h:270)
-        hdr[0] = 0x5B; hdr[1] = 0x60; hdr[2] = (uint8_t) mean; hdr[3] = 0;
-        hdr[4] = u.level; hdr[5] = u.subband; hdr[6] = u.seg; hdr[7] = (uint8_t) (lsb | (u.chan << 4));
-        const uint32_t w = a.w, h = a.h, dc = a.crc[(size_t) f * a.nstreams + s];
-        for (int i = 0; i < 4; i++) {
-            hdr[8 + i] = (uint8_t) (w >> (8 * i)); hdr[12 + i] = (uint8_t) (h >> (8 * i));
-            hdr[16 + i] = (uint8_t) (nb >> (8 * i)); hdr[20 + i] = (uint8_t) (dc >> (8 * i));
-        }
-        const uint32_t hc = crc_bytes(hdr, 24);
-        for (int i = 0; i < 4; i++) hdr[24 + i] = (uint8_t) (hc >> (8 * i));
-    }
-    __syncwarp();
+    // every lane builds the header word its byte lives in (lane = byte index), the CRC of bytes 0..23 comes from the position tables
+    const uint32_t mean = a.mean[(size_t) f * a.chan + u.chan] & 0xFF;    // passes through a uint8_t (icer.h:270)
+    const uint32_t dc = a.crc[(size_t) f * a.nstreams + s];
+    const int wi = lane >> 2;
+    uint32_t word = wi == 0 ? (0x5Bu | (0x60u << 8) | (mean << 16))
+                  : wi == 1 ? ((uint32_t) u.level | ((uint32_t) u.subband << 8) | ((uint32_t) u.seg << 16) | ((lsb | ((uint32_t) u.chan << 4)) << 24))
+                  : wi == 2 ? a.w : wi == 3 ? a.h : wi == 4 ? nb : wi == 5 ? dc : 0u;
+    uint32_t hb = (word >> (8 * (lane & 3))) & 0xFFu;
+    uint32_t x = lane < 24 ? g_hdr_crc_pos[lane][hb] : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x ^= __shfl_xor_sync(0xffffffffu, x, d);
+    const uint32_t hc = ~(x ^ g_hdr_crc_k);
+    if (wi == 6) hb = (hc >> (8 * (lane & 3))) & 0xFFu;
     const uint8_t *pay = reinterpret_cast<const uint8_t *>(a.scratch + (size_t) f * a.scratch_words + a.soff[s]);
     uint8_t *dst = a.out + (size_t) f * a.out_stride + orr;
-    if (lane < ICER_HDR_BYTES) dst[lane] = hdr[lane];
+    if (lane < ICER_HDR_BYTES) dst[lane] = (uint8_t) hb;
     for (uint32_t i = lane; i < nbytes; i += 32) dst[ICER_HDR_BYTES + i] = pay[i];
     if (a.out_prio) {
         uint8_t *d2 = a.out_prio + (size_t) f * a.out_stride + opr;
-        if (lane < ICER_HDR_BYTES) d2[lane] = hdr[lane];
+        if (lane < ICER_HDR_BYTES) d2[lane] = (uint8_t) hb;
         for (uint32_t i = lane; i < nbytes; i += 32) d2[ICER_HDR_BYTES + i] = pay[i];
     }
 }

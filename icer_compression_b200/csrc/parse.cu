@@ -21,6 +21,9 @@
 namespace {
 
 __constant__ uint32_t c_crc[256];
+// CRC-32 of a 24-byte header by position tables (see coder.cu g_hdr_crc_pos): crc = ~(K ^ XOR_i P[i][byte_i])
+__device__ uint32_t g_pos_crc[24][256];
+__device__ uint32_t g_pos_crc_k;
 std::mutex g_crc_mu;
 bool g_crc_uploaded[64] = {false};       // per device: __constant__ memory has one instance per GPU
 
@@ -37,38 +40,82 @@ int upload_crc() {
         tab[n] = c;
     }
     CUDA_TRY(cudaMemcpyToSymbol(c_crc, tab, sizeof tab));
+    {
+        static uint32_t pos[24][256];
+        auto A = [&](uint32_t r) { return tab[r & 0xFF] ^ (r >> 8); };
+        for (int i = 0; i < 24; i++)
+            for (uint32_t b = 0; b < 256; b++) {
+                uint32_t r = tab[b];
+                for (int k = 0; k < 23 - i; k++) r = A(r);
+                pos[i][b] = r;
+            }
+        uint32_t kk = 0xFFFFFFFFu;
+        for (int k = 0; k < 24; k++) kk = A(kk);
+        CUDA_TRY(cudaMemcpyToSymbol(g_pos_crc, pos, sizeof pos));
+        CUDA_TRY(cudaMemcpyToSymbol(g_pos_crc_k, &kk, sizeof kk));
+    }
     g_crc_uploaded[dev] = true;
     return ICER_RESULT_OK;
 }
 
 __device__ __forceinline__ uint32_t ld32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t) p[3] << 24); }
 
+__device__ __forceinline__ uint32_t byte_at(const uint8_t *s, uint64_t len, long long o) { return (o >= 0 && (uint64_t) o < len) ? s[o] : 0u; }
+
+// A thread tests 16 byte offsets for the preamble (four aligned 32-bit words + one for the look-ahead, a SWAR test for "some byte is
+// 0x5B" per word).  The hits of a warp are then checked ONE AFTER THE OTHER BY THE WHOLE WARP: 24 lanes take one header byte each, the
+// position tables and an XOR reduction give the header CRC -- a candidate costs ~20 warp instructions instead of a 24-step serial CRC
+// in a single lane (which was most of this kernel).
 __global__ void __launch_bounds__(256) k_scan(ParseArgs a) {
-    __shared__ uint32_t crc[256];
-    crc[threadIdx.x] = c_crc[threadIdx.x];
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
     const uint32_t frame = blockIdx.y;
     const uint64_t len = a.lens[frame] < a.stride ? a.lens[frame] : a.stride;
     const uint8_t *s = a.streams + (size_t) frame * a.stride;
-    const uint64_t o0 = ((uint64_t) blockIdx.x * 256 + threadIdx.x) * 8;
-    if (o0 >= len) return;
-    uint8_t b[9];
+    const int mis = (int) ((uintptr_t) s & 3);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s - mis);          // aligned view; word j covers stream offsets 4j - mis .. 4j - mis + 3
+    const uint64_t wj = ((uint64_t) blockIdx.x * 256 + threadIdx.x) * 4;       // this thread's four words
+    const long long o0 = (long long) wj * 4 - mis;                             // stream offset of this thread's first byte
+    uint32_t hits = 0;                                                          // bit i: a preamble starts at o0 + i and a header fits behind it
+    if (o0 < (long long) len) {
+        uint32_t w[5];
 #pragma unroll
-    for (int k = 0; k < 9; k++) b[k] = (o0 + k < len) ? s[o0 + k] : 0;
+        for (int k = 0; k < 5; k++) {
+            const long long o = o0 + 4 * k;
+            if (o >= 0 && (uint64_t) o + 4 <= len) w[k] = sw[wj + k];
+            else w[k] = byte_at(s, len, o) | (byte_at(s, len, o + 1) << 8) | (byte_at(s, len, o + 2) << 16) | (byte_at(s, len, o + 3) << 24);
+        }
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        if (b[k] != 0x5B || b[k + 1] != 0x60) continue;
-        const uint64_t o = o0 + k;
-        if (len - o < ICER_HDR_BYTES) continue;
-        const uint8_t *h = s + o;
-        uint32_t c = 0xFFFFFFFFu;
-        for (int i = 0; i < 24; i++) c = crc[(c ^ h[i]) & 0xFF] ^ (c >> 8);
-        if (~c != ld32(h + 24)) continue;
-        const uint32_t nbits = ld32(h + 16);
-        const uint64_t nbytes = ((uint64_t) nbits + 7) >> 3;
-        if (nbytes > len - o - ICER_HDR_BYTES) continue;
-        const uint32_t slot = atomicAdd(&a.ncand[frame], 1u);
-        if (slot < a.cap) a.cand[(size_t) frame * a.cap + slot] = make_uint2((uint32_t) o, (uint32_t) nbytes);
+        for (int k = 0; k < 4; k++) {
+            const uint32_t t = w[k] ^ 0x5B5B5B5Bu;
+            if (((t - 0x01010101u) & ~t & 0x80808080u) == 0u) continue;       // no byte of this word is 0x5B
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const long long o = o0 + 4 * k + b;
+                if ((__funnelshift_r(w[k], w[k + 1], 8 * b) & 0xFFFFu) == 0x605Bu && o >= 0 && (uint64_t) o + ICER_HDR_BYTES <= len) hits |= 1u << (4 * k + b);
+            }
+        }
+    }
+    for (;;) {
+        const uint32_t who = __ballot_sync(0xffffffffu, hits != 0u);
+        if (!who) break;
+        const int src = __ffs((int) who) - 1;
+        const uint32_t hm = __shfl_sync(0xffffffffu, hits, src);
+        const int pos = __ffs((int) hm) - 1;
+        const long long ob = __shfl_sync(0xffffffffu, o0, src);
+        if (lane == src) hits &= hits - 1;
+        const uint8_t *h = s + (ob + pos);
+        uint32_t x = lane < 24 ? g_pos_crc[lane][h[lane]] : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x ^= __shfl_xor_sync(0xffffffffu, x, d);
+        if (lane == 0 && ~(x ^ g_pos_crc_k) == ld32(h + 24)) {
+            const uint64_t o = (uint64_t) (ob + pos);
+            const uint32_t nbits = ld32(h + 16);
+            const uint64_t nbytes = ((uint64_t) nbits + 7) >> 3;
+            if (nbytes <= len - o - ICER_HDR_BYTES) {
+                const uint32_t slot = atomicAdd(&a.ncand[frame], 1u);
+                if (slot < a.cap) a.cand[(size_t) frame * a.cap + slot] = make_uint2((uint32_t) o, (uint32_t) nbytes);
+            }
+        }
     }
 }
 
@@ -198,7 +245,7 @@ int launch_parse(const ParseArgs &a, cudaStream_t st, LaunchStats &ls) {
         ParseArgs b = a;
         const uint32_t cnt = a.n - f0 < 32768 ? a.n - f0 : 32768;
         b.streams += (size_t) f0 * a.stride; b.lens += f0; b.cand += (size_t) f0 * a.cap; b.ncand += f0; b.info += f0; b.n = cnt;
-        dim3 g1((unsigned) ((a.stride + 256 * 8 - 1) / (256 * 8)), cnt);
+        dim3 g1((unsigned) ((a.stride + 3 + 256 * 16 - 1) / (256 * 16)), cnt);      // 16 byte offsets per thread (+3: the aligned view may start up to 3 bytes early)
         k_scan<<<g1, 256, 0, st>>>(b);
         dim3 g2((a.cap + 127) / 128, cnt);
         k_verify<<<g2, 128, 0, st>>>(b);
