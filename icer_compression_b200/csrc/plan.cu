@@ -98,6 +98,9 @@ int build_plan(Plan &pl, uint32_t w, uint32_t h, uint32_t chan, uint32_t stages,
     pl.status = ICER_RESULT_OK; pl.enc_status = ICER_RESULT_OK;
     pl.units.clear(); pl.slots.clear(); pl.nslots = 0; pl.prio_order.clear(); pl.rearr_order.clear(); pl.unit_of.clear();
     pl.nstreams = 0; pl.scratch_words = 0;
+    // lib_icer keeps the partition geometry in 16-bit fields (icer.h:293-312): larger planes are undefined there, refused here (the
+    // bit-slice slot descriptors use 16-bit coordinates as well)
+    if (w > 65535u || h > 65535u) { pl.status = ICER_INVALID_INPUT; return pl.status; }
     if (stages < 1 || stages > max_stages) { pl.status = ICER_TOO_MANY_STAGES; return pl.status; }
     if (dim_low(w, stages) < 3 || dim_low(h, stages) < 3) { pl.status = ICER_TOO_MANY_STAGES; return pl.status; }
 
