@@ -440,8 +440,11 @@ class Bench:
         torch, icer = self.torch, self.icer
         n, chan, h, w = frames.shape
         quota = wl["quota"]
-        big = n * chan * h * w * 2 > (3 << 30)
+        frame_bytes = n * chan * h * w * 2
+        big = frame_bytes > (3 << 30)
         nworkers = 1 if (big or len(self.devices) > 1 or self.args.e2e_workers < 2) else min(self.args.e2e_workers, 4)
+        if nworkers > 2 and frame_bytes > (3 << 29):
+            nworkers = 2            # every worker pins its own output buffers: keep the pinned host memory of an 8-rank job bounded
         old_aff = os.sched_getaffinity(0)
         cpus = gpu_numa_cpus(self.devices[0]) if len(self.devices) == 1 else None
         if cpus:

@@ -22,7 +22,10 @@ namespace {
 
 using icer_core::CoreTables;
 
-constexpr int NT = 128;   // threads per encoder block
+#ifndef ICER_ENC_NT
+#define ICER_ENC_NT 128
+#endif
+constexpr int NT = ICER_ENC_NT;   // threads per encoder block
 #ifndef ICER_ENC_MINBLOCKS
 #define ICER_ENC_MINBLOCKS 8
 #endif
@@ -702,12 +705,6 @@ __global__ void __launch_bounds__(128) k_quota_scan(AssembleArgs a) {
         // priority-prefix encoding: the walk reached the first stream the encoder has not produced yet -> code more, walk again
         if (kept >= a.limit && a.limit < a.nstreams && (rc == ICER_RESULT_OK || rc == ICER_BYTE_QUOTA_EXCEEDED)) atomicOr(&a.stat[1], 1u);
     }
-}
-
-__device__ __forceinline__ uint32_t crc_bytes(const uint8_t *p, int n) {
-    uint32_t c = 0xFFFFFFFFu;
-    for (int i = 0; i < n; i++) c = c_tab.crc[(c ^ p[i]) & 0xFF] ^ (c >> 8);
-    return ~c;
 }
 
 // One warp per (frame, stream): builds the 28-byte header (icer_encoding.c:210-234, icer_partition.c:328-332)
