@@ -95,7 +95,7 @@ int launch_dwt_forward(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t
 int launch_dwt_inverse(uint16_t *planes, uint16_t *tmp, size_t nplanes, uint32_t w, uint32_t h, uint32_t stages,
                        uint32_t filt, bool clamp_negative, cudaStream_t st, LaunchStats &ls, bool bits8 = false,
                        const std::map<uint32_t, const uint32_t *> *perms = nullptr);
-// LL mean removal + sign-magnitude (encode); the decode-side inverse is fused into launch_T_to_frames
+// LL mean removal + sign-magnitude (encode; skip_signmag: the bit-slice kernel applies the mapping instead); the decode-side inverse is fused into launch_unslice
 int launch_ll_mean_signmag(uint16_t *planes, size_t nplanes, uint32_t w, uint32_t h, uint32_t llw, uint32_t llh,
                            uint16_t *d_mean, int *d_ovf, cudaStream_t st, LaunchStats &ls, bool bits8 = false, bool skip_signmag = false);
 
