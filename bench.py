@@ -385,6 +385,8 @@ class Bench:
         e2e = None
         if e2e_steps > 0:
             e2e = self.run_e2e(name, wl, multi, frames, params, e2e_steps, px_step)
+            if isinstance(e2e, dict) and "error" in e2e:
+                sys.stderr.write("[bench] e2e of %s failed: %s\n" % (name, e2e["error"]))
         multi.close()
 
         peak, peak_src = measured_peak_gbs()
@@ -576,7 +578,12 @@ def run_ours(args, names, rank, world, local_rank):
     rest = []
     for nm in names[1:]:
         wl = WORKLOADS[nm]
-        r = b.run(nm, wl, max(1, min(args.steps, 3)), max(1, min(args.warmup, 3)), 0 if args.no_e2e else 2, not args.no_cpu)
+        try:
+            r = b.run(nm, wl, max(1, min(args.steps, 3)), max(1, min(args.warmup, 3)), 0 if args.no_e2e else 2, not args.no_cpu)
+        except Exception as e:       # the headline line must not be lost to a failure of an additional configuration
+            if b.dist is not None:
+                raise                # ranks have to stay in step: a multi-rank job fails as a whole
+            r = {"error": repr(e)}
         r["name"] = nm
         rest.append(r)
     if rank == 0:
