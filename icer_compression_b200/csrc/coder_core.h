@@ -36,6 +36,12 @@
 #ifndef ICER_RING
 #define ICER_RING 2048
 #endif
+#ifndef ICER_BIN_PROBE
+#define ICER_BIN_PROBE 1          /* one probe of the neighbouring bin before the full search: k_encode 19.4 -> 18.6, k_decode 18.6 -> 18.0 ms */
+#endif
+#ifndef ICER_INLINE_FLUSH
+#define ICER_INLINE_FLUSH 0
+#endif
 #define ICER_CHUNK 30          /* pixels per bit-slice word */
 
 namespace icer_core {
@@ -77,8 +83,9 @@ struct CoreTables {
                                      // decoder: keyed by the NEXT 5 stream bits: codeword length | out_bits << 4 | out << 8
     uint16_t gol_m[17], gol_l[17], gol_i[17];
     uint8_t flush[8][9][6];          // pad_word | pad_len << 4
-    uint8_t lut_mag[4][256];         // [subband][neighbour mask] -> context of a category-0 pixel (icer_config.c:26-45)
-    uint8_t lut_sign[2][16];         // [subband == HL][negative-neighbour mask] -> sign context | predicted sign << 7 (:47-67)
+    uint8_t lut[6][256];             // rows 0..3 [subband][neighbour mask] -> context of a category-0 pixel (icer_config.c:26-45);
+                                     // rows 4, 5 [subband == HL][mask of the NEGATIVE significant neighbours] -> sign context | predicted sign << 7
+                                     // (:47-67; only the four direct neighbours count, the diagonal bits of the mask are ignored)
 };
 // neighbour mask bits: 0,1,2 = row above (left, mid, right); 3 = left; 4 = right; 5,6,7 = row below (left, mid, right)
 #define ICER_NM_HV 0x5Au           /* mid-above, left, right, mid-below */
@@ -100,6 +107,12 @@ ICER_HD int bin_cached(const CoreTables &T, uint32_t zz, uint32_t tot, int guess
     const uint32_t lhs = zz << 16;
     const CoreTables::Cut c = T.cut[guess];
     if (lhs >= tot * c.lo && lhs < tot * c.hi) return guess;
+#if ICER_BIN_PROBE
+    // a context that leaves its bin almost always lands in a neighbouring one: one more probe before the full search
+    const int nbr = lhs >= tot * c.hi ? guess + 1 : guess - 1;     // in range: the sentinels 65537 / 0 never fail
+    const CoreTables::Cut c2 = T.cut[nbr];
+    if (lhs >= tot * c2.lo && lhs < tot * c2.hi) return nbr;
+#endif
     return bin_of(T, zz, tot);
 }
 #define ICER_CNT_Z(zt) (((zt) >> 16) & 0x7FFu)
@@ -118,9 +131,10 @@ ICER_HD uint32_t zeros_in_same_bin(const CoreTables &T, int bin, uint32_t z, uin
 
 ICER_HD uint32_t dilate3(uint32_t x) { return x | (x << 1) | (x >> 1); }
 
-// magnitude context from the neighbour mask (icer_context_modeller.c:355-391)
-ICER_HD int mag_ctx(const CoreTables &T, int sb, int cat, uint32_t nm) {
-    if (cat == 0) return T.lut_mag[sb][nm];
+// context of a decision from its table entry (category 0 and sign decisions), the neighbour mask (category 1) or nothing
+// (category 2); icer_context_modeller.c:355-391
+ICER_HD int ctx_of(int cat, uint32_t e, uint32_t nm) {
+    if (cat == 0) return (int) (e & 0x7Fu);
     if (cat == 1) return (nm & ICER_NM_HV) ? 10 : 9;
     return 11;
 }
@@ -253,6 +267,7 @@ struct EncLane {
         int kind = 0;                                       // 1: magnitude decision, 2: ... of a quiet pixel, 4: ... whose one starts the sign decision; 8: sign decision
         int bin = 0, ctx = -1;
         uint32_t bit = 0, code = 0, nb = 0;
+        bool decide = false;
         if (phase == 0) {
             const uint32_t nqs = k.nq >> col;               // bit 0: this column; never zero (the bits above the chunk are set)
             const uint32_t r = fz_left ? (uint32_t) ctz32(nqs) : 0u;
@@ -270,24 +285,21 @@ struct EncLane {
                 fz_run = 0; fz_left = 0;
                 if (kk >= T.gol_m[bin]) { op = OP_DONE; code = 1; nb = 1; }
                 else bst[bin * STRIDE] = (uint16_t) kk;
-            } else {
-                const int selfp = (int) ((k.bP >> col) & 1u);
-                const int cat = selfp ? 1 + (int) ((k.b2 >> col) & 1u) + (int) ((k.b3 >> col) & 1u) : 0;     // icer_context_modeller.c:631-634
-                bit = (k.bB >> col) & 1u;
-                kind = 1 | ((nqs & 1u) ? 0 : 2) | ((cat == 0 && bit) ? 4 : 0);
-                if (cat != 3) {                             // category 3: p(0) = 1/2 -> uncoded bin, no context
-                    const int s = col - 1;
-                    const uint32_t nm = ((k.aS >> s) & 7u) | (((k.bSc >> s) & 1u) << 3) | (((k.bP >> s) & 4u) << 2) | (((k.cP >> s) & 7u) << 5);
-                    ctx = mag_ctx(T, sb, cat, nm);
-                }
-            }
-        } else {
-            const uint32_t m = ((k.nsA >> col) & 1u) | (((k.nsBc >> (col - 1)) & 1u) << 1) | (((k.nsBp >> (col + 1)) & 1u) << 2) |
-                               (((k.nsC >> col) & 1u) << 3);
-            const uint32_t e = T.lut_sign[sb == 1][m];
-            ctx = (int) (e & 0x7Fu);
-            bit = ((e >> 7) ^ (k.bN >> col)) & 1u;
-            kind = 8;
+            } else decide = true;
+        } else decide = true;
+        if (decide) {
+            // Magnitude and sign decisions share ONE set-up: the same neighbour-mask extraction runs on the significance words (magnitude)
+            // or on the "negative and significant" words (sign), and one table look-up gives the context (and the predicted sign).
+            const bool sg = phase != 0;
+            const uint32_t wA = sg ? k.nsA : k.aS, wB0 = sg ? k.nsBc : k.bSc, wB2 = sg ? k.nsBp : k.bP, wC = sg ? k.nsC : k.cP;
+            const int s = col - 1;
+            const uint32_t nm = ((wA >> s) & 7u) | (((wB0 >> s) & 1u) << 3) | (((wB2 >> s) & 4u) << 2) | (((wC >> s) & 7u) << 5);
+            const uint32_t e = T.lut[sg ? 4 + (sb == 1) : sb][nm];
+            const int selfp = sg ? 0 : (int) ((k.bP >> col) & 1u);
+            const int cat = selfp ? 1 + (int) ((k.b2 >> col) & 1u) + (int) ((k.b3 >> col) & 1u) : 0;     // icer_context_modeller.c:631-634
+            bit = (((sg ? k.bN : k.bB) >> col) ^ (e >> 7)) & 1u;       // sign: agreement with the prediction; magnitude entries have no bit 7
+            if (cat != 3) ctx = ctx_of(cat, e, nm);                     // category 3: p(0) = 1/2 -> uncoded bin, no context
+            kind = sg ? 8 : (1 | (((k.nq >> col) & 1u) ? 0 : 2) | ((cat == 0 && bit) ? 4 : 0));
         }
         ICER_CONVERGE(lanes);       // ---- all lanes meet here ----
         if (kind) {
@@ -301,13 +313,23 @@ struct EncLane {
                 if (inv) zz = tot - zz;
                 bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
             }
+#if ICER_INLINE_FLUSH
+            if (window_full_for(bin)) {
+                // window full: the oldest codeword is force-completed first (icer_encoding.c:59-64), then this decision goes on
+                uint32_t fnb;
+                const int fb = oldest;
+                const uint32_t fcode = forced_word(fb, fnb);
+                complete(fb, fcode, fnb);
+            }
+            if ((kind & 2) && ctx >= 0 && !inv && bin > 7) {
+#else
             if (window_full_for(bin)) {
                 // window full: force-complete the oldest codeword (icer_encoding.c:59-64); the decision is retried in the next step
-                // (doing both in one step needs a second completion site and measured slower: k_encode 20.0 -> 23.2 ms on config 2)
                 bin = oldest;
                 code = forced_word(bin, nb);
                 op = OP_DONE;
             } else if ((kind & 2) && ctx >= 0 && !inv && bin > 7) {
+#endif
                 // enter the quiet fast path: this and the following quiet pixels only bump counters
                 open_bin(bin);
                 const uint32_t n1 = (uint32_t) T.gol_m[bin] - bst[bin * STRIDE];
@@ -512,7 +534,7 @@ struct DecLane {
         int bin = 0, ctx = -1;
         int kind = -1;                                          // -1: nothing to decode in this step, 0: sign decision, 2: magnitude decision of a category-0 pixel (a one starts the sign decision), 3: other magnitude decision
         uint32_t z = 0, tot = 0, e = 0;
-        bool inv = false, quiet = false;
+        bool inv = false, quiet = false, decide = false;
         if (phase == 0) {
             const uint32_t nqs = (k.nq | (k.bB << 1)) >> col;
             const uint32_t r = fz_left ? (uint32_t) ctz32(nqs) : 0u;
@@ -530,23 +552,21 @@ struct DecLane {
                     fz_run = 0; fz_left = 0;
                 }
                 quiet = !(nqs & 1u);
-                const int selfp = (int) ((k.bP >> col) & 1u);
-                const int cat = selfp ? 1 + (int) ((k.b2 >> col) & 1u) + (int) ((k.b3 >> col) & 1u) : 0;
-                if (cat != 3) {
-                    const int s = col - 1;
-                    const uint32_t bSc = k.bP | k.bB;
-                    const uint32_t nm = ((k.aS >> s) & 7u) | (((bSc >> s) & 1u) << 3) | (((k.bP >> s) & 4u) << 2) | (((k.cP >> s) & 7u) << 5);
-                    ctx = mag_ctx(T, sb, cat, nm);
-                }
-                kind = (cat == 0) ? 2 : 3;
+                decide = true;
             }
-        } else {
-            const uint32_t nsBc = (k.bNp | k.bNn) & (k.bP | k.bB), nsBp = k.bNp & k.bP;
-            const uint32_t m = ((k.nsA >> col) & 1u) | (((nsBc >> (col - 1)) & 1u) << 1) | (((nsBp >> (col + 1)) & 1u) << 2) |
-                               (((k.nsC >> col) & 1u) << 3);
-            e = T.lut_sign[sb == 1][m];
-            ctx = (int) (e & 0x7Fu);
-            kind = 0;
+        } else decide = true;
+        if (decide) {
+            // one set-up for magnitude and sign decisions (see EncLane::step)
+            const bool sg = phase != 0;
+            const uint32_t bSc = k.bP | k.bB;
+            const uint32_t wA = sg ? k.nsA : k.aS, wB0 = sg ? ((k.bNp | k.bNn) & bSc) : bSc, wB2 = sg ? (k.bNp & k.bP) : k.bP, wC = sg ? k.nsC : k.cP;
+            const int s = col - 1;
+            const uint32_t nm = ((wA >> s) & 7u) | (((wB0 >> s) & 1u) << 3) | (((wB2 >> s) & 4u) << 2) | (((wC >> s) & 7u) << 5);
+            e = T.lut[sg ? 4 + (sb == 1) : sb][nm];
+            const int selfp = sg ? 0 : (int) ((k.bP >> col) & 1u);
+            const int cat = selfp ? 1 + (int) ((k.b2 >> col) & 1u) + (int) ((k.b3 >> col) & 1u) : 0;
+            if (cat != 3) ctx = ctx_of(cat, e, nm);
+            kind = sg ? 0 : ((cat == 0) ? 2 : 3);
         }
         ICER_CONVERGE(lanes);       // ---- all lanes meet here ----
         int dep = 0;

@@ -106,15 +106,16 @@ inline void fill_core_tables(icer_core::CoreTables &d, const HostTables &h, bool
             int hh = ((nm >> 3) & 1) + ((nm >> 4) & 1), vv = ((nm >> 1) & 1) + ((nm >> 6) & 1);
             const int dd = (nm & 1) + ((nm >> 2) & 1) + ((nm >> 5) & 1) + ((nm >> 7) & 1);
             if (sb == 1) { const int t = hh; hh = vv; vv = t; }
-            d.lut_mag[sb][nm] = sb == 3 ? kCtxHH[(hh + vv) * 5 + dd] : kCtxHV[(hh * 3 + vv) * 5 + dd];
+            d.lut[sb][nm] = sb == 3 ? kCtxHH[(hh + vv) * 5 + dd] : kCtxHV[(hh * 3 + vv) * 5 + dd];
         }
-    // negative-neighbour mask (bit 0 above, 1 left, 2 right, 3 below) -> sign context | prediction << 7 (:404-428); get_sign is -1 for a
-    // negative significant neighbour and 0 otherwise, so only the indices 0..2 of the 5x5 tables are reachable
+    // mask of the negative significant neighbours (same bit positions; only above = bit 1, left = 3, right = 4, below = 6 count) -> sign
+    // context | prediction << 7 (:404-428); get_sign is -1 for a negative significant neighbour and 0 otherwise, so only the indices
+    // 0..2 of the 5x5 tables are reachable
     for (int sw = 0; sw < 2; sw++)
-        for (int m = 0; m < 16; m++) {
-            int shh = 2 - ((m >> 1) & 1) - ((m >> 2) & 1), svv = 2 - (m & 1) - ((m >> 3) & 1);
+        for (int m = 0; m < 256; m++) {
+            int shh = 2 - ((m >> 3) & 1) - ((m >> 4) & 1), svv = 2 - ((m >> 1) & 1) - ((m >> 6) & 1);
             if (sw) { const int t = shh; shh = svv; svv = t; }
-            d.lut_sign[sw][m] = (uint8_t) (kCtxSign[shh * 5 + svv] | (kSignPred[shh * 5 + svv] << 7));
+            d.lut[4 + sw][m] = (uint8_t) (kCtxSign[shh * 5 + svv] | (kSignPred[shh * 5 + svv] << 7));
         }
 }
 }  // namespace icer_tables
