@@ -39,9 +39,6 @@
 #ifndef ICER_BIN_PROBE
 #define ICER_BIN_PROBE 1          /* one probe of the neighbouring bin before the full search: k_encode 19.4 -> 18.6, k_decode 18.6 -> 18.0 ms */
 #endif
-#ifndef ICER_INLINE_FLUSH
-#define ICER_INLINE_FLUSH 0
-#endif
 #define ICER_CHUNK 30          /* pixels per bit-slice word */
 
 namespace icer_core {
@@ -313,23 +310,12 @@ struct EncLane {
                 if (inv) zz = tot - zz;
                 bin = bin_cached(T, zz, tot, ICER_CNT_BIN(zt));
             }
-#if ICER_INLINE_FLUSH
-            if (window_full_for(bin)) {
-                // window full: the oldest codeword is force-completed first (icer_encoding.c:59-64), then this decision goes on
-                uint32_t fnb;
-                const int fb = oldest;
-                const uint32_t fcode = forced_word(fb, fnb);
-                complete(fb, fcode, fnb);
-            }
-            if ((kind & 2) && ctx >= 0 && !inv && bin > 7) {
-#else
             if (window_full_for(bin)) {
                 // window full: force-complete the oldest codeword (icer_encoding.c:59-64); the decision is retried in the next step
                 bin = oldest;
                 code = forced_word(bin, nb);
                 op = OP_DONE;
             } else if ((kind & 2) && ctx >= 0 && !inv && bin > 7) {
-#endif
                 // enter the quiet fast path: this and the following quiet pixels only bump counters
                 open_bin(bin);
                 const uint32_t n1 = (uint32_t) T.gol_m[bin] - bst[bin * STRIDE];
