@@ -608,7 +608,7 @@ def main():
     ap.add_argument("--workload", default=None, help="one of %s, or 'all'; default: c2 as the headline + the other BASELINE configs under `configs`" % ", ".join(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="override frames per GPU of the headline workload")
     ap.add_argument("--single-process", action="store_true", help="drive all --gpus devices from this one process through icer_b200_*_batch_multi")
-    ap.add_argument("--e2e-workers", type=int, default=3)
+    ap.add_argument("--e2e-workers", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--watchdog", type=float, default=1500.0, help="dump every Python stack and exit if the run takes longer than this many seconds")
