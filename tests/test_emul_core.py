@@ -121,3 +121,20 @@ def test_lane_machines_on_a_transformed_frame(emul, orc):
         seg = np.ascontiguousarray(co[y:y + h, x:x + w])
         for lsb in range(9):
             check_plane(emul, orc, seg, sb, lsb)
+
+
+def test_lane_machines_random_segments_property(emul, orc):
+    """hypothesis: random segment shapes (incl. widths around the 30-pixel chunk size), densities, sub-band kinds and planes"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(w=st.integers(1, 125), h=st.integers(1, 9), sb=st.integers(0, 3), lsb=st.integers(0, 14), seed=st.integers(0, 2 ** 31 - 1),
+           density=st.sampled_from([0.0, 0.02, 0.2, 0.7, 1.0]), maxbits=st.integers(1, 15))
+    def run(w, h, sb, lsb, seed, density, maxbits):
+        rng = np.random.default_rng(seed)
+        mag = (rng.random((h, w)) < density) * rng.integers(0, 1 << maxbits, (h, w))
+        sign = rng.integers(0, 2, (h, w)) * (mag != 0)
+        seg = (mag | (sign << 15)).astype(np.uint16)
+        check_plane(emul, orc, seg, sb, lsb)
+
+    run()
